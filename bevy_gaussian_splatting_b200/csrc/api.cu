@@ -1,0 +1,507 @@
+// api.cu -- the extern "C" boundary of libbgs (include/bgs.h): contexts, clouds, the per-view
+// frame (stage orchestration on one CUDA stream), parity/debug hooks, stage timing.
+//
+// No PyTorch, no wgpu, no CPU fallback: every stage is a hand-written sm_100a kernel.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+
+namespace bgs {
+// keygen.cu
+void launch_keygen(const float4* pos, uint32_t n, const FrameConsts& fc, int sort_all, uint32_t* keys_out,
+                   uint32_t* ids_out, uint32_t* status, FrameCounters* ctr, cudaStream_t stream);
+uint32_t keygen_num_tiles(uint32_t n);
+void launch_culled_flags(const float4* pos, uint32_t n, const FrameConsts& fc, uint32_t* flags, cudaStream_t stream);
+// radix.cu
+uint32_t radix_num_tiles(uint32_t capacity);
+void launch_radix_hist(const uint32_t* keys, const uint32_t* n_ptr, uint32_t capacity, int passes, uint32_t* hist,
+                       int sm_count, cudaStream_t stream);
+void launch_onesweep(const uint32_t* keys_in, const uint32_t* vals_in, uint32_t* keys_out, uint32_t* vals_out,
+                     const uint32_t* n_ptr, uint32_t capacity, const uint32_t* hist, uint32_t* status,
+                     uint32_t* tile_ctr, int shift, int sm_count, cudaStream_t stream);
+// project.cu
+void launch_project(bool f16, const float4* pos, const void* sh, const void* rot, const void* so,
+                    const uint32_t* sorted_ids, const FrameCounters* ctr, const FrameConsts& fc, SplatRec* recs,
+                    uint32_t n_upper, int sm_count, cudaStream_t stream);
+// bin.cu
+void launch_bin_emit(const SplatRec* recs, FrameCounters* ctr, uint32_t* status, int tiles_x, uint32_t capacity,
+                     uint32_t* pair_keys, uint32_t* pair_vals, uint32_t n_upper, int sm_count, cudaStream_t stream);
+uint32_t bin_num_tiles(uint32_t n);
+void launch_tile_ranges(const uint32_t* sorted_tile_ids, const FrameCounters* ctr, uint2* ranges, uint32_t capacity,
+                        int sm_count, cudaStream_t stream);
+// raster.cu
+void launch_raster(const SplatRec* recs, const uint32_t* tile_entries, const uint2* ranges, int W, int H, int tiles_x,
+                   int tiles_y, void* out, uint32_t format, cudaStream_t stream);
+}  // namespace bgs
+
+using namespace bgs;
+
+struct bgs_cloud {
+    bgs_context* ctx;
+    uint32_t n;
+    bool f16;
+    float4* pos;      // n * 16 B
+    void* sh;         // f32: n * 192 B; f16: n * 96 B
+    void* rot;        // f32: n * 16 B (w,x,y,z); f16: n * 16 B packed rotation+scale+opacity
+    void* so;         // f32: n * 16 B; f16: unused
+};
+
+struct bgs_context {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[6] = {};
+    char err[512] = {0};
+
+    // scratch sized by the cloud (grow-only)
+    uint32_t cap_n = 0;
+    uint32_t* keys[2] = {nullptr, nullptr};
+    uint32_t* vals[2] = {nullptr, nullptr};
+    SplatRec* recs = nullptr;
+    // scratch sized by the pair capacity (grow-only)
+    uint32_t cap_pairs = 0;
+    uint32_t* pkeys[2] = {nullptr, nullptr};
+    uint32_t* pvals[2] = {nullptr, nullptr};
+    // zeroed-per-frame arena: counters | hist | keygen status | bin status | ranges | radix status
+    uint8_t* arena = nullptr;
+    size_t arena_bytes = 0;
+    uint32_t arena_n = 0, arena_pairs = 0, arena_tiles = 0;
+    FrameCounters* ctr = nullptr;
+    uint32_t* hist = nullptr;          // [8][256]: depth passes 0..3, pair passes 4..7
+    uint32_t* status_keygen = nullptr;
+    uint32_t* status_bin = nullptr;
+    uint2* ranges = nullptr;
+    uint32_t* status_depth = nullptr;  // [4][tiles(n)][256]
+    uint32_t* status_pairs = nullptr;  // [4][tiles(cap_pairs)][256]
+    // frame
+    void* frame = nullptr;
+    size_t frame_bytes = 0;
+    const void* last_frame = nullptr;
+    FrameCounters* h_ctr = nullptr;    // pinned
+
+    // last-frame facts (for the debug hooks)
+    bool have_frame = false;
+    const bgs_cloud* last_cloud = nullptr;
+    FrameConsts last_fc;
+    bool last_sort_all = false;
+    int depth_result = 0, pair_result = 0;   // which ping-pong buffer holds the sorted result
+    bgs_frame_stats stats = {};
+    float stage_us[6] = {0, 0, 0, 0, 0, 0};
+    uint32_t launches = 0;
+};
+
+namespace {
+
+bgs_status fail(bgs_context* ctx, bgs_status st, const char* fmt, ...) {
+    if (ctx) {
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(ctx->err, sizeof(ctx->err), fmt, ap);
+        va_end(ap);
+    }
+    return st;
+}
+
+#define CU(ctx, call)                                                                                   \
+    do {                                                                                                \
+        cudaError_t e_ = (call);                                                                        \
+        if (e_ != cudaSuccess)                                                                          \
+            return fail(ctx, e_ == cudaErrorMemoryAllocation ? BGS_ENOMEM : BGS_ECUDA, "%s: %s", #call, \
+                        cudaGetErrorString(e_));                                                        \
+    } while (0)
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+int pair_passes(uint32_t num_tiles) {
+    int bits = 1;
+    while ((1u << bits) < num_tiles) ++bits;
+    return (bits + 7) / 8;
+}
+
+bgs_status ensure_cloud_scratch(bgs_context* c, uint32_t n) {
+    if (n <= c->cap_n) return BGS_OK;
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(c->keys[i]); cudaFree(c->vals[i]);
+        c->keys[i] = c->vals[i] = nullptr;
+    }
+    cudaFree(c->recs); c->recs = nullptr;
+    c->cap_n = 0;
+    for (int i = 0; i < 2; ++i) {
+        CU(c, cudaMalloc(&c->keys[i], (size_t)n * 4));
+        CU(c, cudaMalloc(&c->vals[i], (size_t)n * 4));
+    }
+    CU(c, cudaMalloc(&c->recs, (size_t)n * sizeof(SplatRec)));
+    c->cap_n = n;
+    return BGS_OK;
+}
+
+bgs_status ensure_pair_scratch(bgs_context* c, uint32_t pairs) {
+    if (pairs <= c->cap_pairs) return BGS_OK;
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(c->pkeys[i]); cudaFree(c->pvals[i]);
+        c->pkeys[i] = c->pvals[i] = nullptr;
+    }
+    c->cap_pairs = 0;
+    for (int i = 0; i < 2; ++i) {
+        CU(c, cudaMalloc(&c->pkeys[i], (size_t)pairs * 4));
+        CU(c, cudaMalloc(&c->pvals[i], (size_t)pairs * 4));
+    }
+    c->cap_pairs = pairs;
+    return BGS_OK;
+}
+
+bgs_status ensure_arena(bgs_context* c, uint32_t n, uint32_t pairs, uint32_t tiles) {
+    if (c->arena && n <= c->arena_n && pairs <= c->arena_pairs && tiles <= c->arena_tiles) return BGS_OK;
+    n = n > c->arena_n ? n : c->arena_n;
+    pairs = pairs > c->arena_pairs ? pairs : c->arena_pairs;
+    tiles = tiles > c->arena_tiles ? tiles : c->arena_tiles;
+    cudaFree(c->arena); c->arena = nullptr;
+    size_t off = 0;
+    const size_t o_ctr = off; off = align_up(off + sizeof(FrameCounters), 256);
+    const size_t o_hist = off; off = align_up(off + 8 * 256 * 4, 256);
+    const size_t o_skg = off; off = align_up(off + (size_t)keygen_num_tiles(n) * 4, 256);
+    const size_t o_sbin = off; off = align_up(off + (size_t)bin_num_tiles(n) * 4, 256);
+    const size_t o_rng = off; off = align_up(off + (size_t)tiles * 8, 256);
+    const size_t o_sd = off; off = align_up(off + (size_t)4 * radix_num_tiles(n) * 256 * 4, 256);
+    const size_t o_sp = off; off = align_up(off + (size_t)4 * radix_num_tiles(pairs) * 256 * 4, 256);
+    CU(c, cudaMalloc(&c->arena, off));
+    c->arena_bytes = off;
+    c->ctr = reinterpret_cast<FrameCounters*>(c->arena + o_ctr);
+    c->hist = reinterpret_cast<uint32_t*>(c->arena + o_hist);
+    c->status_keygen = reinterpret_cast<uint32_t*>(c->arena + o_skg);
+    c->status_bin = reinterpret_cast<uint32_t*>(c->arena + o_sbin);
+    c->ranges = reinterpret_cast<uint2*>(c->arena + o_rng);
+    c->status_depth = reinterpret_cast<uint32_t*>(c->arena + o_sd);
+    c->status_pairs = reinterpret_cast<uint32_t*>(c->arena + o_sp);
+    c->arena_n = n; c->arena_pairs = pairs; c->arena_tiles = tiles;
+    return BGS_OK;
+}
+
+bgs_status ensure_frame(bgs_context* c, size_t bytes) {
+    if (bytes <= c->frame_bytes) return BGS_OK;
+    cudaFree(c->frame); c->frame = nullptr; c->frame_bytes = 0;
+    CU(c, cudaMalloc(&c->frame, bytes));
+    c->frame_bytes = bytes;
+    return BGS_OK;
+}
+
+size_t format_bpp(uint32_t f) { return f == BGS_FORMAT_RGBA32F ? 16 : (f == BGS_FORMAT_RGBA16F ? 8 : 4); }
+
+}  // namespace
+
+extern "C" {
+
+bgs_status bgs_context_create(int cuda_device, bgs_context** out) {
+    if (!out) return BGS_EINVAL;
+    *out = nullptr;
+    bgs_context* c = new (std::nothrow) bgs_context();
+    if (!c) return BGS_ENOMEM;
+    c->device = cuda_device;
+    cudaError_t e = cudaSetDevice(cuda_device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 6 && e == cudaSuccess; ++i) e = cudaEventCreate(&c->ev[i]);
+    if (e == cudaSuccess) e = cudaMallocHost(&c->h_ctr, sizeof(FrameCounters));
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, cuda_device);
+    if (e != cudaSuccess) {
+        // no CUDA device / driver: the product has no CPU path
+        fprintf(stderr, "libbgs: CUDA initialisation failed on device %d: %s\n", cuda_device, cudaGetErrorString(e));
+        bgs_context_destroy(c);
+        return BGS_ECUDA;
+    }
+    *out = c;
+    return BGS_OK;
+}
+
+void bgs_context_destroy(bgs_context* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(c->keys[i]); cudaFree(c->vals[i]); cudaFree(c->pkeys[i]); cudaFree(c->pvals[i]);
+    }
+    cudaFree(c->recs); cudaFree(c->arena); cudaFree(c->frame);
+    if (c->h_ctr) cudaFreeHost(c->h_ctr);
+    for (int i = 0; i < 6; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+static bgs_status upload_common(bgs_context* ctx, uint32_t n, bool f16, const float* pos_vis, const void* sh,
+                                const void* rot, const void* so, bgs_cloud** out) {
+    if (!ctx || !out) return BGS_EINVAL;
+    *out = nullptr;
+    if (!pos_vis || !sh || !rot || (!f16 && !so)) return fail(ctx, BGS_EINVAL, "cloud upload: null plane pointer");
+    if (n == 0 || n >= (1u << 30)) return fail(ctx, BGS_EINVAL, "cloud upload: n must be in [1, 2^30)");
+    CU(ctx, cudaSetDevice(ctx->device));
+    bgs_cloud* cl = new (std::nothrow) bgs_cloud();
+    if (!cl) return BGS_ENOMEM;
+    cl->ctx = ctx; cl->n = n; cl->f16 = f16;
+    cl->pos = nullptr; cl->sh = nullptr; cl->rot = nullptr; cl->so = nullptr;
+    const size_t sh_bytes = (size_t)n * (f16 ? 96 : 192);
+    cudaError_t e = cudaMalloc(&cl->pos, (size_t)n * 16);
+    if (e == cudaSuccess) e = cudaMalloc(&cl->sh, sh_bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&cl->rot, (size_t)n * 16);
+    if (e == cudaSuccess && !f16) e = cudaMalloc(&cl->so, (size_t)n * 16);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(cl->pos, pos_vis, (size_t)n * 16, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(cl->sh, sh, sh_bytes, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(cl->rot, rot, (size_t)n * 16, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess && !f16) e = cudaMemcpyAsync(cl->so, so, (size_t)n * 16, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        bgs_cloud_destroy(cl);
+        return fail(ctx, e == cudaErrorMemoryAllocation ? BGS_ENOMEM : BGS_ECUDA, "cloud upload: %s", cudaGetErrorString(e));
+    }
+    *out = cl;
+    return BGS_OK;
+}
+
+bgs_status bgs_cloud_upload_f32(bgs_context* ctx, uint32_t n, const float* pos_vis, const float* sh,
+                                const float* rot_wxyz, const float* scale_opacity, bgs_cloud** out) {
+    return upload_common(ctx, n, false, pos_vis, sh, rot_wxyz, scale_opacity, out);
+}
+
+bgs_status bgs_cloud_upload_f16(bgs_context* ctx, uint32_t n, const float* pos_vis, const uint32_t* sh_packed,
+                                const uint32_t* rot_scale_opacity, bgs_cloud** out) {
+    return upload_common(ctx, n, true, pos_vis, sh_packed, rot_scale_opacity, nullptr, out);
+}
+
+void bgs_cloud_destroy(bgs_cloud* cl) {
+    if (!cl) return;
+    if (cl->ctx) {
+        cudaSetDevice(cl->ctx->device);
+        if (cl->ctx->last_cloud == cl) { cl->ctx->last_cloud = nullptr; cl->ctx->have_frame = false; }
+    }
+    cudaFree(cl->pos); cudaFree(cl->sh); cudaFree(cl->rot); cudaFree(cl->so);
+    delete cl;
+}
+
+bgs_status bgs_render(bgs_context* c, const bgs_cloud* cloud, const bgs_view* view, const bgs_cloud_uniform* uni,
+                      const bgs_settings* st, void* out_rgba, uint32_t out_format, int out_is_device_ptr) {
+    if (!c) return BGS_EINVAL;
+    // not-ready inputs map to the reference's silent skip-frame (radix.rs:645-658, mod.rs:1533-1539)
+    if (!cloud || !view || !uni || !st) return fail(c, BGS_NOT_READY, "render: cloud/view/uniform/settings not ready");
+    if (cloud->ctx != c) return fail(c, BGS_EINVAL, "render: cloud belongs to another context");
+    if (out_format > BGS_FORMAT_RGBA32F) return fail(c, BGS_EINVAL, "render: unknown out_format %u", out_format);
+    if (st->radix_sort_depth_bits != 16 && st->radix_sort_depth_bits != 24 && st->radix_sort_depth_bits != 32)
+        return fail(c, BGS_EINVAL, "render: radix_sort_depth_bits must be 16, 24 or 32");
+    if (st->gaussian_mode != BGS_GAUSSIAN_3D) return fail(c, BGS_EINVAL, "render: gaussian_mode %u not supported yet", st->gaussian_mode);
+    if (st->aabb) return fail(c, BGS_EINVAL, "render: aabb (USE_AABB) not supported yet");
+    if (st->rasterize_mode != BGS_RASTERIZE_COLOR && st->rasterize_mode != BGS_RASTERIZE_NORMAL)
+        return fail(c, BGS_EINVAL, "render: rasterize_mode %u not supported yet", st->rasterize_mode);
+    if (st->draw_mode > BGS_DRAW_HIGHLIGHT_SELECTED) return fail(c, BGS_EINVAL, "render: bad draw_mode");
+    const int W = (int)view->viewport[2], H = (int)view->viewport[3];
+    if (W <= 0 || H <= 0 || W > 65535 || H > 65535) return fail(c, BGS_EINVAL, "render: viewport %dx%d out of range", W, H);
+    CU(c, cudaSetDevice(c->device));
+
+    const uint32_t n = cloud->n;
+    const int tiles_x = (W + TILE_PX - 1) / TILE_PX, tiles_y = (H + TILE_PX - 1) / TILE_PX;
+    const uint32_t num_tiles = (uint32_t)tiles_x * (uint32_t)tiles_y;
+    const int depth_passes = (int)st->radix_sort_depth_bits / 8;
+    const int tile_passes = pair_passes(num_tiles);
+    const bool sort_all = (st->flags & BGS_FLAG_SORT_ALL) != 0;
+
+    FrameConsts fc;
+    memcpy(fc.model, uni->transform, 64);
+    memcpy(fc.view_from_world, view->view_from_world, 64);
+    memcpy(fc.clip_from_world, view->clip_from_world, 64);
+    memcpy(fc.cam, view->world_position, 12);
+    fc.W = view->viewport[2]; fc.H = view->viewport[3];
+    fc.p00 = view->clip_from_view[0]; fc.p11 = view->clip_from_view[5];
+    fc.global_opacity = uni->global_opacity; fc.global_scale = uni->global_scale;
+    fc.color_space = uni->color_space;
+    fc.key_shift = 32u - st->radix_sort_depth_bits;
+    fc.gaussian_mode = st->gaussian_mode; fc.rasterize_mode = st->rasterize_mode; fc.aabb = st->aabb;
+    fc.adaptive = st->opacity_adaptive_radius; fc.draw_mode = st->draw_mode;
+    fc.Wi = W; fc.Hi = H; fc.tiles_x = tiles_x; fc.tiles_y = tiles_y;
+
+    bgs_status s = ensure_cloud_scratch(c, n);
+    if (s != BGS_OK) return s;
+    if (c->cap_pairs == 0) {
+        uint32_t init = n < (1u << 20) ? (1u << 20) : n;   // first guess; grows on demand
+        s = ensure_pair_scratch(c, init);
+        if (s != BGS_OK) return s;
+    }
+    const size_t frame_bytes = (size_t)W * H * format_bpp(out_format);
+    void* target = c->frame;
+    if (out_rgba && out_is_device_ptr) target = out_rgba;
+    else {
+        s = ensure_frame(c, frame_bytes);
+        if (s != BGS_OK) return s;
+        target = c->frame;
+    }
+
+    for (int attempt = 0; attempt < 4; ++attempt) {
+        s = ensure_arena(c, n, c->cap_pairs, num_tiles);
+        if (s != BGS_OK) return s;
+        cudaStream_t q = c->stream;
+        uint32_t launches = 0;
+        CU(c, cudaMemsetAsync(c->arena, 0, c->arena_bytes, q));
+        CU(c, cudaEventRecord(c->ev[0], q));
+        // ---- stage 1: key-gen (+ stable compaction of the visible set)
+        launch_keygen(cloud->pos, n, fc, sort_all ? 1 : 0, c->keys[0], c->vals[0], c->status_keygen, c->ctr, q);
+        ++launches;
+        CU(c, cudaEventRecord(c->ev[1], q));
+        // ---- stage 2: depth radix sort (P = depth_bits / 8 onesweep passes)
+        launch_radix_hist(c->keys[0], &c->ctr->n_sort, n, depth_passes, c->hist, c->sm_count, q);
+        ++launches;
+        int cur = 0;
+        const size_t depth_status_stride = (size_t)radix_num_tiles(c->arena_n) * 256;
+        for (int p = 0; p < depth_passes; ++p) {
+            launch_onesweep(c->keys[cur], c->vals[cur], c->keys[cur ^ 1], c->vals[cur ^ 1], &c->ctr->n_sort, n,
+                            c->hist + p * 256, c->status_depth + p * depth_status_stride, &c->ctr->tile_ctr[1 + p],
+                            8 * p, c->sm_count, q);
+            ++launches;
+            cur ^= 1;
+        }
+        c->depth_result = cur;
+        CU(c, cudaEventRecord(c->ev[2], q));
+        // ---- stage 3: projection + colour, front-to-back rank order
+        launch_project(cloud->f16, cloud->pos, cloud->sh, cloud->rot, cloud->so, c->vals[cur], c->ctr, fc, c->recs, n,
+                       c->sm_count, q);
+        ++launches;
+        CU(c, cudaEventRecord(c->ev[3], q));
+        // ---- stage 4: tile binning -> stable tile-id sort -> ranges
+        launch_bin_emit(c->recs, c->ctr, c->status_bin, tiles_x, c->cap_pairs, c->pkeys[0], c->pvals[0], n, c->sm_count, q);
+        ++launches;
+        launch_radix_hist(c->pkeys[0], &c->ctr->n_pairs, c->cap_pairs, tile_passes, c->hist + 4 * 256, c->sm_count, q);
+        ++launches;
+        int pcur = 0;
+        const size_t pair_status_stride = (size_t)radix_num_tiles(c->arena_pairs) * 256;
+        for (int p = 0; p < tile_passes; ++p) {
+            launch_onesweep(c->pkeys[pcur], c->pvals[pcur], c->pkeys[pcur ^ 1], c->pvals[pcur ^ 1], &c->ctr->n_pairs,
+                            c->cap_pairs, c->hist + (4 + p) * 256, c->status_pairs + p * pair_status_stride,
+                            &c->ctr->tile_ctr[6 + p], 8 * p, c->sm_count, q);
+            ++launches;
+            pcur ^= 1;
+        }
+        c->pair_result = pcur;
+        launch_tile_ranges(c->pkeys[pcur], c->ctr, c->ranges, c->cap_pairs, c->sm_count, q);
+        ++launches;
+        CU(c, cudaEventRecord(c->ev[4], q));
+        // ---- stage 5: per-tile front-to-back blend
+        launch_raster(c->recs, c->pvals[pcur], c->ranges, W, H, tiles_x, tiles_y, target, out_format, q);
+        ++launches;
+        CU(c, cudaEventRecord(c->ev[5], q));
+        CU(c, cudaMemcpyAsync(c->h_ctr, c->ctr, sizeof(FrameCounters), cudaMemcpyDeviceToHost, q));
+        if (out_rgba && !out_is_device_ptr)
+            CU(c, cudaMemcpyAsync(out_rgba, target, frame_bytes, cudaMemcpyDeviceToHost, q));
+        CU(c, cudaStreamSynchronize(q));
+        CU(c, cudaGetLastError());
+        c->launches = launches;
+        if (c->h_ctr->n_pairs_needed > c->cap_pairs) {
+            // the pair list did not fit: grow (x1.25 head-room) and redo the frame
+            uint64_t want = (uint64_t)c->h_ctr->n_pairs_needed + c->h_ctr->n_pairs_needed / 4 + 1024;
+            if (want >= (1ull << 30)) want = (1ull << 30) - 1;
+            if (c->h_ctr->n_pairs_needed >= LB_VMASK || want <= c->cap_pairs)
+                return fail(c, BGS_ENOMEM, "render: frame needs >= 2^30 (splat, tile) pairs");
+            s = ensure_pair_scratch(c, (uint32_t)want);
+            if (s != BGS_OK) return s;
+            continue;
+        }
+        // success
+        for (int i = 0; i < 5; ++i) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, c->ev[i], c->ev[i + 1]);
+            c->stage_us[i] = ms * 1000.f;
+        }
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, c->ev[0], c->ev[5]);
+        c->stage_us[5] = ms * 1000.f;
+        c->stats.n = n; c->stats.n_visible = c->h_ctr->n_vis; c->stats.n_pairs = c->h_ctr->n_pairs;
+        c->stats.tiles_x = (uint32_t)tiles_x; c->stats.tiles_y = (uint32_t)tiles_y;
+        c->stats.width = (uint32_t)W; c->stats.height = (uint32_t)H;
+        c->have_frame = true; c->last_cloud = cloud; c->last_fc = fc; c->last_sort_all = sort_all;
+        c->last_frame = target;
+        c->err[0] = 0;
+        return BGS_OK;
+    }
+    return fail(c, BGS_ENOMEM, "render: pair list kept overflowing");
+}
+
+bgs_status bgs_debug_sorted_entries(bgs_context* c, uint32_t* out) {
+    if (!c || !out) return BGS_EINVAL;
+    if (!c->have_frame || !c->last_cloud) return fail(c, BGS_NOT_READY, "no frame rendered yet");
+    CU(c, cudaSetDevice(c->device));
+    const uint32_t n = c->last_cloud->n, n_vis = c->stats.n_visible;
+    const uint32_t n_sorted = c->last_sort_all ? n : n_vis;
+    std::vector<uint32_t> k(n_sorted), v(n_sorted);
+    CU(c, cudaMemcpy(k.data(), c->keys[c->depth_result], (size_t)n_sorted * 4, cudaMemcpyDeviceToHost));
+    CU(c, cudaMemcpy(v.data(), c->vals[c->depth_result], (size_t)n_sorted * 4, cudaMemcpyDeviceToHost));
+    for (uint32_t i = 0; i < n_sorted; ++i) { out[2 * i] = k[i]; out[2 * i + 1] = v[i]; }
+    if (!c->last_sort_all) {
+        // culled tail: key = all-ones >> shift, indices ascending (what a stable sort leaves there)
+        uint32_t* flags = nullptr;
+        CU(c, cudaMalloc(&flags, (size_t)n * 4));
+        launch_culled_flags(c->last_cloud->pos, n, c->last_fc, flags, c->stream);
+        std::vector<uint32_t> f(n);
+        cudaError_t e = cudaMemcpyAsync(f.data(), flags, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        cudaFree(flags);
+        if (e != cudaSuccess) return fail(c, BGS_ECUDA, "debug_sorted_entries: %s", cudaGetErrorString(e));
+        const uint32_t culled_key = 0xFFFFFFFFu >> c->last_fc.key_shift;
+        uint32_t at = n_vis;
+        for (uint32_t i = 0; i < n; ++i)
+            if (f[i]) {
+                if (at >= n) return fail(c, BGS_ECUDA, "debug_sorted_entries: visible/culled counts disagree");
+                out[2 * at] = culled_key; out[2 * at + 1] = i; ++at;
+            }
+        if (at != n) return fail(c, BGS_ECUDA, "debug_sorted_entries: visible/culled counts disagree");
+    }
+    return BGS_OK;
+}
+
+bgs_status bgs_debug_tile_ranges(bgs_context* c, uint32_t* start_end) {
+    if (!c || !start_end) return BGS_EINVAL;
+    if (!c->have_frame) return fail(c, BGS_NOT_READY, "no frame rendered yet");
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaMemcpy(start_end, c->ranges, (size_t)c->stats.tiles_x * c->stats.tiles_y * 8, cudaMemcpyDeviceToHost));
+    return BGS_OK;
+}
+
+bgs_status bgs_debug_tile_entries(bgs_context* c, uint32_t* ranks, uint64_t capacity) {
+    if (!c || !ranks) return BGS_EINVAL;
+    if (!c->have_frame) return fail(c, BGS_NOT_READY, "no frame rendered yet");
+    CU(c, cudaSetDevice(c->device));
+    const uint64_t cnt = c->stats.n_pairs < capacity ? c->stats.n_pairs : capacity;
+    CU(c, cudaMemcpy(ranks, c->pvals[c->pair_result], (size_t)cnt * 4, cudaMemcpyDeviceToHost));
+    return BGS_OK;
+}
+
+bgs_status bgs_debug_projected(bgs_context* c, float* records, uint32_t* rank_to_index) {
+    if (!c) return BGS_EINVAL;
+    if (!c->have_frame) return fail(c, BGS_NOT_READY, "no frame rendered yet");
+    CU(c, cudaSetDevice(c->device));
+    const uint32_t n_vis = c->stats.n_visible;
+    if (records) CU(c, cudaMemcpy(records, c->recs, (size_t)n_vis * sizeof(SplatRec), cudaMemcpyDeviceToHost));
+    if (rank_to_index) {
+        std::vector<uint32_t> v(n_vis);
+        CU(c, cudaMemcpy(v.data(), c->vals[c->depth_result], (size_t)n_vis * 4, cudaMemcpyDeviceToHost));
+        for (uint32_t r = 0; r < n_vis; ++r) rank_to_index[r] = v[n_vis - 1 - r];
+    }
+    return BGS_OK;
+}
+
+bgs_status bgs_frame_stats_get(bgs_context* c, bgs_frame_stats* out) {
+    if (!c || !out) return BGS_EINVAL;
+    if (!c->have_frame) return fail(c, BGS_NOT_READY, "no frame rendered yet");
+    *out = c->stats;
+    return BGS_OK;
+}
+
+bgs_status bgs_stage_times_us(bgs_context* c, float out[6]) {
+    if (!c || !out) return BGS_EINVAL;
+    if (!c->have_frame) return fail(c, BGS_NOT_READY, "no frame rendered yet");
+    for (int i = 0; i < 6; ++i) out[i] = c->stage_us[i];
+    return BGS_OK;
+}
+
+const char* bgs_last_error(const bgs_context* c) { return c ? c->err : "null context"; }
+void* bgs_context_stream(bgs_context* c) { return c ? (void*)c->stream : nullptr; }
+const void* bgs_frame_device_ptr(bgs_context* c) { return (c && c->have_frame) ? c->last_frame : nullptr; }
+uint32_t bgs_last_launch_count(const bgs_context* c) { return c ? c->launches : 0; }
+
+}  // extern "C"

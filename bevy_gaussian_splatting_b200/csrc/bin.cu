@@ -1,0 +1,125 @@
+// bin.cu -- stage 4: tile binning / range build (no counterpart in the
+// reference, which rasterises one instanced quad per gaussian: src/render/mod.rs:1562-1566).
+//
+// For every visible splat in front-to-back rank order, emit one (tile id, rank) pair per 16x16
+// tile its conservative pixel bbox touches.  Pair offsets come from a single-pass chained scan
+// (decoupled look-back) over the per-splat tile counts, so pairs are emitted in rank order and
+// the stable tile-id radix sort that follows yields, per tile, a slice of the GLOBAL depth order.
+// range build: boundaries of equal tile ids in the sorted pair keys.
+#include "common.cuh"
+
+namespace bgs {
+
+constexpr int BIN_THREADS = 256;
+constexpr int BIN_ITEMS = 4;
+constexpr int BIN_TILE = BIN_THREADS * BIN_ITEMS;
+
+__global__ void __launch_bounds__(BIN_THREADS)
+bin_emit_kernel(const SplatRec* __restrict__ recs, FrameCounters* __restrict__ ctr, uint32_t* __restrict__ status,
+                int tiles_x, uint32_t capacity, uint32_t* __restrict__ pair_keys, uint32_t* __restrict__ pair_vals) {
+    __shared__ uint32_t s_wtot[BIN_THREADS / 32];
+    __shared__ uint32_t s_base;
+    __shared__ uint32_t s_tile;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const uint32_t n_vis = ctr->n_vis;
+    const uint32_t num_tiles = (n_vis + BIN_TILE - 1) / BIN_TILE;
+    while (true) {
+        if (t == 0) s_tile = atomicAdd(&ctr->tile_ctr[5], 1u);
+        __syncthreads();
+        const uint32_t tile = s_tile;
+        if (tile >= num_tiles) break;
+        const uint32_t r0 = tile * BIN_TILE + t * BIN_ITEMS;   // blocked: 4 consecutive ranks per thread
+        uint32_t bx[BIN_ITEMS], by[BIN_ITEMS], cnt[BIN_ITEMS];
+        uint32_t mine = 0u;
+#pragma unroll
+        for (int j = 0; j < BIN_ITEMS; ++j) {
+            const uint32_t r = r0 + j;
+            cnt[j] = 0u;
+            if (r < n_vis) {
+                const uint2 b = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const char*>(recs + r) + 24));
+                bx[j] = b.x; by[j] = b.y;
+                const uint32_t xlo = b.x & 0xFFFFu, xhi = b.x >> 16, ylo = b.y & 0xFFFFu, yhi = b.y >> 16;
+                if (xlo <= xhi && ylo <= yhi)
+                    cnt[j] = ((xhi >> 4) - (xlo >> 4) + 1u) * ((yhi >> 4) - (ylo >> 4) + 1u);
+            }
+            mine += cnt[j];
+        }
+        uint32_t incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += y;
+        }
+        if (lane == 31) s_wtot[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t v = (lane < BIN_THREADS / 32) ? s_wtot[lane] : 0u;
+            uint32_t total = v;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+            // a frame needing >= 2^30 pairs cannot be represented in the status word: saturate
+            const uint32_t agg = total > LB_VMASK ? LB_VMASK : total;
+            const uint32_t base = warp_lookback(status, (int)tile, agg);
+            if (lane == 0) {
+                s_base = base;
+                if (tile == num_tiles - 1) {
+                    const uint32_t need = base + agg;
+                    ctr->n_pairs_needed = need;
+                    ctr->n_pairs = need < capacity ? need : capacity;
+                }
+            }
+        }
+        __syncthreads();
+        uint32_t wprefix = 0u;
+        for (int w = 0; w < warp; ++w) wprefix += s_wtot[w];
+        uint32_t off = s_base + wprefix + incl - mine;
+#pragma unroll
+        for (int j = 0; j < BIN_ITEMS; ++j) {
+            if (cnt[j] == 0u) continue;
+            const uint32_t r = r0 + j;
+            const uint32_t txlo = (bx[j] & 0xFFFFu) >> 4, txhi = (bx[j] >> 16) >> 4;
+            const uint32_t tylo = (by[j] & 0xFFFFu) >> 4, tyhi = (by[j] >> 16) >> 4;
+            for (uint32_t ty = tylo; ty <= tyhi; ++ty)
+                for (uint32_t tx = txlo; tx <= txhi; ++tx) {
+                    if (off < capacity) {
+                        pair_keys[off] = ty * (uint32_t)tiles_x + tx;
+                        pair_vals[off] = r;
+                    }
+                    ++off;
+                }
+        }
+        __syncthreads();
+    }
+    // n_vis == 0: nothing was published; counters stay zero from the per-frame clear
+}
+
+__global__ void tile_ranges_kernel(const uint32_t* __restrict__ sorted_tile_ids, const FrameCounters* __restrict__ ctr,
+                                   uint2* __restrict__ ranges) {
+    const uint32_t n = ctr->n_pairs;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t t = sorted_tile_ids[i];
+        if (i == 0 || sorted_tile_ids[i - 1] != t) ranges[t].x = i;
+        if (i == n - 1 || sorted_tile_ids[i + 1] != t) ranges[t].y = i + 1;
+    }
+}
+
+void launch_bin_emit(const SplatRec* recs, FrameCounters* ctr, uint32_t* status, int tiles_x, uint32_t capacity,
+                     uint32_t* pair_keys, uint32_t* pair_vals, uint32_t n_upper, int sm_count, cudaStream_t stream) {
+    uint32_t blocks = (n_upper + BIN_TILE - 1) / BIN_TILE;
+    const uint32_t cap_blocks = (uint32_t)sm_count * 4u;
+    if (blocks > cap_blocks) blocks = cap_blocks;
+    if (blocks == 0) blocks = 1;
+    bin_emit_kernel<<<blocks, BIN_THREADS, 0, stream>>>(recs, ctr, status, tiles_x, capacity, pair_keys, pair_vals);
+}
+uint32_t bin_num_tiles(uint32_t n) { return (n + BIN_TILE - 1) / BIN_TILE; }
+
+void launch_tile_ranges(const uint32_t* sorted_tile_ids, const FrameCounters* ctr, uint2* ranges, uint32_t capacity,
+                        int sm_count, cudaStream_t stream) {
+    uint32_t blocks = (capacity + 255) / 256;
+    const uint32_t cap_blocks = (uint32_t)sm_count * 8u;
+    if (blocks > cap_blocks) blocks = cap_blocks;
+    if (blocks == 0) blocks = 1;
+    tile_ranges_kernel<<<blocks, 256, 0, stream>>>(sorted_tile_ids, ctr, ranges);
+}
+
+}  // namespace bgs

@@ -1,0 +1,103 @@
+// common.cuh -- shared device-side types and helpers of libbgs (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/bgs.h"
+
+namespace bgs {
+
+constexpr int TILE_PX = 16;           // 16x16-pixel raster tiles (a7)
+constexpr float T_STOP = 1.0e-4f;     // a pixel stops once its transmittance drops below this
+
+// Look-back status word: bits 31:30 flag, bits 29:0 value (n and n_pairs are < 2^30).
+constexpr uint32_t LB_EMPTY = 0u, LB_AGG = 1u << 30, LB_INC = 2u << 30, LB_VMASK = (1u << 30) - 1u;
+
+// Per-frame constants handed to the kernels by value (column-major matrices, as Bevy).
+struct FrameConsts {
+    float model[16];            // CloudUniform.transform
+    float view_from_world[16];
+    float clip_from_world[16];
+    float cam[3];
+    float W, H;                 // viewport.zw
+    float p00, p11;             // clip_from_view[0].x, clip_from_view[1].y
+    float global_opacity, global_scale;
+    uint32_t color_space;
+    uint32_t key_shift;         // 32 - radix_sort_depth_bits
+    uint32_t gaussian_mode, rasterize_mode, aabb, adaptive, draw_mode;
+    int Wi, Hi, tiles_x, tiles_y;
+};
+
+// Projected splat record, 48 B, stored by front-to-back rank.
+struct __align__(16) SplatRec {
+    float cx, cy, ux, uy;       // centre (px), first row of the pixel-offset -> uv map
+    float vx, vy;               // second row
+    uint32_t bx, by;            // pixel bbox: lo | hi << 16 (inclusive); lo > hi = empty
+    float r, g, b, op;          // linear rgb (unclamped), opacity * global_opacity
+};
+static_assert(sizeof(SplatRec) == 48, "SplatRec must be 48 bytes");
+
+// Device-resident per-frame counters (one cudaMemsetAsync per frame clears them).
+struct FrameCounters {
+    uint32_t n_sort;            // entries the depth sort runs over (n_vis, or N with SORT_ALL)
+    uint32_t n_vis;             // in-frustum gaussians
+    uint32_t n_pairs;           // (splat, tile) pairs emitted (clamped to capacity)
+    uint32_t n_pairs_needed;    // pairs the frame needs (may exceed capacity -> host regrows)
+    uint32_t tile_ctr[16];      // dynamic tile tickets: [0] keygen, [1..4] depth passes,
+                                // [5] bin, [6..7] pair passes, [8..] spare
+    uint32_t culled_min, culled_min2, culled_max;   // for RasterizeMode::Depth's sorted[1]/[N-1]
+    uint32_t pad;
+};
+
+__device__ __forceinline__ uint32_t ld_volatile(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_volatile(uint32_t* p, uint32_t v) {
+    asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t lanemask_lt() {
+    uint32_t m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+__device__ __forceinline__ uint32_t lanemask_le() {
+    uint32_t m;
+    asm("mov.u32 %0, %%lanemask_le;" : "=r"(m));
+    return m;
+}
+
+// Decoupled look-back over single-word tile status, executed by ONE full warp.
+// Publishes this tile's aggregate, sums predecessors' aggregates back to the nearest inclusive
+// prefix, publishes the inclusive prefix, returns the exclusive prefix (same value on all lanes).
+__device__ __forceinline__ uint32_t warp_lookback(uint32_t* status, int tile, uint32_t aggregate) {
+    const int lane = threadIdx.x & 31;
+    if (tile == 0) {
+        if (lane == 0) st_volatile(status, LB_INC | aggregate);
+        return 0u;
+    }
+    if (lane == 0) st_volatile(status + tile, LB_AGG | aggregate);
+    uint32_t excl = 0u;
+    for (int base = tile - 1; base >= 0; base -= 32) {
+        const int idx = base - lane;
+        uint32_t w;
+        do {
+            w = (idx >= 0) ? ld_volatile(status + idx) : (LB_INC | 0u);
+        } while (__any_sync(0xffffffffu, (w >> 30) == 0u));
+        const uint32_t inc_mask = __ballot_sync(0xffffffffu, (w >> 30) == 2u);
+        uint32_t v = w & LB_VMASK;
+        if (inc_mask) {
+            const int first = __ffs(inc_mask) - 1;   // nearest predecessor holding an inclusive prefix
+            if (lane > first) v = 0u;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        excl += v;
+        if (inc_mask) break;
+    }
+    if (lane == 0) st_volatile(status + tile, LB_INC | ((excl + aggregate) & LB_VMASK));
+    return excl;
+}
+
+}  // namespace bgs

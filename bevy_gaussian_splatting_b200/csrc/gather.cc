@@ -1,0 +1,120 @@
+// gather.cc -- multi-GPU frame gather: one view per GPU, replicated cloud, and
+// ONE collective per frame: every rank's finished frame is sent to `root` over NCCL (NVLink 5 /
+// NVSwitch), on the render stream.  The reference has no multi-GPU path at all.
+//
+// NCCL is resolved lazily with dlopen so single-GPU users of libbgs.so never need it, and so a
+// host process that already loaded an NCCL (e.g. the torch-bundled one) shares that instance.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/bgs.h"
+
+namespace {
+
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*CommCount)(const ncclComm_t, int*) = nullptr;
+    ncclResult_t (*CommUserRank)(const ncclComm_t, int*) = nullptr;
+    bool ok = false;
+};
+
+NcclApi& api() {
+    static NcclApi a;
+    if (a.lib || a.ok) return a;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* nm : names) {
+        a.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+        if (a.lib) break;
+    }
+    if (!a.lib) return a;
+#define SYM(field, name) *(void**)(&a.field) = dlsym(a.lib, name)
+    SYM(GetUniqueId, "ncclGetUniqueId");
+    SYM(CommInitRank, "ncclCommInitRank");
+    SYM(CommDestroy, "ncclCommDestroy");
+    SYM(GroupStart, "ncclGroupStart");
+    SYM(GroupEnd, "ncclGroupEnd");
+    SYM(Send, "ncclSend");
+    SYM(Recv, "ncclRecv");
+    SYM(CommCount, "ncclCommCount");
+    SYM(CommUserRank, "ncclCommUserRank");
+#undef SYM
+    a.ok = a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.GroupStart && a.GroupEnd && a.Send && a.Recv &&
+           a.CommCount && a.CommUserRank;
+    return a;
+}
+
+}  // namespace
+
+extern "C" {
+
+bgs_status bgs_nccl_unique_id(void* out_id128) {
+    if (!out_id128) return BGS_EINVAL;
+    NcclApi& a = api();
+    if (!a.ok) return BGS_ENCCL;
+    ncclUniqueId id;
+    if (a.GetUniqueId(&id) != ncclSuccess) return BGS_ENCCL;
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    memcpy(out_id128, &id, 128);
+    return BGS_OK;
+}
+
+bgs_status bgs_nccl_comm_init(bgs_context* ctx, int nranks, int rank, const void* id128, void** out_comm) {
+    if (!ctx || !id128 || !out_comm || nranks < 1 || rank < 0 || rank >= nranks) return BGS_EINVAL;
+    NcclApi& a = api();
+    if (!a.ok) return BGS_ENCCL;
+    ncclUniqueId id;
+    memcpy(&id, id128, 128);
+    ncclComm_t comm = nullptr;
+    // the caller's current device must be the context's device; bgs_context_create set it
+    if (a.CommInitRank(&comm, nranks, id, rank) != ncclSuccess) return BGS_ENCCL;
+    *out_comm = comm;
+    return BGS_OK;
+}
+
+void bgs_nccl_comm_destroy(void* nccl_comm) {
+    NcclApi& a = api();
+    if (a.ok && nccl_comm) a.CommDestroy((ncclComm_t)nccl_comm);
+}
+
+bgs_status bgs_gather_frames(bgs_context* ctx, void* nccl_comm, int root, const void* local_frame, void* all_frames,
+                             size_t bytes) {
+    if (!ctx || !nccl_comm || !local_frame || bytes == 0) return BGS_EINVAL;
+    NcclApi& a = api();
+    if (!a.ok) return BGS_ENCCL;
+    ncclComm_t comm = (ncclComm_t)nccl_comm;
+    int nranks = 0, rank = -1;
+    if (a.CommCount(comm, &nranks) != ncclSuccess || a.CommUserRank(comm, &rank) != ncclSuccess) return BGS_ENCCL;
+    if (root < 0 || root >= nranks) return BGS_EINVAL;
+    if (rank == root && !all_frames) return BGS_EINVAL;
+    cudaStream_t q = (cudaStream_t)bgs_context_stream(ctx);
+    ncclResult_t r = a.GroupStart();
+    if (r != ncclSuccess) return BGS_ENCCL;
+    if (rank == root) {
+        for (int p = 0; p < nranks && r == ncclSuccess; ++p) {
+            char* dst = (char*)all_frames + (size_t)p * bytes;
+            if (p == root) {
+                if (cudaMemcpyAsync(dst, local_frame, bytes, cudaMemcpyDeviceToDevice, q) != cudaSuccess) r = ncclUnhandledCudaError;
+            } else {
+                r = a.Recv(dst, bytes, ncclUint8, p, comm, q);
+            }
+        }
+    } else {
+        r = a.Send(local_frame, bytes, ncclUint8, root, comm, q);
+    }
+    const ncclResult_t e = a.GroupEnd();
+    if (r != ncclSuccess || e != ncclSuccess) return BGS_ENCCL;
+    return BGS_OK;
+}
+
+}  // extern "C"

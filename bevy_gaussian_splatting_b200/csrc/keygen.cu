@@ -1,0 +1,126 @@
+// keygen.cu -- stage 1: depth-key generation + stable stream compaction of the visible set.
+//
+// Replaces radix_sort_a's key half (src/sort/radix.wgsl:86-106): key = 0xFFFFFFFF - bits(|Mp-cam|^2)
+// for in-frustum gaussians, 0xFFFFFFFF otherwise, shifted by 32 - depth_bits.  Instead of sorting
+// the culled (all-ones) keys with everything else, the visible (key, index) pairs are compacted
+// IN INDEX ORDER (single-pass chained scan with decoupled look-back), so the stable LSD sort that
+// follows sees the same tie order as the reference; the culled tail of the reference's
+// sorted_entry_buffer is "ascending index" and is reconstructed only by the debug hook.
+//
+// HBM-bound streaming kernel: 16 B read per gaussian (coalesced float4), 8 B written per
+// visible gaussian.  Compiled with -fmad=false (see project_math.cuh).
+#include "project_math.cuh"
+
+namespace bgs {
+
+constexpr int KG_THREADS = 256;
+constexpr int KG_ITEMS = 8;
+constexpr int KG_TILE = KG_THREADS * KG_ITEMS;
+
+__global__ void __launch_bounds__(KG_THREADS)
+keygen_compact_kernel(const float4* __restrict__ pos, uint32_t n, FrameConsts fc, int sort_all,
+                      uint32_t* __restrict__ keys_out, uint32_t* __restrict__ ids_out,
+                      uint32_t* __restrict__ status, FrameCounters* __restrict__ ctr) {
+    __shared__ uint32_t s_cnt[KG_ITEMS * (KG_THREADS / 32)];
+    __shared__ uint32_t s_off[KG_ITEMS * (KG_THREADS / 32)];
+    __shared__ uint32_t s_base;
+    __shared__ int s_tile;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    // dynamic tile ticket: look-back only ever waits on tiles that already started
+    if (t == 0) s_tile = (int)atomicAdd(&ctr->tile_ctr[0], 1u);
+    __syncthreads();
+    const int tile = s_tile;
+    const uint32_t tile_base = (uint32_t)tile * KG_TILE;
+
+    float4 p[KG_ITEMS];
+#pragma unroll
+    for (int j = 0; j < KG_ITEMS; ++j) {
+        const uint32_t i = tile_base + j * KG_THREADS + t;
+        p[j] = (i < n) ? __ldcs(pos + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    uint32_t key[KG_ITEMS];
+    uint32_t prefix[KG_ITEMS];   // rank among the visible items of (item j, this warp)
+    uint32_t vis_bits = 0;
+#pragma unroll
+    for (int j = 0; j < KG_ITEMS; ++j) {
+        const uint32_t i = tile_base + j * KG_THREADS + t;
+        const KeyOut k = key_of(fc, p[j].x, p[j].y, p[j].z);
+        const bool v = (i < n) && k.visible;
+        key[j] = k.key;
+        const uint32_t b = __ballot_sync(0xffffffffu, v);
+        prefix[j] = __popc(b & lanemask_lt());
+        if (v) vis_bits |= 1u << j;
+        if (lane == 0) s_cnt[j * (KG_THREADS / 32) + warp] = __popc(b);
+    }
+    __syncthreads();
+    if (sort_all) {
+        // reference-literal mode: every entry goes to the sort; just count the visible ones
+        if (warp == 0) {
+            uint32_t v = s_cnt[lane] + s_cnt[lane + 32];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0 && v) atomicAdd(&ctr->n_vis, v);
+            if (lane == 0 && tile == 0) ctr->n_sort = n;
+        }
+#pragma unroll
+        for (int j = 0; j < KG_ITEMS; ++j) {
+            const uint32_t i = tile_base + j * KG_THREADS + t;
+            if (i < n) { keys_out[i] = key[j]; ids_out[i] = i; }
+        }
+        return;
+    }
+    if (warp == 0) {
+        // 64 (item, warp) counts in index order: exclusive scan, two per lane
+        const uint32_t a = s_cnt[2 * lane], b = s_cnt[2 * lane + 1];
+        uint32_t incl = a + b;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += y;
+        }
+        const uint32_t excl = incl - (a + b);
+        s_off[2 * lane] = excl;
+        s_off[2 * lane + 1] = excl + a;
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        const uint32_t base = warp_lookback(status, tile, total);
+        if (lane == 0) {
+            s_base = base;
+            // the last tile (in index order) knows the final count
+            if (tile_base + KG_TILE >= n) { ctr->n_vis = base + total; ctr->n_sort = base + total; }
+        }
+    }
+    __syncthreads();
+    const uint32_t base = s_base;
+#pragma unroll
+    for (int j = 0; j < KG_ITEMS; ++j) {
+        if (vis_bits & (1u << j)) {
+            const uint32_t dst = base + s_off[j * (KG_THREADS / 32) + warp] + prefix[j];
+            keys_out[dst] = key[j];
+            ids_out[dst] = tile_base + j * KG_THREADS + t;
+        }
+    }
+}
+
+// Debug hook: rebuild the reference's full sorted_entry_buffer (sort/mod.rs:323-329) from the
+// compacted result: [0, n_vis) = sorted visible entries, then every culled index ascending
+// with key 0xFFFFFFFF >> shift.  Single block per call chunk; not on the hot path.
+__global__ void culled_flags_kernel(const float4* __restrict__ pos, uint32_t n, FrameConsts fc,
+                                    uint32_t* __restrict__ flags) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 p = pos[i];
+    flags[i] = key_of(fc, p.x, p.y, p.z).visible ? 0u : 1u;
+}
+
+void launch_keygen(const float4* pos, uint32_t n, const FrameConsts& fc, int sort_all, uint32_t* keys_out,
+                   uint32_t* ids_out, uint32_t* status, FrameCounters* ctr, cudaStream_t stream) {
+    const uint32_t tiles = (n + KG_TILE - 1) / KG_TILE;
+    keygen_compact_kernel<<<tiles, KG_THREADS, 0, stream>>>(pos, n, fc, sort_all, keys_out, ids_out, status, ctr);
+}
+uint32_t keygen_num_tiles(uint32_t n) { return (n + KG_TILE - 1) / KG_TILE; }
+
+void launch_culled_flags(const float4* pos, uint32_t n, const FrameConsts& fc, uint32_t* flags, cudaStream_t stream) {
+    culled_flags_kernel<<<(n + 255) / 256, 256, 0, stream>>>(pos, n, fc, flags);
+}
+
+}  // namespace bgs

@@ -1,0 +1,294 @@
+// project.cu -- stage 3: per-gaussian 3D->2D covariance projection + SH-degree-3 colour, run
+// ONCE per visible gaussian in front-to-back rank order (the reference runs it 4x per gaussian in
+// its vertex stage: src/render/gaussian.wgsl:185-436).
+//
+// rank r (0 = nearest) -> gaussian id = sorted_ids[n_vis-1-r] (the sort is far->near like the
+// reference's, src/sort/radix.wgsl) -> gather the planar attributes (f32 240 B or f16 128 B per
+// gaussian) -> write one 48 B SplatRec at recs[r] (coalesced), which is all the tile stages read.
+//
+// Geometry (centre, OBB uv rows, pixel bbox) is bit-exact vs the oracle: compiled -fmad=false.
+#include <cuda_fp16.h>
+
+#include "project_math.cuh"
+
+namespace bgs {
+
+__constant__ float c_shc[16] = {   // src/material/spherical_harmonics.wgsl:3-20
+    0.28209479177387814f, -0.4886025119029199f, 0.4886025119029199f, -0.4886025119029199f,
+    1.0925484305920792f, -1.0925484305920792f, 0.31539156525252005f, -1.0925484305920792f,
+    0.5462742152960396f, -0.5900435899266435f, 2.890611442640554f, -0.4570457994644658f,
+    0.3731763325901154f, -0.4570457994644658f, 1.445305721320277f, -0.5900435899266435f};
+
+__device__ __forceinline__ void normalize3(const float a[3], float out[3]) {
+    const float l = sqrtf((a[0] * a[0] + a[1] * a[1]) + a[2] * a[2]);
+    out[0] = a[0] / l; out[1] = a[1] / l; out[2] = a[2] / l;
+}
+__device__ __forceinline__ float dot3(const float a[3], const float b[3]) {
+    return (a[0] * b[0] + a[1] * b[1]) + a[2] * b[2];
+}
+// spherical_harmonics.wgsl:22-32; no clamp on either side
+__device__ __forceinline__ float srgb_to_linear(float v) {
+    if (v <= 0.04045f) return v / 12.92f;
+    return powf((v + 0.055f) / 1.055f, 2.4f);
+}
+__device__ __forceinline__ uint32_t pack_bbox(float lo, float hi) {
+    return (uint32_t)(int)lo | ((uint32_t)(int)hi << 16);
+}
+constexpr uint32_t BBOX_EMPTY = 1u;   // lo = 1, hi = 0
+
+// conservative pixel bbox of |fx - cx| <= hx, |fy - cy| <= hy (this repo's a7 rule; see oracle)
+__device__ __forceinline__ void make_bbox(float cx, float cy, float hx, float hy, int Wi, int Hi,
+                                          uint32_t& bx, uint32_t& by) {
+    bx = BBOX_EMPTY; by = BBOX_EMPTY;
+    if (!(hx >= 0.0f) || !(hy >= 0.0f) || !(cx == cx) || !(cy == cy)) return;
+    const float sx = hx * 1.0e-3f + 1.0e-2f, sy = hy * 1.0e-3f + 1.0e-2f;
+    float x0 = ceilf((cx - hx) - (0.5f + sx));
+    float x1 = floorf((cx + hx) - (0.5f - sx));
+    float y0 = ceilf((cy - hy) - (0.5f + sy));
+    float y1 = floorf((cy + hy) - (0.5f - sy));
+    if (!(x0 <= x1) || !(y0 <= y1)) return;
+    x0 = fmaxf(x0, 0.0f); y0 = fmaxf(y0, 0.0f);
+    x1 = fminf(x1, (float)(Wi - 1)); y1 = fminf(y1, (float)(Hi - 1));
+    if (!(x0 <= x1) || !(y0 <= y1)) return;
+    bx = pack_bbox(x0, x1); by = pack_bbox(y0, y1);
+}
+
+template <bool F16>
+struct Attr;
+template <>
+struct Attr<false> {   // f32 planes: src/gaussian/f32.rs:53-175, planar.wgsl:334-364
+    __device__ static void load(const void* sh_p, const void* rot_p, const void* so_p, uint32_t id, float* sh,
+                                float q[4], float so[4], bool need_sh) {
+        const float4 r = __ldg(reinterpret_cast<const float4*>(rot_p) + id);
+        const float4 s = __ldg(reinterpret_cast<const float4*>(so_p) + id);
+        q[0] = r.x; q[1] = r.y; q[2] = r.z; q[3] = r.w;
+        so[0] = s.x; so[1] = s.y; so[2] = s.z; so[3] = s.w;
+        if (need_sh) {
+            const float4* p = reinterpret_cast<const float4*>(sh_p) + (size_t)id * 12;
+#pragma unroll
+            for (int i = 0; i < 12; ++i) {
+                const float4 v = __ldg(p + i);
+                sh[4 * i] = v.x; sh[4 * i + 1] = v.y; sh[4 * i + 2] = v.z; sh[4 * i + 3] = v.w;
+            }
+        }
+    }
+};
+template <>
+struct Attr<true> {    // f16 planes: src/gaussian/f16.rs:30-56,244-263; planar.wgsl:117-176
+    __device__ static float lo(uint32_t w) { return __half2float(__ushort_as_half((unsigned short)(w & 0xFFFFu))); }
+    __device__ static float hi(uint32_t w) { return __half2float(__ushort_as_half((unsigned short)(w >> 16))); }
+    __device__ static void load(const void* sh_p, const void* rso_p, const void*, uint32_t id, float* sh,
+                                float q[4], float so[4], bool need_sh) {
+        const uint4 w = __ldg(reinterpret_cast<const uint4*>(rso_p) + id);
+        q[0] = hi(w.x); q[1] = lo(w.x); q[2] = hi(w.y); q[3] = lo(w.y);
+        so[0] = hi(w.z); so[1] = lo(w.z); so[2] = hi(w.w); so[3] = lo(w.w);
+        if (need_sh) {
+            const uint4* p = reinterpret_cast<const uint4*>(sh_p) + (size_t)id * 6;
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+                const uint4 v = __ldg(p + i);
+                sh[8 * i] = lo(v.x); sh[8 * i + 1] = hi(v.x); sh[8 * i + 2] = lo(v.y); sh[8 * i + 3] = hi(v.y);
+                sh[8 * i + 4] = lo(v.z); sh[8 * i + 5] = hi(v.z); sh[8 * i + 6] = lo(v.w); sh[8 * i + 7] = hi(v.w);
+            }
+        }
+    }
+};
+
+template <bool F16>
+__global__ void __launch_bounds__(128)
+project_kernel(const float4* __restrict__ pos, const void* __restrict__ sh_p, const void* __restrict__ rot_p,
+               const void* __restrict__ so_p, const uint32_t* __restrict__ sorted_ids,
+               const FrameCounters* __restrict__ ctr, FrameConsts fc, SplatRec* __restrict__ recs) {
+    const uint32_t n_vis = ctr->n_vis;
+    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n_vis; r += gridDim.x * blockDim.x) {
+        const uint32_t id = __ldg(sorted_ids + (n_vis - 1u - r));
+        const float4 p4 = __ldg(pos + id);
+        float sh[48], q[4], so[4];
+        const bool need_sh = fc.rasterize_mode == BGS_RASTERIZE_COLOR;
+        Attr<F16>::load(sh_p, rot_p, so_p, id, sh, q, so, need_sh);
+
+        SplatRec rec;
+        rec.ux = 0.f; rec.uy = 0.f; rec.vx = 0.f; rec.vy = 0.f;
+        rec.bx = BBOX_EMPTY; rec.by = BBOX_EMPTY;
+        rec.r = 0.f; rec.g = 0.f; rec.b = 0.f;
+
+        const KeyOut k = key_of(fc, p4.x, p4.y, p4.z);
+        const float W = fc.W, H = fc.H;
+        const float hw = 0.5f * W, hh = 0.5f * H;
+        const float cx = k.ndc[0] * hw + hw;
+        const float cy = hh - k.ndc[1] * hh;
+        rec.cx = cx; rec.cy = cy;
+        const float opacity = so[3];
+        rec.op = opacity * fc.global_opacity;
+        const bool drawn = k.visible && !(fc.draw_mode == BGS_DRAW_SELECTED && p4.w < 0.5f);
+
+        float A[3][3];
+#pragma unroll
+        for (int rr = 0; rr < 3; ++rr)
+#pragma unroll
+            for (int cc = 0; cc < 3; ++cc) A[rr][cc] = fc.model[cc * 4 + rr];
+        // helpers.wgsl:137-158 as (row, col); the quaternion is NOT normalised
+        float Rm[3][3];
+        {
+            const float qr = q[0], x = q[1], y = q[2], z = q[3];
+            Rm[0][0] = 1.0f - 2.0f * (y * y + z * z);
+            Rm[1][0] = 2.0f * (x * y - qr * z);
+            Rm[2][0] = 2.0f * (x * z + qr * y);
+            Rm[0][1] = 2.0f * (x * y + qr * z);
+            Rm[1][1] = 1.0f - 2.0f * (x * x + z * z);
+            Rm[2][1] = 2.0f * (y * z - qr * x);
+            Rm[0][2] = 2.0f * (x * z - qr * y);
+            Rm[1][2] = 2.0f * (y * z + qr * x);
+            Rm[2][2] = 1.0f - 2.0f * (x * x + y * y);
+        }
+        const float sc[3] = {so[0] * fc.global_scale, so[1] * fc.global_scale, so[2] * fc.global_scale};
+
+        if (drawn) {
+            float cutoff = 3.0f;
+            if (fc.adaptive) {   // gaussian.wgsl:228-232
+                const float a = 9.0f + 2.0f * det_ln(opacity);
+                cutoff = sqrtf(a > 0.000001f ? a : 0.000001f);
+            }
+            // gaussian_3d.wgsl:49-72
+            float M[3][3], Sg[3][3], X[3][3], TS[3][3];
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) M[i][j] = sc[i] * Rm[i][j];
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) Sg[i][j] = (M[0][i] * M[0][j] + M[1][i] * M[1][j]) + M[2][i] * M[2][j];
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) X[i][j] = (A[i][0] * Sg[0][j] + A[i][1] * Sg[1][j]) + A[i][2] * Sg[2][j];
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) TS[i][j] = (X[i][0] * A[j][0] + X[i][1] * A[j][1]) + X[i][2] * A[j][2];
+            const float c3[6] = {TS[0][0], TS[1][0], TS[2][0], TS[1][1], TS[2][1], TS[2][2]};
+            const float Vrk[3][3] = {{c3[0], c3[1], c3[2]}, {c3[1], c3[3], c3[4]}, {c3[2], c3[4], c3[5]}};
+            // helpers.wgsl:8-47
+            float tv[4];
+            mat4_point(fc.view_from_world, k.pw[0], k.pw[1], k.pw[2], tv);
+            const float fx = fc.p00 * W, fy = fc.p11 * H;
+            const float sz = 1.0f / (tv[2] * tv[2]);
+            const float J00 = fx / tv[2], J20 = -(fx * tv[0]) * sz;
+            const float J11 = -fy / tv[2], J21 = (fy * tv[1]) * sz;
+            float Tm[3][2];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const float v0 = fc.view_from_world[i * 4 + 0], v1 = fc.view_from_world[i * 4 + 1],
+                            v2 = fc.view_from_world[i * 4 + 2];
+                Tm[i][0] = v0 * J00 + v2 * J20;
+                Tm[i][1] = v1 * J11 + v2 * J21;
+            }
+            float Y[3][2];
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int b = 0; b < 2; ++b) Y[i][b] = (Vrk[i][0] * Tm[0][b] + Vrk[i][1] * Tm[1][b]) + Vrk[i][2] * Tm[2][b];
+            const float a = ((Tm[0][0] * Y[0][0] + Tm[1][0] * Y[1][0]) + Tm[2][0] * Y[2][0]) + 0.3f;
+            const float b = (Tm[0][1] * Y[0][0] + Tm[1][1] * Y[1][0]) + Tm[2][1] * Y[2][0];
+            const float c = ((Tm[0][1] * Y[0][1] + Tm[1][1] * Y[1][1]) + Tm[2][1] * Y[2][1]) + 0.3f;
+            // helpers.wgsl:49-67,81-119 (USE_OBB)
+            const float det = a * c - b * b;
+            const float mid = 0.5f * (a + c);
+            const float disc = fmaxf(0.0f, mid * mid - det);
+            const float term = sqrtf(disc);
+            const float l1 = mid + term;
+            const float aa = (a - c) * (a - c);
+            const float bb = sqrtf(aa + (4.0f * b) * b);
+            const float major = sqrtf(((a + c) + bb) * 0.5f);
+            const float minor = sqrtf(((a + c) - bb) * 0.5f);
+            const float Bx = cutoff * major, By = cutoff * minor;
+            const float evx = -b, evy = l1 - a;
+            const float el = sqrtf(evx * evx + evy * evy);
+            const float e1x = evx / el, e1y = evy / el;
+            const float e2x = e1y, e2y = -e1x;
+            rec.ux = (2.0f * e1x) / Bx; rec.uy = (-2.0f * e1y) / Bx;
+            rec.vx = (2.0f * e2x) / By; rec.vy = (-2.0f * e2y) / By;
+            const float hx = 0.5f * (fabsf(e1x) * Bx + fabsf(e2x) * By);
+            const float hy = 0.5f * (fabsf(e1y) * Bx + fabsf(e2y) * By);
+            if (rec.ux == rec.ux && rec.uy == rec.uy && rec.vx == rec.vx && rec.vy == rec.vy)
+                make_bbox(cx, cy, hx, hy, fc.Wi, fc.Hi, rec.bx, rec.by);
+
+            // colour source
+            float rgb[3] = {0.f, 0.f, 0.f};
+            if (fc.rasterize_mode == BGS_RASTERIZE_COLOR) {
+                // gaussian.wgsl:166-183,406-416
+                const float dlt[3] = {k.pw[0] - fc.cam[0], k.pw[1] - fc.cam[1], k.pw[2] - fc.cam[2]};
+                float dw[3], loc[3], dl[3];
+                normalize3(dlt, dw);
+#pragma unroll
+                for (int cc = 0; cc < 3; ++cc) {
+                    const float col[3] = {A[0][cc], A[1][cc], A[2][cc]};
+                    float bn[3];
+                    normalize3(col, bn);
+                    loc[cc] = dot3(bn, dw);
+                }
+                normalize3(loc, dl);
+                // spherical_harmonics.wgsl:34-68
+                const float x = dl[0], y = dl[1], z = dl[2];
+                const float xx = x * x, yy = y * y, zz = z * z;
+                float basis[16];
+                basis[0] = 1.0f;
+                basis[1] = y; basis[2] = z; basis[3] = x;
+                basis[4] = x * y; basis[5] = y * z; basis[6] = (2.0f * zz - xx) - yy;
+                basis[7] = x * z; basis[8] = xx - yy;
+                basis[9] = y * (3.0f * xx - yy);
+                basis[10] = (x * y) * z;
+                basis[11] = y * ((4.0f * zz - xx) - yy);
+                basis[12] = z * ((2.0f * zz - 3.0f * xx) - 3.0f * yy);
+                basis[13] = x * ((4.0f * zz - xx) - yy);
+                basis[14] = z * (xx - yy);
+                basis[15] = x * (xx - 3.0f * yy);
+#pragma unroll
+                for (int cc = 0; cc < 3; ++cc) {
+                    float acc = 0.5f;
+#pragma unroll
+                    for (int kk = 0; kk < 16; ++kk) acc += (c_shc[kk] * sh[3 * kk + cc]) * basis[kk];
+                    rgb[cc] = acc;
+                }
+                if (fc.color_space == 0u) {
+#pragma unroll
+                    for (int cc = 0; cc < 3; ++cc) rgb[cc] = srgb_to_linear(rgb[cc]);
+                }
+            } else if (fc.rasterize_mode == BGS_RASTERIZE_NORMAL) {
+                // gaussian.wgsl:350-368
+                float SR[3], Ln[3], wn[4];
+#pragma unroll
+                for (int i = 0; i < 3; ++i) SR[i] = sc[i] * Rm[i][2];
+#pragma unroll
+                for (int i = 0; i < 3; ++i) Ln[i] = (A[i][0] * SR[0] + A[i][1] * SR[1]) + A[i][2] * SR[2];
+                mat4_dir(fc.view_from_world, Ln[0], Ln[1], Ln[2], wn);
+                const float l = sqrtf(((wn[0] * wn[0] + wn[1] * wn[1]) + wn[2] * wn[2]) + wn[3] * wn[3]);
+#pragma unroll
+                for (int cc = 0; cc < 3; ++cc) rgb[cc] = 0.5f * (wn[cc] / l + 1.0f);
+            }
+            rec.r = rgb[0]; rec.g = rgb[1]; rec.b = rgb[2];
+            if (fc.draw_mode == BGS_DRAW_HIGHLIGHT_SELECTED && p4.w > 0.5f) {   // gaussian.wgsl:423-427
+                rec.r = 0.3f; rec.g = 1.0f; rec.b = 0.1f; rec.op = 1.0f;
+            }
+        }
+        // 48 B record, three 16 B stores
+        float4* out = reinterpret_cast<float4*>(recs + r);
+        out[0] = make_float4(rec.cx, rec.cy, rec.ux, rec.uy);
+        out[1] = make_float4(rec.vx, rec.vy, __uint_as_float(rec.bx), __uint_as_float(rec.by));
+        out[2] = make_float4(rec.r, rec.g, rec.b, rec.op);
+    }
+}
+
+void launch_project(bool f16, const float4* pos, const void* sh, const void* rot, const void* so,
+                    const uint32_t* sorted_ids, const FrameCounters* ctr, const FrameConsts& fc, SplatRec* recs,
+                    uint32_t n_upper, int sm_count, cudaStream_t stream) {
+    uint32_t blocks = (n_upper + 127) / 128;
+    const uint32_t cap_blocks = (uint32_t)sm_count * 8u;
+    if (blocks > cap_blocks) blocks = cap_blocks;
+    if (blocks == 0) blocks = 1;
+    if (f16) project_kernel<true><<<blocks, 128, 0, stream>>>(pos, sh, rot, so, sorted_ids, ctr, fc, recs);
+    else project_kernel<false><<<blocks, 128, 0, stream>>>(pos, sh, rot, so, sorted_ids, ctr, fc, recs);
+}
+
+}  // namespace bgs

@@ -1,0 +1,105 @@
+// raster.cu -- stage 5: per-16x16-tile front-to-back alpha blend.
+//
+// Replaces the reference's instanced-quad draw + fixed-function ROP blending
+// (vs_points/fs_main, src/render/gaussian.wgsl:185-505; PREMULTIPLIED_ALPHA_BLENDING applied
+// far->near, src/render/mod.rs:944-948).  Per pixel, the same coverage rule (pixel centre inside
+// the splat's OBB quad, |u|<=1 and |v|<=1), the same falloff (alpha = min(exp(-4.5|uv|^2) * o *
+// g_o, 0.999), gaussian.wgsl:474-504) and the same "over" operator, evaluated front-to-back:
+//   C = sum_j rgb_j a_j T_j,  T_j = prod_{k nearer}(1 - a_k);   out = C + T*background(=0), a=1.
+// A pixel stops once T < 1e-4; a tile stops when all its pixels have stopped (block vote).
+//
+// One CTA per tile, 256 threads = 8 warps, each warp owning an 8x4-pixel sub-rectangle so a
+// warp-uniform bbox test skips splats that cannot touch any of its 32 pixels.  The tile's slice
+// of the sorted pair list is staged through shared memory in chunks of 256 records.
+// Coverage maths uses explicit __fmul_rn/__fmaf_rn so u,v are bit-identical to the oracle.
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+
+namespace bgs {
+
+constexpr int RT_THREADS = 256;
+constexpr int RT_CHUNK = 256;
+
+__device__ __forceinline__ float linear_to_srgb(float c) {
+    c = fminf(fmaxf(c, 0.0f), 1.0f);
+    return c <= 0.0031308f ? 12.92f * c : 1.055f * powf(c, 1.0f / 2.4f) - 0.055f;
+}
+
+__global__ void __launch_bounds__(RT_THREADS)
+raster_kernel(const SplatRec* __restrict__ recs, const uint32_t* __restrict__ tile_entries,
+              const uint2* __restrict__ ranges, int W, int H, int tiles_x, void* __restrict__ out, uint32_t format) {
+    __shared__ float4 s_q0[RT_CHUNK];   // cx, cy, ux, uy
+    __shared__ float4 s_q1[RT_CHUNK];   // vx, vy, bbox x, bbox y
+    __shared__ float4 s_q2[RT_CHUNK];   // r, g, b, opacity
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int tile = blockIdx.x;
+    const int tile_x = tile % tiles_x, tile_y = tile / tiles_x;
+    // warp w covers the 8x4 rectangle at ((w & 1) * 8, (w >> 1) * 4) of the tile
+    const int wx0 = tile_x * TILE_PX + (warp & 1) * 8, wy0 = tile_y * TILE_PX + (warp >> 1) * 4;
+    const int px = wx0 + (lane & 7), py = wy0 + (lane >> 3);
+    const bool inside = px < W && py < H;
+    const float fx = (float)px + 0.5f, fy = (float)py + 0.5f;
+    const uint2 range = ranges[tile];
+
+    float T = 1.0f, cr = 0.0f, cg = 0.0f, cb = 0.0f;
+    bool done = !inside;
+    for (uint32_t base = range.x; base < range.y; base += RT_CHUNK) {
+        if (__syncthreads_count(done ? 0 : 1) == 0) break;   // also fences reuse of the staging buffers
+        const uint32_t cnt = min((uint32_t)RT_CHUNK, range.y - base);
+        if ((uint32_t)t < cnt) {
+            const uint32_t r = __ldg(tile_entries + base + t);
+            const float4* rp = reinterpret_cast<const float4*>(recs + r);
+            s_q0[t] = __ldg(rp);
+            s_q1[t] = __ldg(rp + 1);
+            s_q2[t] = __ldg(rp + 2);
+        }
+        __syncthreads();
+        if (!done) {
+            for (uint32_t j = 0; j < cnt; ++j) {
+                const float4 q1 = s_q1[j];
+                const uint32_t bx = __float_as_uint(q1.z), by = __float_as_uint(q1.w);
+                // warp-uniform reject: splat bbox vs this warp's 8x4 pixel rectangle
+                if ((int)(bx >> 16) < wx0 || (int)(bx & 0xFFFFu) > wx0 + 7 || (int)(by >> 16) < wy0 ||
+                    (int)(by & 0xFFFFu) > wy0 + 3)
+                    continue;
+                const float4 q0 = s_q0[j];
+                const float dx = __fsub_rn(fx, q0.x), dy = __fsub_rn(fy, q0.y);
+                const float u = __fmaf_rn(q0.w, dy, __fmul_rn(q0.z, dx));
+                const float v = __fmaf_rn(q1.y, dy, __fmul_rn(q1.x, dx));
+                if (fabsf(u) <= 1.0f && fabsf(v) <= 1.0f) {
+                    const float qd = __fmaf_rn(v, v, __fmul_rn(u, u));
+                    const float4 q2 = s_q2[j];
+                    const float a = fminf(__expf(-4.5f * qd) * q2.w, 0.999f);
+                    const float w = a * T;
+                    cr = fmaf(w, q2.x, cr); cg = fmaf(w, q2.y, cg); cb = fmaf(w, q2.z, cb);
+                    T *= (1.0f - a);
+                    if (T < T_STOP) { done = true; break; }
+                }
+            }
+        }
+    }
+    if (!inside) return;
+    const size_t pix = (size_t)py * W + px;
+    if (format == BGS_FORMAT_RGBA32F) {
+        reinterpret_cast<float4*>(out)[pix] = make_float4(cr, cg, cb, 1.0f);
+    } else if (format == BGS_FORMAT_RGBA16F) {
+        const __half2 lo = __floats2half2_rn(cr, cg), hi = __floats2half2_rn(cb, 1.0f);
+        uint2 o;
+        o.x = *reinterpret_cast<const uint32_t*>(&lo);
+        o.y = *reinterpret_cast<const uint32_t*>(&hi);
+        reinterpret_cast<uint2*>(out)[pix] = o;
+    } else {
+        const uint32_t r8 = (uint32_t)(linear_to_srgb(cr) * 255.0f + 0.5f);
+        const uint32_t g8 = (uint32_t)(linear_to_srgb(cg) * 255.0f + 0.5f);
+        const uint32_t b8 = (uint32_t)(linear_to_srgb(cb) * 255.0f + 0.5f);
+        reinterpret_cast<uint32_t*>(out)[pix] = r8 | (g8 << 8) | (b8 << 16) | 0xFF000000u;
+    }
+}
+
+void launch_raster(const SplatRec* recs, const uint32_t* tile_entries, const uint2* ranges, int W, int H, int tiles_x,
+                   int tiles_y, void* out, uint32_t format, cudaStream_t stream) {
+    raster_kernel<<<tiles_x * tiles_y, RT_THREADS, 0, stream>>>(recs, tile_entries, ranges, W, H, tiles_x, out, format);
+}
+
+}  // namespace bgs

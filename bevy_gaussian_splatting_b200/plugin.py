@@ -1,0 +1,180 @@
+"""Python host mirror of the plugin surface for the forward splat path.
+
+Reference: `GaussianSplattingPlugin` (src/lib.rs:48-80) wires, for this path, the render-world
+system `run_radix_sort` (src/sort/radix.rs:616-756) and the `DrawGaussians` render command
+(src/render/mod.rs:986-992,1501-1569), both invoked once per `GaussianCamera` view per frame over
+entities holding `(PlanarGaussian3dHandle, CloudSettings)`.  Here the same roles exist with the
+same names, but the per-view work is ONE call across the C ABI (`bgs_render`).
+
+This module is test/bench plumbing above the ABI (the production host stays Rust, see
+INTEGRATION.md); it never computes anything itself and has no fallback path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import dataclasses
+
+import numpy as np
+
+from . import abi
+from .camera import GaussianCamera, View
+from .gaussian import PlanarGaussian3d
+from .settings import CloudSettings
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+@dataclasses.dataclass
+class CloudTransform:
+    """GlobalTransform of the cloud entity -> CloudUniform.transform (render/mod.rs:1056-1072)."""
+
+    matrix: np.ndarray = dataclasses.field(default_factory=lambda: np.eye(4, dtype=np.float32))
+
+
+class PlanarGaussian3dHandle:
+    """A cloud resident in HBM (the role of `Handle<PlanarGaussian3d>` + its prepared GPU planes)."""
+
+    def __init__(self, plugin: "GaussianSplattingPlugin", cloud: PlanarGaussian3d, f16: bool = False):
+        self._plugin = plugin
+        self._lib = plugin._lib
+        self.n = len(cloud)
+        self.f16 = f16
+        self._h = C.c_void_p()
+        if f16:
+            sh_p, rso = cloud.pack_f16()
+            st = self._lib.bgs_cloud_upload_f16(plugin._ctx, self.n, _ptr(cloud.position_visibility), _ptr(sh_p),
+                                                _ptr(rso), C.byref(self._h))
+        else:
+            st = self._lib.bgs_cloud_upload_f32(plugin._ctx, self.n, _ptr(cloud.position_visibility),
+                                                _ptr(cloud.spherical_harmonic), _ptr(cloud.rotation),
+                                                _ptr(cloud.scale_opacity), C.byref(self._h))
+        plugin._check(st)
+
+    def destroy(self):
+        if self._h:
+            self._lib.bgs_cloud_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+
+class GaussianSplattingPlugin:
+    """Owns one `bgs_context` (one GPU).  `render_view` = run_radix_sort + DrawGaussians for one view."""
+
+    FORMATS = {"rgba8_srgb": (abi.BGS_FORMAT_RGBA8_SRGB, np.uint8, 4), "rgba16f": (abi.BGS_FORMAT_RGBA16F, np.float16, 4),
+               "rgba32f": (abi.BGS_FORMAT_RGBA32F, np.float32, 4)}
+
+    def __init__(self, cuda_device: int = 0):
+        self._lib = abi.load()
+        self._ctx = C.c_void_p()
+        st = self._lib.bgs_context_create(cuda_device, C.byref(self._ctx))
+        if st != abi.BGS_OK:
+            raise abi.BgsError(st, f"bgs_context_create(device={cuda_device}) failed (no usable CUDA device?)")
+        self.device = cuda_device
+
+    # -- resources
+    def add_cloud(self, cloud: PlanarGaussian3d, f16: bool = False) -> PlanarGaussian3dHandle:
+        return PlanarGaussian3dHandle(self, cloud, f16)
+
+    def _check(self, st: int):
+        if st != abi.BGS_OK:
+            raise abi.BgsError(st, (self._lib.bgs_last_error(self._ctx) or b"").decode())
+
+    @staticmethod
+    def cloud_uniform(settings: CloudSettings, transform: CloudTransform | None = None) -> abi.bgs_cloud_uniform:
+        u = abi.bgs_cloud_uniform()
+        m = (transform.matrix if transform is not None else np.eye(4, dtype=np.float32)).astype(np.float32)
+        u.transform[:] = m.T.reshape(-1).tolist()
+        u.global_opacity = settings.global_opacity
+        u.global_scale = settings.global_scale
+        u.color_space = int(settings.color_space)
+        u.time = settings.time
+        return u
+
+    # -- the per-view, per-frame call
+    def render_view(self, handle: PlanarGaussian3dHandle, settings: CloudSettings, view: View,
+                    camera: GaussianCamera | None = None, transform: CloudTransform | None = None,
+                    fmt: str = "rgba32f", out: np.ndarray | None = None, to_host: bool = True):
+        """Returns the (H, W, 4) frame (host) or None when `to_host` is False / the camera is warming up."""
+        if camera is not None and camera.warmup:   # queue_gaussians skips warm-up cameras (render/mod.rs:361-371)
+            return None
+        code, dtype, ch = self.FORMATS[fmt]
+        v = view.to_abi()
+        u = self.cloud_uniform(settings, transform)
+        s = settings.to_abi()
+        if to_host:
+            if out is None:
+                out = np.empty((view.height, view.width, ch), dtype)
+            assert out.dtype == dtype and out.size == view.height * view.width * ch and out.flags.c_contiguous
+            st = self._lib.bgs_render(self._ctx, handle._h, C.byref(v), C.byref(u), C.byref(s), _ptr(out), code, 0)
+        else:
+            st = self._lib.bgs_render(self._ctx, handle._h, C.byref(v), C.byref(u), C.byref(s), None, code, 0)
+        self._check(st)
+        return out if to_host else None
+
+    # -- parity / measurement hooks
+    def frame_stats(self) -> abi.bgs_frame_stats:
+        fs = abi.bgs_frame_stats()
+        self._check(self._lib.bgs_frame_stats_get(self._ctx, C.byref(fs)))
+        return fs
+
+    def stage_times_us(self) -> np.ndarray:
+        arr = (C.c_float * 6)()
+        self._check(self._lib.bgs_stage_times_us(self._ctx, C.byref(arr)))
+        return np.array(list(arr), np.float32)
+
+    def sorted_entries(self) -> np.ndarray:
+        n = self.frame_stats().n
+        out = np.empty((n, 2), np.uint32)
+        self._check(self._lib.bgs_debug_sorted_entries(self._ctx, _ptr(out)))
+        return out
+
+    def tile_ranges(self) -> np.ndarray:
+        fs = self.frame_stats()
+        out = np.empty((fs.tiles_x * fs.tiles_y, 2), np.uint32)
+        self._check(self._lib.bgs_debug_tile_ranges(self._ctx, _ptr(out)))
+        return out
+
+    def tile_entries(self) -> np.ndarray:
+        fs = self.frame_stats()
+        out = np.empty((fs.n_pairs,), np.uint32)
+        if fs.n_pairs:
+            self._check(self._lib.bgs_debug_tile_entries(self._ctx, _ptr(out), fs.n_pairs))
+        return out
+
+    def projected(self):
+        fs = self.frame_stats()
+        rec = np.empty((fs.n_visible, 12), np.float32)
+        ids = np.empty((fs.n_visible,), np.uint32)
+        if fs.n_visible:
+            self._check(self._lib.bgs_debug_projected(self._ctx, _ptr(rec), _ptr(ids)))
+        return rec, ids
+
+    @property
+    def stream_ptr(self) -> int:
+        return int(self._lib.bgs_context_stream(self._ctx) or 0)
+
+    @property
+    def frame_device_ptr(self) -> int:
+        return int(self._lib.bgs_frame_device_ptr(self._ctx) or 0)
+
+    @property
+    def last_launch_count(self) -> int:
+        return int(self._lib.bgs_last_launch_count(self._ctx))
+
+    def destroy(self):
+        if self._ctx:
+            self._lib.bgs_context_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass

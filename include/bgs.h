@@ -1,0 +1,145 @@
+/*
+ * bgs.h -- C ABI of the B200-native forward splat path (libbgs.so).
+ *
+ * Drop-in boundary for mosure/bevy_gaussian_splatting's per-view, per-frame GPU work.
+ * One Rust render-world system calls bgs_render() in place of BOTH reference call sites:
+ *   - system  run_radix_sort::<R>                 (src/sort/radix.rs:616-756, scheduled :97-118)
+ *   - command DrawGaussians<R> / DrawGaussianInstanced::render
+ *                                                 (src/render/mod.rs:986-992, :1501-1569)
+ * The Bevy plugin surface (GaussianSplattingPlugin, PlanarGaussian3dHandle, CloudSettings,
+ * GaussianCamera) stays Rust; see INTEGRATION.md for the binding and the system that calls this.
+ *
+ * Conventions: plain pointers and sizes only; host arrays are borrowed for the duration of the
+ * call; device memory is library-owned; every entry point returns a bgs_status and never
+ * aborts or throws across the boundary.  A context is single-threaded (Bevy's render thread);
+ * distinct contexts (one per GPU) may be used concurrently.  Matrices are column-major f32,
+ * exactly as Bevy's `View` uniform / `CloudUniform` hold them.
+ */
+#ifndef BGS_H
+#define BGS_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct bgs_context bgs_context; /* opaque, library-owned */
+typedef struct bgs_cloud bgs_cloud;     /* opaque, library-owned */
+
+typedef enum {
+    BGS_OK = 0,
+    BGS_NOT_READY = 1, /* maps to the reference's silent skip-frame (radix.rs:645-658, mod.rs:1533-1539) */
+    BGS_EINVAL = 2,
+    BGS_ECUDA = 3,
+    BGS_ENOMEM = 4,
+    BGS_ENCCL = 5
+} bgs_status;
+
+/* The Bevy `View` uniform fields the path reads (src/render/bindings.wgsl:3-9;
+ * helpers.wgsl:18-38, transform.wgsl:6, gaussian_2d.wgsl:104, radix.wgsl:92). */
+typedef struct {
+    float view_from_world[16];
+    float clip_from_view[16];
+    float clip_from_world[16]; /* used as unjittered_clip_from_world and clip_from_world */
+    float world_position[3];
+    float viewport[4]; /* x, y, w, h (px); the frame is w x h */
+} bgs_view;
+
+/* CloudUniform (src/render/mod.rs:995-1009, bindings.wgsl:13-26), fields this path reads. */
+typedef struct {
+    float transform[16]; /* model -> world */
+    float global_opacity;
+    float global_scale;
+    uint32_t color_space; /* GaussianColorSpace: 0 SrgbRec709Display, 1 LinRec709Display */
+    float time;
+} bgs_cloud_uniform;
+
+/* CloudSettings / CloudPipelineKey (src/gaussian/settings.rs:90-133, render/mod.rs:898-909). */
+enum { BGS_GAUSSIAN_2D = 0, BGS_GAUSSIAN_3D = 1 };
+enum { BGS_RASTERIZE_COLOR = 0, BGS_RASTERIZE_DEPTH = 1, BGS_RASTERIZE_NORMAL = 2 };
+enum { BGS_DRAW_ALL = 0, BGS_DRAW_SELECTED = 1, BGS_DRAW_HIGHLIGHT_SELECTED = 2 };
+enum {
+    BGS_FLAG_SORT_ALL = 1u /* sort all N entries like the reference (culled keyed 0xFFFFFFFF)
+                              instead of stream-compacting the visible ones first; same output */
+};
+typedef struct {
+    uint32_t gaussian_mode;           /* BGS_GAUSSIAN_* */
+    uint32_t rasterize_mode;          /* BGS_RASTERIZE_* */
+    uint32_t aabb;                    /* 0 = USE_OBB (default), 1 = USE_AABB */
+    uint32_t opacity_adaptive_radius; /* default 1 */
+    uint32_t draw_mode;               /* BGS_DRAW_* */
+    uint32_t radix_sort_depth_bits;   /* 16 | 24 | 32 (RadixSortDepthBits) */
+    uint32_t flags;                   /* BGS_FLAG_* */
+    uint32_t reserved;
+} bgs_settings;
+
+/* Output frame formats.  RGBA8_SRGB / RGBA16F mirror the reference targets
+ * (Rgba8UnormSrgb / Rgba16Float, render/mod.rs:917-921); RGBA32F is the premultiplied linear
+ * accumulator parity is judged on. */
+enum { BGS_FORMAT_RGBA8_SRGB = 0, BGS_FORMAT_RGBA16F = 1, BGS_FORMAT_RGBA32F = 2 };
+
+typedef struct {
+    uint32_t n;          /* gaussians in the cloud */
+    uint32_t n_visible;  /* in-frustum gaussians this frame */
+    uint64_t n_pairs;    /* (splat, tile) intersections this frame */
+    uint32_t tiles_x, tiles_y;
+    uint32_t width, height;
+} bgs_frame_stats;
+
+bgs_status bgs_context_create(int cuda_device, bgs_context** out);
+void bgs_context_destroy(bgs_context* ctx);
+
+/* Planar SoA upload, f32 layout (240 B/gaussian): planar_3d.rs:45-54, f32.rs:53-175.
+ * pos_vis n*4 (x,y,z,visibility); sh n*48 (interleaved RGB x16); rot n*4 (w,x,y,z);
+ * scale_opacity n*4 (linear scale xyz, linear opacity). */
+bgs_status bgs_cloud_upload_f32(bgs_context* ctx, uint32_t n, const float* pos_vis, const float* sh,
+                                const float* rot_wxyz, const float* scale_opacity, bgs_cloud** out);
+/* f16 planar layout (128 B/gaussian): f16.rs:30-56,244-263; planar.wgsl:117-176.
+ * sh_packed n*24 words (even coefficient in the low half); rot_scale_opacity n*4 words. */
+bgs_status bgs_cloud_upload_f16(bgs_context* ctx, uint32_t n, const float* pos_vis, const uint32_t* sh_packed,
+                                const uint32_t* rot_scale_opacity, bgs_cloud** out);
+void bgs_cloud_destroy(bgs_cloud* cloud);
+
+/* One view of one cloud: key-gen -> depth radix sort -> projection + SH colour -> tile
+ * binning -> per-tile front-to-back blend.  out_rgba is caller-owned (host pointer, or a
+ * device pointer when out_is_device_ptr != 0); may be NULL to keep the frame on the device. */
+bgs_status bgs_render(bgs_context* ctx, const bgs_cloud* cloud, const bgs_view* view,
+                      const bgs_cloud_uniform* uniform, const bgs_settings* settings, void* out_rgba,
+                      uint32_t out_format, int out_is_device_ptr);
+
+/* Parity / debug hooks (valid after a bgs_render on this context). */
+/* n*2 words (key, index): the reference's sorted_entry_buffer (sort/mod.rs:323-329). */
+bgs_status bgs_debug_sorted_entries(bgs_context* ctx, uint32_t* key_index_pairs);
+/* tiles*2 words (start, end) into the per-tile entry list. */
+bgs_status bgs_debug_tile_ranges(bgs_context* ctx, uint32_t* start_end);
+/* n_pairs words: front-to-back rank of each (tile, splat) pair, tile-major. */
+bgs_status bgs_debug_tile_entries(bgs_context* ctx, uint32_t* ranks, uint64_t capacity);
+/* n_visible records of 12 floats: cx, cy, ux, uy, vx, vy, bbox(2 words), r, g, b, opacity;
+ * and n_visible gaussian indices (front-to-back rank -> index). */
+bgs_status bgs_debug_projected(bgs_context* ctx, float* records, uint32_t* rank_to_index);
+bgs_status bgs_frame_stats_get(bgs_context* ctx, bgs_frame_stats* out);
+
+/* Last frame's stage times (CUDA events on the context stream), microseconds:
+ * [0] key-gen, [1] depth sort, [2] projection, [3] binning + tile sort + ranges,
+ * [4] raster, [5] whole frame. */
+bgs_status bgs_stage_times_us(bgs_context* ctx, float out[6]);
+const char* bgs_last_error(const bgs_context* ctx);
+/* The CUDA stream (cudaStream_t) all of this context's work is launched on. */
+void* bgs_context_stream(bgs_context* ctx);
+/* Device pointer of the last frame in `out_format` layout (valid until the next render). */
+const void* bgs_frame_device_ptr(bgs_context* ctx);
+/* Kernel launches issued by the last bgs_render. */
+uint32_t bgs_last_launch_count(const bgs_context* ctx);
+
+/* Multi-GPU (one view per GPU, replicated cloud): gather every rank's frame to `root`.
+ * nccl_comm is an ncclComm_t.  Runs on the context stream. */
+bgs_status bgs_nccl_unique_id(void* out_id128 /* 128 bytes */);
+bgs_status bgs_nccl_comm_init(bgs_context* ctx, int nranks, int rank, const void* id128, void** out_comm);
+void bgs_nccl_comm_destroy(void* nccl_comm);
+bgs_status bgs_gather_frames(bgs_context* ctx, void* nccl_comm, int root, const void* local_frame,
+                             void* all_frames, size_t bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
