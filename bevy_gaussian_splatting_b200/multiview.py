@@ -1,0 +1,88 @@
+"""Multi-GPU view batch: one process per GPU, the cloud replicated on every GPU,
+rank r renders view r, and ONE collective per frame gathers the finished frames on `root`.
+
+torch.distributed is plumbing only (rendezvous + broadcasting the 128-byte NCCL unique id); the
+frame gather itself is `bgs_gather_frames` (ncclSend/ncclRecv on the render stream, libbgs).  With
+backend="gloo" (CPU tests of the host logic, no GPU) the same rank/view/ordering logic runs over
+host tensors; that path never renders anything.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import abi
+from .camera import View, orbit_view
+
+
+def view_for_rank(rank: int, world: int, width: int = 1920, height: int = 1080) -> View:
+    """Config C5: `world` cameras on a circle of radius 5 around (0, 1.5, 0); rank r gets camera r."""
+    return orbit_view(rank, world, width, height)
+
+
+def broadcast_unique_id(make_id, rank: int, root: int = 0) -> bytes:
+    """Root creates the 128-byte id (make_id() -> bytes), everyone receives it via torch.distributed."""
+    import torch
+    import torch.distributed as dist
+
+    buf = torch.zeros(128, dtype=torch.uint8)
+    if rank == root:
+        raw = make_id()
+        assert len(raw) == 128
+        buf = torch.frombuffer(bytearray(raw), dtype=torch.uint8).clone()
+    if dist.get_backend() == "nccl":
+        dev = torch.device("cuda", torch.cuda.current_device())
+        t = buf.to(dev)
+        dist.broadcast(t, src=root)
+        buf = t.cpu()
+    else:
+        dist.broadcast(buf, src=root)
+    return bytes(buf.numpy().tobytes())
+
+
+class MultiViewSession:
+    def __init__(self, rank: int, world: int, root: int = 0, plugin=None):
+        self.rank, self.world, self.root, self.plugin = rank, world, root, plugin
+        self._comm = C.c_void_p()
+        self._lib = None
+        if plugin is not None:
+            self._lib = plugin._lib
+
+            def make_id():
+                raw = (C.c_ubyte * 128)()
+                st = self._lib.bgs_nccl_unique_id(raw)
+                if st != abi.BGS_OK:
+                    raise abi.BgsError(st, "bgs_nccl_unique_id failed (libnccl.so.2 not loadable?)")
+                return bytes(raw)
+
+            ident = broadcast_unique_id(make_id, rank, root)
+            idbuf = (C.c_ubyte * 128).from_buffer_copy(ident)
+            st = self._lib.bgs_nccl_comm_init(plugin._ctx, world, rank, idbuf, C.byref(self._comm))
+            if st != abi.BGS_OK:
+                raise abi.BgsError(st, "bgs_nccl_comm_init failed")
+
+    def view(self, width: int = 1920, height: int = 1080) -> View:
+        return view_for_rank(self.rank, self.world, width, height)
+
+    def gather_device(self, local_ptr: int, all_ptr: int, nbytes: int) -> None:
+        """Enqueue the gather on the context's stream (device pointers)."""
+        st = self._lib.bgs_gather_frames(self.plugin._ctx, self._comm, self.root, C.c_void_p(local_ptr),
+                                         C.c_void_p(all_ptr) if all_ptr else None, nbytes)
+        if st != abi.BGS_OK:
+            raise abi.BgsError(st, "bgs_gather_frames failed")
+
+    def gather_host(self, frame: np.ndarray):
+        """gloo stand-in used by the CPU tests: same ordering contract (frames[r] = rank r's frame)."""
+        import torch
+        import torch.distributed as dist
+
+        t = torch.from_numpy(np.ascontiguousarray(frame))
+        out = [torch.empty_like(t) for _ in range(self.world)] if self.rank == self.root else None
+        dist.gather(t, out, dst=self.root)
+        return None if out is None else np.stack([o.numpy() for o in out])
+
+    def destroy(self):
+        if self._comm and self._lib is not None:
+            self._lib.bgs_nccl_comm_destroy(self._comm)
+            self._comm = C.c_void_p()

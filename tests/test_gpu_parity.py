@@ -1,0 +1,216 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (ctypes -> libbgs.so), against
+the CPU oracle on the same seeded inputs.  Bar (BASELINE.json north_star): radix order and tile
+ranges BIT-EXACT; per-pixel RGBA within 1e-3 L-inf (f32 accumulators).  Full-size configurations are
+covered through size-independent properties (sortedness, permutation, range partition, idempotence,
+compaction == sort-all)."""
+import numpy as np
+import pytest
+
+import bevy_gaussian_splatting_b200 as B
+
+pytestmark = pytest.mark.gpu
+
+PIXEL_TOL = 1e-3   # north_star: per-pixel RGBA within 1e-3 L-inf (f32)
+
+
+@pytest.fixture(scope="module")
+def plugin():
+    p = B.GaussianSplattingPlugin(0)
+    yield p
+    p.destroy()
+
+
+def _uniform(s):
+    return B.GaussianSplattingPlugin.cloud_uniform(s)
+
+
+def check_against_oracle(plugin, oracle, cloud, settings, view, f16=False, pixel_tol=PIXEL_TOL):
+    h = plugin.add_cloud(cloud, f16=f16)
+    try:
+        img = plugin.render_view(h, settings, view, fmt="rgba32f")
+        oc = cloud.rounded_to_f16() if f16 else cloud
+        u = _uniform(settings)
+        bits = int(settings.radix_sort_depth_bits)
+        keys = oracle.keygen(oc.position_visibility, view.to_abi(), u, bits)
+        sk, si = oracle.radix_sort(keys, bits)
+        got = plugin.sorted_entries()
+        assert np.array_equal(got[:, 0], sk), "sorted keys differ (must be bit-exact)"
+        assert np.array_equal(got[:, 1], si), "sort permutation differs (must be bit-exact)"
+        til = oracle.render_tiles(oc, view.to_abi(), u, settings.to_abi())
+        fs = plugin.frame_stats()
+        assert fs.n_visible == til["n_vis"] and fs.n_pairs == til["n_pairs"]
+        assert np.array_equal(plugin.tile_ranges(), til["tile_ranges"]), "tile ranges differ (must be bit-exact)"
+        assert np.array_equal(plugin.tile_entries(), til["tile_entries"]), "per-tile slices differ"
+        rec, ids = plugin.projected()
+        assert np.array_equal(ids, til["rank_to_id"])
+        orec = oracle.project(oc, view.to_abi(), u, settings.to_abi(), til["rank_to_id"])
+        drawn = orec["xlo"] <= orec["xhi"]
+        geo = np.stack([orec[k] for k in ("cx", "cy", "ux", "uy", "vx", "vy")], 1)
+        assert np.array_equal(rec[drawn, :6].view(np.uint32), geo[drawn].view(np.uint32)), "projected geometry not bit-exact"
+        bb = rec[:, 6:8].view(np.uint32)
+        assert np.array_equal(bb[drawn, 0], (orec["xlo"][drawn].astype(np.uint32) | (orec["xhi"][drawn].astype(np.uint32) << 16)))
+        assert np.array_equal(bb[drawn, 1], (orec["ylo"][drawn].astype(np.uint32) | (orec["yhi"][drawn].astype(np.uint32) << 16)))
+        assert np.all((bb[~drawn, 0] & 0xFFFF) > (bb[~drawn, 0] >> 16))      # empty bbox where the oracle's is
+        if drawn.any():
+            col = np.stack([orec[k] for k in ("r", "g", "b", "op")], 1)
+            assert np.abs(rec[drawn, 8:12] - col[drawn]).max() <= 1e-4
+        err = float(np.abs(img - til["image"]).max())
+        assert err <= pixel_tol, f"pixel L-inf {err}"
+        return img, til
+    finally:
+        h.destroy()
+
+
+CASES = [
+    # n, w, h, scale, f16, bits, sort_all
+    (1000, 256, 256, 1.0, False, 32, False),      # config C1
+    (1000, 256, 256, 1.0, True, 32, False),
+    (20000, 320, 200, 0.25, False, 32, False),
+    (20000, 320, 200, 0.25, False, 32, True),
+    (60000, 640, 360, 0.1, True, 32, False),
+    (60000, 333, 177, 0.1, False, 24, False),     # viewport not a multiple of 16; 3-pass keys
+    (60000, 333, 177, 0.1, False, 16, False),     # 2-pass keys (close depths collapse: stability matters)
+    (60000, 640, 360, 0.05, True, 16, True),
+    (8191, 64, 64, 0.5, False, 32, False),        # ragged tile counts everywhere
+    (4097, 17, 9, 0.5, False, 32, True),          # tiny viewport
+]
+
+
+@pytest.mark.parametrize("n,w,h,scale,f16,bits,sort_all", CASES)
+def test_parity_vs_oracle(plugin, oracle, n, w, h, scale, f16, bits, sort_all):
+    cloud = B.random_gaussians_3d_seeded(n, n % 7)
+    s = B.CloudSettings(global_scale=scale, radix_sort_depth_bits=B.RadixSortDepthBits(bits), sort_all=sort_all)
+    check_against_oracle(plugin, oracle, cloud, s, B.headless_view(w, h), f16=f16)
+
+
+def test_parity_settings_variants(plugin, oracle):
+    cloud = B.random_gaussians_3d_seeded(15000, 11)
+    view = B.orbit_view(3, 8, 400, 240)
+    for kw in (dict(opacity_adaptive_radius=False), dict(global_opacity=1.8), dict(color_space=B.GaussianColorSpace.LinRec709Display),
+               dict(rasterize_mode=B.RasterizeMode.Normal), dict(draw_mode=B.DrawMode.HighlightSelected)):
+        s = B.CloudSettings(global_scale=0.2, **kw)
+        check_against_oracle(plugin, oracle, cloud, s, view)
+
+
+def test_parity_model_transform_and_draw_selected(plugin, oracle):
+    cloud = B.random_gaussians_3d_seeded(12000, 5)
+    cloud.position_visibility[::3, 3] = 0.0          # a third of the cloud is "unselected"
+    m = np.eye(4, dtype=np.float32)
+    a = 0.7
+    m[:3, :3] = np.array([[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]], np.float32) * np.float32(1.3)
+    m[:3, 3] = [0.5, -0.25, 1.0]
+    view = B.headless_view(320, 180)
+    s = B.CloudSettings(global_scale=0.15, draw_mode=B.DrawMode.Selected)
+    h = plugin.add_cloud(cloud)
+    try:
+        img = plugin.render_view(h, s, view, transform=B.CloudTransform(m))
+        u = plugin.cloud_uniform(s, B.CloudTransform(m))
+        til = oracle.render_tiles(cloud, view.to_abi(), u, s.to_abi())
+        assert np.array_equal(plugin.tile_ranges(), til["tile_ranges"])
+        assert np.abs(img - til["image"]).max() <= PIXEL_TOL
+        keys = oracle.keygen(cloud.position_visibility, view.to_abi(), u, 32)
+        sk, si = oracle.radix_sort(keys, 32)
+        got = plugin.sorted_entries()
+        assert np.array_equal(got[:, 0], sk) and np.array_equal(got[:, 1], si)
+    finally:
+        h.destroy()
+
+
+def test_edge_cases(plugin, oracle):
+    view = B.headless_view(96, 64)
+    s = B.CloudSettings(global_scale=0.5)
+    # a single gaussian
+    one = B.PlanarGaussian3d(np.array([[0, 1.5, 0, 1]], np.float32), np.full((1, 48), 0.3, np.float32),
+                             np.array([[0.9, 0.1, 0.2, 0.3]], np.float32), np.array([[0.5, 0.2, 0.3, 0.7]], np.float32))
+    check_against_oracle(plugin, oracle, one, s, view)
+    # every gaussian culled (behind the camera): black frame, empty ranges
+    cloud = B.random_gaussians_3d_seeded(5000, 2)
+    cloud.position_visibility[:, 2] = np.abs(cloud.position_visibility[:, 2]) + 6.0
+    img, til = check_against_oracle(plugin, oracle, cloud, s, view)
+    assert plugin.frame_stats().n_visible == 0 and np.all(img[..., :3] == 0) and np.all(img[..., 3] == 1)
+    # degenerate inputs: zero opacity, zero scale, NaN position, identity rotation (NaN eigenvector quirk)
+    deg = B.random_gaussians_3d_seeded(3000, 4)
+    deg.scale_opacity[::5, 3] = 0.0
+    deg.scale_opacity[1::5, :3] = 0.0
+    deg.position_visibility[2::50, 0] = np.nan
+    deg.rotation[3::5] = [1, 0, 0, 0]
+    deg.scale_opacity[3::5, :3] = 0.3
+    check_against_oracle(plugin, oracle, deg, s, view)
+
+
+def test_output_formats_agree(plugin):
+    cloud = B.random_gaussians_3d_seeded(30000, 9)
+    view = B.headless_view(320, 192)
+    s = B.CloudSettings(global_scale=0.3)
+    h = plugin.add_cloud(cloud)
+    try:
+        f32 = plugin.render_view(h, s, view, fmt="rgba32f")
+        f16 = plugin.render_view(h, s, view, fmt="rgba16f")
+        u8 = plugin.render_view(h, s, view, fmt="rgba8_srgb")
+        assert np.abs(f16.astype(np.float32) - f32).max() <= 4e-3 * max(1.0, np.abs(f32).max())
+        c = np.clip(f32[..., :3], 0, 1)
+        enc = np.where(c <= 0.0031308, 12.92 * c, 1.055 * np.power(c, 1 / 2.4) - 0.055) * 255
+        assert np.abs(u8[..., :3].astype(np.float32) - enc).max() <= 0.51
+        assert np.all(u8[..., 3] == 255)
+    finally:
+        h.destroy()
+
+
+def test_not_ready_and_bad_arguments(plugin):
+    import ctypes as C
+
+    from bevy_gaussian_splatting_b200 import abi
+
+    lib = abi.load()
+    v = B.headless_view(64, 64).to_abi(); s = B.CloudSettings().to_abi(); u = plugin.cloud_uniform(B.CloudSettings())
+    # cloud asset not ready -> the reference skips the frame (radix.rs:645-658)
+    assert lib.bgs_render(plugin._ctx, None, C.byref(v), C.byref(u), C.byref(s), None, 2, 0) == abi.BGS_NOT_READY
+    h = plugin.add_cloud(B.random_gaussians_3d_seeded(100, 0))
+    s.radix_sort_depth_bits = 20
+    assert lib.bgs_render(plugin._ctx, h._h, C.byref(v), C.byref(u), C.byref(s), None, 2, 0) == abi.BGS_EINVAL
+    assert b"radix_sort_depth_bits" in lib.bgs_last_error(plugin._ctx)
+    h.destroy()
+
+
+@pytest.mark.parametrize("n,f16,scale", [(1_000_000, False, 0.02), (6_000_000, True, 0.02)])
+def test_full_size_properties(plugin, n, f16, scale):
+    """Configs C2 / C3 at BASELINE.json's sizes: properties the oracle-free way."""
+    cloud = B.random_gaussians_3d_seeded(n, 0)
+    view = B.headless_view(1920, 1080)
+    h = plugin.add_cloud(cloud, f16=f16)
+    try:
+        s = B.CloudSettings(global_scale=scale)
+        img = plugin.render_view(h, s, view, fmt="rgba32f")
+        ent = plugin.sorted_entries()
+        fs = plugin.frame_stats()
+        nv = fs.n_visible
+        # sortedness + stability + permutation
+        k = ent[:, 0].astype(np.int64)
+        assert np.all(np.diff(k) >= 0)
+        ties = np.diff(k) == 0
+        assert np.all(np.diff(ent[:, 1].astype(np.int64))[ties] > 0), "ties must keep ascending index (stable)"
+        assert np.array_equal(np.sort(ent[:, 1]), np.arange(n, dtype=np.uint32))
+        assert np.all(ent[nv:, 0] == 0xFFFFFFFF) and np.all(ent[:nv, 0] != 0xFFFFFFFF)
+        # keys are the key formula of the positions (recomputed in numpy f32 for the visible head)
+        p = cloud.position_visibility[ent[:nv, 1], :3]
+        d = p - np.array([0, 1.5, 5], np.float32)
+        d2 = (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]).astype(np.float32) + d[:, 2] * d[:, 2]
+        assert np.array_equal(0xFFFFFFFF - d2.astype(np.float32).view(np.uint32), ent[:nv, 0])
+        # tile ranges partition the pair list; slices ascend in rank
+        rng_ = plugin.tile_ranges().astype(np.int64)
+        assert int((rng_[:, 1] - rng_[:, 0]).sum()) == fs.n_pairs
+        ne = rng_[rng_[:, 1] > rng_[:, 0]]
+        assert np.all(ne[1:, 0] == ne[:-1, 1]) and ne[0, 0] == 0 and ne[-1, 1] == fs.n_pairs
+        te = plugin.tile_entries().astype(np.int64)
+        brk = np.zeros(len(te), bool); brk[ne[:, 0]] = True
+        assert np.all((np.diff(te) > 0) | brk[1:])
+        # idempotence, and stream-compaction mode == reference-literal sort-all mode
+        img2 = plugin.render_view(h, s, view, fmt="rgba32f")
+        assert np.array_equal(img, img2)
+        s_all = B.CloudSettings(global_scale=scale, sort_all=True)
+        img3 = plugin.render_view(h, s_all, view, fmt="rgba32f")
+        assert np.array_equal(img, img3)
+        assert np.array_equal(plugin.sorted_entries(), ent)
+        assert np.isfinite(img).all() and img[..., :3].max() > 0.05
+    finally:
+        h.destroy()
