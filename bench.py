@@ -1,0 +1,307 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the forward splat path (BASELINE.json metric).
+
+metric : rendered Msplats/sec @1080p, 6M-gaussian cloud  (= gaussians in the cloud x views / s)
+config : C3 of BASELINE.json -- 6 M synthetic random_gaussians, f16 planar (128 B/gaussian),
+         1920x1080, "Mip-NeRF-360-scale" = the generator's cloud with global_scale 0.02
+         (SURVEY.md §8d); one camera view per GPU, cloud replicated, frames gathered on rank 0.
+A step = one frame of every view: key-gen -> depth radix sort -> projection + SH colour -> tile
+binning -> tile blend (+ the NCCL frame gather when N > 1).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo (CUDA, through the C ABI)
+  python bench.py --impl reference --steps K --warmup W    # the reference's path on the host CPU
+                                                           # (oracle port: the reference cannot be built here)
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "rendered Msplats/sec @1080p, 6M-gaussian cloud"
+N_GAUSSIANS = 6_000_000
+WIDTH, HEIGHT = 1920, 1080
+GLOBAL_SCALE = 0.02
+WORKLOAD = ("C3: 6M random_gaussians (seed 0), f16 planar 128 B/gaussian, 1920x1080, global_scale=0.02 "
+            "(Mip-NeRF-360-scale), headless camera (0,1.5,5) / one orbit view per GPU")
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 9 for i in range(4) if r[5 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def make_cloud(n: int):
+    import bevy_gaussian_splatting_b200 as B
+
+    return B.random_gaussians_3d_seeded(n, 0)
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_run(steps: int, warmup: int, budget_s: float, cloud=None):
+    """The reference's path on the host CPU: oracle ref_mode (back-to-front instanced quads, exactly
+    the reference's blending semantics), OpenMP over all host cores.  kind = "port": the Rust/WGSL
+    reference cannot be built or run in this image."""
+    import bevy_gaussian_splatting_b200 as B
+    from oracle import oracle as O
+
+    if cloud is None:
+        cloud = make_cloud(N_GAUSSIANS)
+    cloud = cloud.rounded_to_f16()          # the f16 layout's behaviour: f32 maths on f16-rounded inputs
+    view = B.headless_view(WIDTH, HEIGHT)
+    s = B.CloudSettings(global_scale=GLOBAL_SCALE)
+    u = B.GaussianSplattingPlugin.cloud_uniform(s)
+    cores = O.num_threads()
+    # size the sample from one probe frame on a 1/6 prefix
+    n_probe = min(len(cloud), 1_000_000)
+    t0 = time.perf_counter()
+    O.render_ref(cloud.subset(n_probe), view.to_abi(), u, s.to_abi())
+    t_probe = time.perf_counter() - t0
+    est_full = t_probe * max(1.0, len(cloud) / n_probe) * 0.6 + 0.2
+    frames = steps + warmup
+    n_s = len(cloud)
+    if est_full * frames > budget_s:
+        n_s = int(max(250_000, min(len(cloud), len(cloud) * budget_s / (est_full * frames))))
+    sample = cloud.subset(n_s)
+    for _ in range(warmup):
+        O.render_ref(sample, view.to_abi(), u, s.to_abi())
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        O.render_ref(sample, view.to_abi(), u, s.to_abi())
+        times.append(time.perf_counter() - t0)
+    ms = 1000.0 * float(np.mean(times))
+    value = n_s / (ms / 1000.0) / 1e6
+    desc = (f"first {n_s} of the {len(cloud)} gaussians of the same cloud, full 1920x1080 frame, oracle ref_mode "
+            f"(key-gen + stable sort + back-to-front quad blending), {steps} frames after {warmup} warm-up")
+    return value, ms, cores, desc, n_s
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    value, ms, cores, desc, n_s = cpu_reference_run(args.steps, args.warmup, budget_s=150.0)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": "Msplats/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 3), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32 (f16-rounded inputs)", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample_gaussians": n_s},
+        "cpu_baseline": {"value": round(value, 3), "unit": "Msplats/s", "cores": cores, "kind": "port", "sample": desc},
+        "e2e": {"value": round(value, 3), "unit": "Msplats/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+def run_cuda(args):
+    import torch
+
+    import bevy_gaussian_splatting_b200 as B
+    from bevy_gaussian_splatting_b200 import abi
+    from bevy_gaussian_splatting_b200.multiview import MultiViewSession
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    plugin = B.GaussianSplattingPlugin(local_rank)
+    cloud = make_cloud(N_GAUSSIANS)
+    handle = plugin.add_cloud(cloud, f16=True)
+    settings = B.CloudSettings(global_scale=GLOBAL_SCALE)
+    sess = MultiViewSession(rank, world, 0, plugin=plugin if world > 1 else None)
+    view = sess.view(WIDTH, HEIGHT) if world > 1 else B.headless_view(WIDTH, HEIGHT)
+    frame_bytes = WIDTH * HEIGHT * 4
+    stream = torch.cuda.ExternalStream(plugin.stream_ptr, device=torch.device("cuda", local_rank))
+    all_frames = torch.empty(world * frame_bytes, dtype=torch.uint8, device="cuda") if (world > 1 and rank == 0) else None
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device():
+        plugin.render_view(handle, settings, view, fmt="rgba8_srgb", to_host=False)
+        if world > 1:
+            sess.gather_device(plugin.frame_device_ptr, all_frames.data_ptr() if all_frames is not None else 0, frame_bytes)
+
+    # ---- device-resident throughput ("value"): inputs (768 MB cloud >> 126 MB L2) already in HBM
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    frame_us, stage_rows = [], []
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_device()
+        st = plugin.stage_times_us()
+        frame_us.append(float(st[5])); stage_rows.append(st)
+    e1.record(stream)
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    clk = clocks.stop() if rank == 0 else None
+    ms_step = ms_total / args.steps
+    if dist is not None:
+        t = torch.tensor([ms_step], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_step = float(t.item())
+    launches_per_frame = plugin.last_launch_count
+    fs = plugin.frame_stats()
+    stage_med = np.median(np.array(stage_rows), axis=0)
+
+    # ---- end to end through the C ABI with HOST buffers: per step the view/uniform/settings structs go
+    #      host->device as kernel arguments and the finished RGBA8 frame comes back into pinned host memory
+    host_frame = torch.empty((HEIGHT, WIDTH, 4), dtype=torch.uint8).pin_memory().numpy()
+    for _ in range(min(3, args.warmup)):
+        plugin.render_view(handle, settings, view, fmt="rgba8_srgb", out=host_frame)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        plugin.render_view(handle, settings, view, fmt="rgba8_srgb", out=host_frame)
+        if world > 1:
+            sess.gather_device(plugin.frame_device_ptr, all_frames.data_ptr() if all_frames is not None else 0, frame_bytes)
+    barrier()
+    e2e_ms = 1000.0 * (time.perf_counter() - t0) / args.steps
+    if dist is not None:
+        t = torch.tensor([e2e_ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    h2d = sum(__import__("ctypes").sizeof(c) for c in (abi.bgs_view, abi.bgs_cloud_uniform, abi.bgs_settings))
+
+    if rank != 0:
+        sess.destroy()
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline (HBM): algorithmic bytes per launch / live CUDA-event duration of that launch
+    peak, peak_src = peaks()
+    n, nv, I = fs.n, fs.n_visible, int(fs.n_pairs)
+    depth_passes = 4
+    alg = {
+        "keygen": 16 * n + 8 * nv,                                        # positions in, compacted (key,id) out
+        "depth_sort": 4 * nv + depth_passes * 16 * nv,                    # histogram read + P x (8 in + 8 out)
+        "project": 4 * nv + (16 + 112) * nv + 48 * nv,                    # ids + f16 attrs (pos 16 + 16 + 96) + record
+        "bin": 8 * nv + 8 * I + (4 * I + 2 * 16 * I) + 4 * I + 8 * fs.tiles_x * fs.tiles_y,
+        "raster": 4 * I + 48 * I + 4 * WIDTH * HEIGHT,
+    }
+    names = ["keygen", "depth_sort", "project", "bin", "raster"]
+    stages = []
+    for i, nm in enumerate(names):
+        us = float(stage_med[i])
+        gbs = alg[nm] / (us * 1e-6) / 1e9 if us > 0 else 0.0
+        stages.append({"stage": nm, "us": round(us, 1), "alg_bytes": int(alg[nm]), "gbs": round(gbs, 1), "frac": round(gbs / peak, 4)})
+    dom = max(stages, key=lambda s: s["us"])
+    traffic_path = os.path.join(ROOT, "profiles", "traffic.json")
+    traffic = None
+    if os.path.exists(traffic_path):
+        traffic = json.load(open(traffic_path)).get(dom["stage"])
+    roofline = {"kernel": dom["stage"], "bound": "hbm", "achieved": dom["gbs"], "peak": peak, "unit": "GB/s",
+                "frac": dom["frac"], "traffic": traffic, "peak_source": peak_src,
+                "note": "dominant kernel by time; raster is ALU/SFU/shared-memory bound, not HBM bound -- see stages[]"}
+
+    # ---- CPU baseline beside it (rank 0, N=1 only): bounded sample, ~10-30 s of CPU work
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        v, ms, cores, desc, _ = cpu_reference_run(steps=3, warmup=1, budget_s=25.0, cloud=cloud)
+        cpu = {"value": round(v, 3), "unit": "Msplats/s", "cores": cores, "kind": "port", "sample": desc}
+
+    views = world
+    value = N_GAUSSIANS * views / (ms_step / 1000.0) / 1e6
+    line = {
+        "metric": METRIC, "value": round(value, 1), "unit": "Msplats/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32 (f16-packed inputs)", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "views": views, "parallelism": f"view-parallel x{world}, replicated cloud",
+                   "n_visible": nv, "n_pairs": I, "l2": "inputs larger than L2 (768 MB cloud vs 126 MB)",
+                   "frame_format": "rgba8_srgb"},
+        "frame_ms_p50": round(float(np.percentile(frame_us, 50)) / 1000.0, 4),
+        "frame_ms_p95": round(float(np.percentile(frame_us, 95)) / 1000.0, 4),
+        "fps_per_gpu": round(1000.0 / ms_step, 1),
+        "e2e": {"value": round(N_GAUSSIANS * views / (e2e_ms / 1000.0) / 1e6, 1), "unit": "Msplats/s",
+                "ms_per_step": round(e2e_ms, 4), "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": frame_bytes},
+        "gpu_launches": int(launches_per_frame * args.steps),
+        "roofline": roofline, "stages": stages, "cpu_baseline": cpu, "clocks": clk,
+    }
+    print(json.dumps(line), flush=True)
+    sess.destroy()
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_cuda(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())
