@@ -15,6 +15,10 @@ namespace bgs {
 void launch_keygen(const float4* pos, uint32_t n, const FrameConsts& fc, int sort_all, uint32_t* keys_out,
                    uint32_t* ids_out, uint32_t* status, FrameCounters* ctr, cudaStream_t stream);
 uint32_t keygen_num_tiles(uint32_t n);
+int keygen_coop_blocks_per_sm();
+cudaError_t launch_keygen_coop(const float4* pos, uint32_t n, const FrameConsts& fc, uint32_t* keys_tmp, uint32_t* keys_out,
+                               uint32_t* ids_out, uint32_t* block_cnt, FrameCounters* ctr, uint32_t grid,
+                               cudaStream_t stream);
 void launch_culled_flags(const float4* pos, uint32_t n, const FrameConsts& fc, uint32_t* flags, cudaStream_t stream);
 // radix.cu
 uint32_t radix_num_tiles(uint32_t capacity);
@@ -31,6 +35,10 @@ void launch_project(bool f16, const float4* pos, const void* sh, const void* rot
 void launch_bin_emit(const SplatRec* recs, FrameCounters* ctr, uint32_t* status, int tiles_x, uint32_t capacity,
                      uint32_t* pair_keys, uint32_t* pair_vals, uint32_t n_upper, int sm_count, cudaStream_t stream);
 uint32_t bin_num_tiles(uint32_t n);
+int bin_coop_blocks_per_sm();
+cudaError_t launch_bin_emit_coop(const SplatRec* recs, FrameCounters* ctr, uint32_t* block_cnt, int tiles_x,
+                                 uint32_t capacity, uint32_t* pair_keys, uint32_t* pair_vals, uint32_t grid,
+                                 cudaStream_t stream);
 void launch_tile_ranges(const uint32_t* sorted_tile_ids, const FrameCounters* ctr, uint2* ranges, uint32_t capacity,
                         int sm_count, cudaStream_t stream);
 // raster.cu
@@ -53,6 +61,8 @@ struct bgs_cloud {
 struct bgs_context {
     int device = 0;
     int sm_count = 148;
+    int coop = 0;                 // device supports cooperative launch
+    uint32_t kg_grid = 0, bin_grid = 0;   // co-resident grid sizes of the cooperative kernels
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[6] = {};
     char err[512] = {0};
@@ -163,8 +173,8 @@ bgs_status ensure_arena(bgs_context* c, uint32_t n, uint32_t pairs, uint32_t til
     size_t off = 0;
     const size_t o_ctr = off; off = align_up(off + sizeof(FrameCounters), 256);
     const size_t o_hist = off; off = align_up(off + 8 * 256 * 4, 256);
-    const size_t o_skg = off; off = align_up(off + (size_t)keygen_num_tiles(n) * 4, 256);
-    const size_t o_sbin = off; off = align_up(off + (size_t)bin_num_tiles(n) * 4, 256);
+    const size_t o_skg = off; off = align_up(off + ((size_t)keygen_num_tiles(n) + 4096) * 4, 256);
+    const size_t o_sbin = off; off = align_up(off + ((size_t)bin_num_tiles(n) + 4096) * 4, 256);
     const size_t o_rng = off; off = align_up(off + (size_t)tiles * 8, 256);
     const size_t o_sd = off; off = align_up(off + (size_t)4 * radix_num_tiles(n) * 256 * 4, 256);
     const size_t o_sp = off; off = align_up(off + (size_t)4 * radix_num_tiles(pairs) * 256 * 4, 256);
@@ -206,6 +216,13 @@ bgs_status bgs_context_create(int cuda_device, bgs_context** out) {
     for (int i = 0; i < 6 && e == cudaSuccess; ++i) e = cudaEventCreate(&c->ev[i]);
     if (e == cudaSuccess) e = cudaMallocHost(&c->h_ctr, sizeof(FrameCounters));
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, cuda_device);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&c->coop, cudaDevAttrCooperativeLaunch, cuda_device);
+    if (e == cudaSuccess && c->coop) {
+        const int kb = keygen_coop_blocks_per_sm(), bb = bin_coop_blocks_per_sm();
+        c->kg_grid = (uint32_t)(c->sm_count * (kb > 4 ? 4 : kb));
+        c->bin_grid = (uint32_t)(c->sm_count * (bb > 4 ? 4 : bb));
+        if (c->kg_grid == 0 || c->bin_grid == 0 || c->kg_grid > 4096 || c->bin_grid > 4096) c->coop = 0;
+    }
     if (e != cudaSuccess) {
         // no CUDA device / driver: the product has no CPU path
         fprintf(stderr, "libbgs: CUDA initialisation failed on device %d: %s\n", cuda_device, cudaGetErrorString(e));
@@ -342,7 +359,13 @@ bgs_status bgs_render(bgs_context* c, const bgs_cloud* cloud, const bgs_view* vi
         CU(c, cudaMemsetAsync(c->arena, 0, c->arena_bytes, q));
         CU(c, cudaEventRecord(c->ev[0], q));
         // ---- stage 1: key-gen (+ stable compaction of the visible set)
-        launch_keygen(cloud->pos, n, fc, sort_all ? 1 : 0, c->keys[0], c->vals[0], c->status_keygen, c->ctr, q);
+        if (!sort_all && c->coop) {
+            // cooperative: uncompacted keys go through keys[1] (scratch until the first sort pass overwrites it)
+            CU(c, launch_keygen_coop(cloud->pos, n, fc, c->keys[1], c->keys[0], c->vals[0], c->status_keygen, c->ctr,
+                                     c->kg_grid, q));
+        } else {
+            launch_keygen(cloud->pos, n, fc, sort_all ? 1 : 0, c->keys[0], c->vals[0], c->status_keygen, c->ctr, q);
+        }
         ++launches;
         CU(c, cudaEventRecord(c->ev[1], q));
         // ---- stage 2: depth radix sort (P = depth_bits / 8 onesweep passes)
@@ -365,7 +388,12 @@ bgs_status bgs_render(bgs_context* c, const bgs_cloud* cloud, const bgs_view* vi
         ++launches;
         CU(c, cudaEventRecord(c->ev[3], q));
         // ---- stage 4: tile binning -> stable tile-id sort -> ranges
-        launch_bin_emit(c->recs, c->ctr, c->status_bin, tiles_x, c->cap_pairs, c->pkeys[0], c->pvals[0], n, c->sm_count, q);
+        if (c->coop) {
+            CU(c, launch_bin_emit_coop(c->recs, c->ctr, c->status_bin, tiles_x, c->cap_pairs, c->pkeys[0], c->pvals[0],
+                                       c->bin_grid, q));
+        } else {
+            launch_bin_emit(c->recs, c->ctr, c->status_bin, tiles_x, c->cap_pairs, c->pkeys[0], c->pvals[0], n, c->sm_count, q);
+        }
         ++launches;
         launch_radix_hist(c->pkeys[0], &c->ctr->n_pairs, c->cap_pairs, tile_passes, c->hist + 4 * 256, c->sm_count, q);
         ++launches;

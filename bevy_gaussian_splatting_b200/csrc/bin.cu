@@ -13,6 +13,7 @@ namespace bgs {
 constexpr int BIN_THREADS = 256;
 constexpr int BIN_ITEMS = 4;
 constexpr int BIN_TILE = BIN_THREADS * BIN_ITEMS;
+constexpr uint32_t BIN_BIG = 16u;   // splats touching more tiles than this are emitted by the whole block
 
 __global__ void __launch_bounds__(BIN_THREADS)
 bin_emit_kernel(const SplatRec* __restrict__ recs, FrameCounters* __restrict__ ctr, uint32_t* __restrict__ status,
@@ -20,11 +21,13 @@ bin_emit_kernel(const SplatRec* __restrict__ recs, FrameCounters* __restrict__ c
     __shared__ uint32_t s_wtot[BIN_THREADS / 32];
     __shared__ uint32_t s_base;
     __shared__ uint32_t s_tile;
+    __shared__ uint32_t s_nbig;
+    __shared__ uint4 s_big[BIN_TILE];   // (rank, pair offset, bbox x, bbox y) of large-footprint splats
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const uint32_t n_vis = ctr->n_vis;
     const uint32_t num_tiles = (n_vis + BIN_TILE - 1) / BIN_TILE;
     while (true) {
-        if (t == 0) s_tile = atomicAdd(&ctr->tile_ctr[5], 1u);
+        if (t == 0) { s_tile = atomicAdd(&ctr->tile_ctr[5], 1u); s_nbig = 0u; }
         __syncthreads();
         const uint32_t tile = s_tile;
         if (tile >= num_tiles) break;
@@ -77,20 +80,179 @@ bin_emit_kernel(const SplatRec* __restrict__ recs, FrameCounters* __restrict__ c
         for (int j = 0; j < BIN_ITEMS; ++j) {
             if (cnt[j] == 0u) continue;
             const uint32_t r = r0 + j;
-            const uint32_t txlo = (bx[j] & 0xFFFFu) >> 4, txhi = (bx[j] >> 16) >> 4;
-            const uint32_t tylo = (by[j] & 0xFFFFu) >> 4, tyhi = (by[j] >> 16) >> 4;
-            for (uint32_t ty = tylo; ty <= tyhi; ++ty)
-                for (uint32_t tx = txlo; tx <= txhi; ++tx) {
-                    if (off < capacity) {
-                        pair_keys[off] = ty * (uint32_t)tiles_x + tx;
-                        pair_vals[off] = r;
+            if (cnt[j] > BIN_BIG) {
+                // large footprint: hand it to the whole block (coalesced, parallel emission below)
+                const uint32_t q = atomicAdd(&s_nbig, 1u);
+                s_big[q] = make_uint4(r, off, bx[j], by[j]);
+            } else {
+                const uint32_t txlo = (bx[j] & 0xFFFFu) >> 4, txhi = (bx[j] >> 16) >> 4;
+                const uint32_t tylo = (by[j] & 0xFFFFu) >> 4, tyhi = (by[j] >> 16) >> 4;
+                uint32_t o = off;
+                for (uint32_t ty = tylo; ty <= tyhi; ++ty)
+                    for (uint32_t tx = txlo; tx <= txhi; ++tx) {
+                        if (o < capacity) {
+                            pair_keys[o] = ty * (uint32_t)tiles_x + tx;
+                            pair_vals[o] = r;
+                        }
+                        ++o;
                     }
-                    ++off;
+            }
+            off += cnt[j];
+        }
+        __syncthreads();
+        const uint32_t nbig = s_nbig;
+        for (uint32_t q = 0; q < nbig; ++q) {
+            const uint4 b = s_big[q];
+            const uint32_t txlo = (b.z & 0xFFFFu) >> 4, txhi = (b.z >> 16) >> 4;
+            const uint32_t tylo = (b.w & 0xFFFFu) >> 4, tyhi = (b.w >> 16) >> 4;
+            const uint32_t w = txhi - txlo + 1u, total = w * (tyhi - tylo + 1u);
+            for (uint32_t i = t; i < total; i += BIN_THREADS) {
+                const uint32_t o = b.y + i;
+                if (o < capacity) {
+                    pair_keys[o] = (tylo + i / w) * (uint32_t)tiles_x + (txlo + i % w);
+                    pair_vals[o] = b.x;
                 }
+            }
         }
         __syncthreads();
     }
     // n_vis == 0: nothing was published; counters stay zero from the per-frame clear
+}
+
+// Cooperative variant (all CTAs co-resident): phase 1 counts the tiles touched by this CTA's
+// contiguous rank range; one grid barrier; phase 2 sums the earlier CTAs' counts in parallel and emits.
+__global__ void __launch_bounds__(BIN_THREADS)
+bin_emit_coop_kernel(const SplatRec* __restrict__ recs, FrameCounters* __restrict__ ctr, uint32_t* __restrict__ block_cnt,
+                     int tiles_x, uint32_t capacity, uint32_t* __restrict__ pair_keys, uint32_t* __restrict__ pair_vals) {
+    __shared__ uint32_t s_wtot[BIN_THREADS / 32];
+    __shared__ uint32_t s_red[BIN_THREADS / 32];
+    __shared__ uint32_t s_total;
+    __shared__ uint32_t s_nbig;
+    __shared__ uint4 s_big[BIN_TILE];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const uint32_t G = gridDim.x, b = blockIdx.x;
+    const uint32_t n_vis = ctr->n_vis;
+    const uint32_t tiles_total = (n_vis + BIN_TILE - 1) / BIN_TILE;
+    const uint32_t t0 = (uint32_t)((uint64_t)b * tiles_total / G), t1 = (uint32_t)((uint64_t)(b + 1) * tiles_total / G);
+
+    auto tiles_of = [&](uint32_t r, uint32_t& bx, uint32_t& by) -> uint32_t {
+        if (r >= n_vis) return 0u;
+        const uint2 bb = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const char*>(recs + r) + 24));
+        bx = bb.x; by = bb.y;
+        const uint32_t xlo = bb.x & 0xFFFFu, xhi = bb.x >> 16, ylo = bb.y & 0xFFFFu, yhi = bb.y >> 16;
+        if (xlo <= xhi && ylo <= yhi) return ((xhi >> 4) - (xlo >> 4) + 1u) * ((yhi >> 4) - (ylo >> 4) + 1u);
+        return 0u;
+    };
+
+    // ---- phase 1
+    uint32_t mine = 0u;
+    for (uint32_t tile = t0; tile < t1; ++tile) {
+#pragma unroll
+        for (int j = 0; j < BIN_ITEMS; ++j) {
+            uint32_t bx, by;
+            mine += tiles_of(tile * BIN_TILE + t * BIN_ITEMS + j, bx, by);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+    if (lane == 0) s_red[warp] = mine;
+    __syncthreads();
+    if (t == 0) {
+        uint32_t tot = 0u;
+#pragma unroll
+        for (int w = 0; w < BIN_THREADS / 32; ++w) tot += s_red[w];
+        s_total = tot > LB_VMASK ? LB_VMASK : tot;
+        st_volatile(block_cnt + b, s_total);
+    }
+    grid_barrier(&ctr->barrier[1], G);
+
+    // ---- phase 2 (sums saturate at 2^30 - 1: such a frame is rejected by the host)
+    uint64_t run64 = 0;
+    {
+        uint64_t v = 0;
+        for (uint32_t p = t; p < b; p += BIN_THREADS) v += ld_volatile(block_cnt + p);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        __shared__ unsigned long long s_red64[BIN_THREADS / 32];
+        if (lane == 0) s_red64[warp] = v;
+        __syncthreads();
+#pragma unroll
+        for (int w = 0; w < BIN_THREADS / 32; ++w) run64 += s_red64[w];
+    }
+    if (b == G - 1 && t == 0) {
+        const uint64_t need64 = run64 + s_total;
+        const uint32_t need = need64 > LB_VMASK ? LB_VMASK : (uint32_t)need64;
+        ctr->n_pairs_needed = need;
+        ctr->n_pairs = need < capacity ? need : capacity;
+    }
+    uint32_t run = run64 > LB_VMASK ? LB_VMASK : (uint32_t)run64;
+    for (uint32_t tile = t0; tile < t1; ++tile) {
+        if (t == 0) s_nbig = 0u;
+        const uint32_t r0 = tile * BIN_TILE + t * BIN_ITEMS;
+        uint32_t bx[BIN_ITEMS], by[BIN_ITEMS], cnt[BIN_ITEMS];
+        uint32_t tmine = 0u;
+#pragma unroll
+        for (int j = 0; j < BIN_ITEMS; ++j) {
+            bx[j] = 0u; by[j] = 0u;
+            cnt[j] = tiles_of(r0 + j, bx[j], by[j]);
+            tmine += cnt[j];
+        }
+        uint32_t incl = tmine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += y;
+        }
+        if (lane == 31) s_wtot[warp] = incl;
+        __syncthreads();
+        uint32_t wprefix = 0u, ttotal = 0u;
+#pragma unroll
+        for (int w = 0; w < BIN_THREADS / 32; ++w) {
+            const uint32_t c = s_wtot[w];
+            if (w < warp) wprefix += c;
+            ttotal += c;
+        }
+        uint32_t off = run + wprefix + incl - tmine;
+#pragma unroll
+        for (int j = 0; j < BIN_ITEMS; ++j) {
+            if (cnt[j] == 0u) continue;
+            const uint32_t r = r0 + j;
+            if (cnt[j] > BIN_BIG) {
+                const uint32_t q = atomicAdd(&s_nbig, 1u);
+                s_big[q] = make_uint4(r, off, bx[j], by[j]);
+            } else {
+                const uint32_t txlo = (bx[j] & 0xFFFFu) >> 4, txhi = (bx[j] >> 16) >> 4;
+                const uint32_t tylo = (by[j] & 0xFFFFu) >> 4, tyhi = (by[j] >> 16) >> 4;
+                uint32_t o = off;
+                for (uint32_t ty = tylo; ty <= tyhi; ++ty)
+                    for (uint32_t tx = txlo; tx <= txhi; ++tx) {
+                        if (o < capacity) {
+                            pair_keys[o] = ty * (uint32_t)tiles_x + tx;
+                            pair_vals[o] = r;
+                        }
+                        ++o;
+                    }
+            }
+            off += cnt[j];
+        }
+        __syncthreads();
+        const uint32_t nbig = s_nbig;
+        for (uint32_t q = 0; q < nbig; ++q) {
+            const uint4 bg = s_big[q];
+            const uint32_t txlo = (bg.z & 0xFFFFu) >> 4, txhi = (bg.z >> 16) >> 4;
+            const uint32_t tylo = (bg.w & 0xFFFFu) >> 4, tyhi = (bg.w >> 16) >> 4;
+            const uint32_t w = txhi - txlo + 1u, total = w * (tyhi - tylo + 1u);
+            for (uint32_t i = t; i < total; i += BIN_THREADS) {
+                const uint32_t o = bg.y + i;
+                if (o < capacity) {
+                    pair_keys[o] = (tylo + i / w) * (uint32_t)tiles_x + (txlo + i % w);
+                    pair_vals[o] = bg.x;
+                }
+            }
+        }
+        run += ttotal;
+        __syncthreads();
+    }
 }
 
 __global__ void tile_ranges_kernel(const uint32_t* __restrict__ sorted_tile_ids, const FrameCounters* __restrict__ ctr,
@@ -112,6 +274,19 @@ void launch_bin_emit(const SplatRec* recs, FrameCounters* ctr, uint32_t* status,
     bin_emit_kernel<<<blocks, BIN_THREADS, 0, stream>>>(recs, ctr, status, tiles_x, capacity, pair_keys, pair_vals);
 }
 uint32_t bin_num_tiles(uint32_t n) { return (n + BIN_TILE - 1) / BIN_TILE; }
+
+int bin_coop_blocks_per_sm() {
+    int b = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, bin_emit_coop_kernel, BIN_THREADS, 0) != cudaSuccess) return 0;
+    return b;
+}
+cudaError_t launch_bin_emit_coop(const SplatRec* recs, FrameCounters* ctr, uint32_t* block_cnt, int tiles_x,
+                                 uint32_t capacity, uint32_t* pair_keys, uint32_t* pair_vals, uint32_t grid,
+                                 cudaStream_t stream) {
+    void* args[] = {(void*)&recs, (void*)&ctr, (void*)&block_cnt, (void*)&tiles_x, (void*)&capacity, (void*)&pair_keys,
+                    (void*)&pair_vals};
+    return cudaLaunchCooperativeKernel((const void*)bin_emit_coop_kernel, dim3(grid), dim3(BIN_THREADS), args, 0, stream);
+}
 
 void launch_tile_ranges(const uint32_t* sorted_tile_ids, const FrameCounters* ctr, uint2* ranges, uint32_t capacity,
                         int sm_count, cudaStream_t stream) {

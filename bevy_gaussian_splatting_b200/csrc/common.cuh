@@ -47,6 +47,7 @@ struct FrameCounters {
                                 // [5] bin, [6..7] pair passes, [8..] spare
     uint32_t culled_min, culled_min2, culled_max;   // for RasterizeMode::Depth's sorted[1]/[N-1]
     uint32_t pad;
+    uint32_t barrier[8];        // grid barriers of the cooperative kernels: [0] keygen, [1] bin
 };
 
 __device__ __forceinline__ uint32_t ld_volatile(const uint32_t* p) {
@@ -66,6 +67,36 @@ __device__ __forceinline__ uint32_t lanemask_le() {
     uint32_t m;
     asm("mov.u32 %0, %%lanemask_le;" : "=r"(m));
     return m;
+}
+
+// Grid-wide barrier for kernels launched with cudaLaunchCooperativeKernel (all CTAs co-resident).
+// `bar` is zeroed by the per-frame clear; each use passes the cumulative arrival target.
+__device__ __forceinline__ void grid_barrier(uint32_t* bar, uint32_t target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(bar, 1u);
+        while (ld_volatile(bar) < target) { __nanosleep(32); }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+// Sum of counts[0 .. upto) by the whole CTA (counts were published before a grid barrier).
+template <int THREADS>
+__device__ __forceinline__ uint32_t block_sum_prefix(const uint32_t* counts, uint32_t upto, uint32_t* s_red /*[THREADS/32]*/) {
+    uint32_t v = 0u;
+    for (uint32_t p = threadIdx.x; p < upto; p += THREADS) v += ld_volatile(counts + p);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    uint32_t tot = 0u;
+#pragma unroll
+    for (int w = 0; w < THREADS / 32; ++w) tot += s_red[w];
+    __syncthreads();
+    return tot;
 }
 
 // Decoupled look-back over single-word tile status, executed by ONE full warp.

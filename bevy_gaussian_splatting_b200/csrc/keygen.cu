@@ -101,6 +101,107 @@ keygen_compact_kernel(const float4* __restrict__ pos, uint32_t n, FrameConsts fc
     }
 }
 
+// Cooperative variant (all CTAs co-resident, launched with cudaLaunchCooperativeKernel): each CTA owns
+// a CONTIGUOUS range of tiles.  Phase 1 streams the positions once (16 B/gaussian), writes the
+// uncompacted keys (4 B/gaussian, L2-sized scratch) and publishes the CTA's visible count.  One grid
+// barrier.  Phase 2 sums the counts of all earlier CTAs in parallel (no chained look-back), re-reads
+// its own keys from L2 and writes the visible (key, index) pairs compacted in index order.
+__global__ void __launch_bounds__(KG_THREADS)
+keygen_coop_kernel(const float4* __restrict__ pos, uint32_t n, FrameConsts fc, uint32_t* __restrict__ keys_tmp,
+                   uint32_t* __restrict__ keys_out, uint32_t* __restrict__ ids_out, uint32_t* __restrict__ block_cnt,
+                   FrameCounters* __restrict__ ctr) {
+    __shared__ uint32_t s_cnt[KG_ITEMS * (KG_THREADS / 32)];
+    __shared__ uint32_t s_off[KG_ITEMS * (KG_THREADS / 32)];
+    __shared__ uint32_t s_red[KG_THREADS / 32];
+    __shared__ uint32_t s_total;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const uint32_t G = gridDim.x, b = blockIdx.x;
+    const uint32_t tiles_total = (n + KG_TILE - 1) / KG_TILE;
+    const uint32_t t0 = (uint32_t)((uint64_t)b * tiles_total / G), t1 = (uint32_t)((uint64_t)(b + 1) * tiles_total / G);
+    const uint32_t culled = 0xFFFFFFFFu >> fc.key_shift;
+
+    // ---- phase 1: keys for every gaussian of this CTA's range, visible count
+    uint32_t mine = 0u;
+    for (uint32_t tile = t0; tile < t1; ++tile) {
+        const uint32_t tile_base = tile * KG_TILE;
+        float4 p[KG_ITEMS];
+#pragma unroll
+        for (int j = 0; j < KG_ITEMS; ++j) {
+            const uint32_t i = tile_base + j * KG_THREADS + t;
+            p[j] = (i < n) ? __ldcs(pos + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int j = 0; j < KG_ITEMS; ++j) {
+            const uint32_t i = tile_base + j * KG_THREADS + t;
+            const KeyOut k = key_of(fc, p[j].x, p[j].y, p[j].z);
+            if (i < n) {
+                const uint32_t key = k.visible ? k.key : culled;
+                __stcg(keys_tmp + i, key);
+                mine += k.visible ? 1u : 0u;
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+    if (lane == 0) s_red[warp] = mine;
+    __syncthreads();
+    if (t == 0) {
+        uint32_t tot = 0u;
+#pragma unroll
+        for (int w = 0; w < KG_THREADS / 32; ++w) tot += s_red[w];
+        s_total = tot;
+        st_volatile(block_cnt + b, tot);
+    }
+    grid_barrier(&ctr->barrier[0], G);
+
+    // ---- phase 2: exclusive prefix over CTAs, then ordered compaction of this CTA's range
+    uint32_t run = block_sum_prefix<KG_THREADS>(block_cnt, b, s_red);
+    if (b == G - 1 && t == 0) { ctr->n_vis = run + s_total; ctr->n_sort = run + s_total; }
+    for (uint32_t tile = t0; tile < t1; ++tile) {
+        const uint32_t tile_base = tile * KG_TILE;
+        uint32_t key[KG_ITEMS], prefix[KG_ITEMS];
+        uint32_t vis_bits = 0u;
+#pragma unroll
+        for (int j = 0; j < KG_ITEMS; ++j) {
+            const uint32_t i = tile_base + j * KG_THREADS + t;
+            key[j] = (i < n) ? __ldcg(keys_tmp + i) : culled;
+        }
+#pragma unroll
+        for (int j = 0; j < KG_ITEMS; ++j) {
+            const bool v = key[j] != culled;
+            const uint32_t bal = __ballot_sync(0xffffffffu, v);
+            prefix[j] = __popc(bal & lanemask_lt());
+            if (v) vis_bits |= 1u << j;
+            if (lane == 0) s_cnt[j * (KG_THREADS / 32) + warp] = __popc(bal);
+        }
+        __syncthreads();
+        if (warp == 0) {
+            const uint32_t a = s_cnt[2 * lane], c2 = s_cnt[2 * lane + 1];
+            uint32_t incl = a + c2;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += y;
+            }
+            const uint32_t excl = incl - (a + c2);
+            s_off[2 * lane] = excl;
+            s_off[2 * lane + 1] = excl + a;
+            if (lane == 31) s_total = incl;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < KG_ITEMS; ++j) {
+            if (vis_bits & (1u << j)) {
+                const uint32_t dst = run + s_off[j * (KG_THREADS / 32) + warp] + prefix[j];
+                keys_out[dst] = key[j];
+                ids_out[dst] = tile_base + j * KG_THREADS + t;
+            }
+        }
+        run += s_total;
+        __syncthreads();
+    }
+}
+
 // Debug hook: rebuild the reference's full sorted_entry_buffer (sort/mod.rs:323-329) from the
 // compacted result: [0, n_vis) = sorted visible entries, then every culled index ascending
 // with key 0xFFFFFFFF >> shift.  Single block per call chunk; not on the hot path.
@@ -118,6 +219,20 @@ void launch_keygen(const float4* pos, uint32_t n, const FrameConsts& fc, int sor
     keygen_compact_kernel<<<tiles, KG_THREADS, 0, stream>>>(pos, n, fc, sort_all, keys_out, ids_out, status, ctr);
 }
 uint32_t keygen_num_tiles(uint32_t n) { return (n + KG_TILE - 1) / KG_TILE; }
+
+int keygen_coop_blocks_per_sm() {
+    int b = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, keygen_coop_kernel, KG_THREADS, 0) != cudaSuccess) return 0;
+    return b;
+}
+cudaError_t launch_keygen_coop(const float4* pos, uint32_t n, const FrameConsts& fc, uint32_t* keys_tmp, uint32_t* keys_out,
+                               uint32_t* ids_out, uint32_t* block_cnt, FrameCounters* ctr, uint32_t grid,
+                               cudaStream_t stream) {
+    FrameConsts fcc = fc;
+    void* args[] = {(void*)&pos, (void*)&n, (void*)&fcc, (void*)&keys_tmp, (void*)&keys_out, (void*)&ids_out,
+                    (void*)&block_cnt, (void*)&ctr};
+    return cudaLaunchCooperativeKernel((const void*)keygen_coop_kernel, dim3(grid), dim3(KG_THREADS), args, 0, stream);
+}
 
 void launch_culled_flags(const float4* pos, uint32_t n, const FrameConsts& fc, uint32_t* flags, cudaStream_t stream) {
     culled_flags_kernel<<<(n + 255) / 256, 256, 0, stream>>>(pos, n, fc, flags);

@@ -17,6 +17,7 @@ constexpr int RS_THREADS = 256;
 constexpr int RS_WARPS = RS_THREADS / 32;
 constexpr int RS_ITEMS = 16;
 constexpr int RS_TILE = RS_THREADS * RS_ITEMS;   // 4096 entries per tile
+constexpr int LB_BATCH = 8;                       // look-back loads in flight per thread
 
 // ---- digit histograms for all passes in one read of the keys -----------------------------
 constexpr int HS_THREADS = 256;
@@ -167,13 +168,26 @@ onesweep_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict
         } else {
             st_volatile(my_status, LB_AGG | cnt_valid);
             excl = 0u;
+            // look back over the predecessors' per-digit words, LB_BATCH independent loads in flight
             const uint32_t* ps = my_status;
-            for (uint32_t back = tile; back > 0; --back) {
-                ps -= 256;
-                uint32_t w;
-                do { w = ld_volatile(ps); } while ((w >> 30) == 0u);
-                excl += w & LB_VMASK;
-                if ((w >> 30) == 2u) break;
+            uint32_t back = tile;
+            bool found = false;
+            while (!found) {
+                uint32_t w[LB_BATCH];
+#pragma unroll
+                for (int q = 0; q < LB_BATCH; ++q)
+                    w[q] = ((uint32_t)q < back) ? ld_volatile(ps - 256 * (q + 1)) : (LB_INC | 0u);
+#pragma unroll
+                for (int q = 0; q < LB_BATCH; ++q) {
+                    if (!found) {
+                        uint32_t x = w[q];
+                        while ((x >> 30) == 0u) x = ld_volatile(ps - 256 * (q + 1));
+                        excl += x & LB_VMASK;
+                        found = (x >> 30) == 2u;
+                    }
+                }
+                ps -= 256 * LB_BATCH;
+                back = back > (uint32_t)LB_BATCH ? back - LB_BATCH : 0u;
             }
             st_volatile(my_status, LB_INC | ((excl + cnt_valid) & LB_VMASK));
         }

@@ -29,9 +29,11 @@ __device__ __forceinline__ float linear_to_srgb(float c) {
 __global__ void __launch_bounds__(RT_THREADS)
 raster_kernel(const SplatRec* __restrict__ recs, const uint32_t* __restrict__ tile_entries,
               const uint2* __restrict__ ranges, int W, int H, int tiles_x, void* __restrict__ out, uint32_t format) {
-    __shared__ float4 s_q0[RT_CHUNK];   // cx, cy, ux, uy
-    __shared__ float4 s_q1[RT_CHUNK];   // vx, vy, bbox x, bbox y
-    __shared__ float4 s_q2[RT_CHUNK];   // r, g, b, opacity
+    __shared__ float4 s_q0[RT_CHUNK];            // cx, cy, ux, uy
+    __shared__ float2 s_uv[RT_CHUNK];            // vx, vy
+    __shared__ uint2 s_bb[RT_CHUNK];             // pixel bbox: lo | hi << 16 (x, y)
+    __shared__ float4 s_q2[RT_CHUNK];            // r, g, b, opacity
+    __shared__ uint8_t s_list[RT_THREADS / 32][RT_CHUNK];   // per-warp candidates (indices into the chunk)
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int tile = blockIdx.x;
     const int tile_x = tile % tiles_x, tile_y = tile / tiles_x;
@@ -50,20 +52,35 @@ raster_kernel(const SplatRec* __restrict__ recs, const uint32_t* __restrict__ ti
         if ((uint32_t)t < cnt) {
             const uint32_t r = __ldg(tile_entries + base + t);
             const float4* rp = reinterpret_cast<const float4*>(recs + r);
-            s_q0[t] = __ldg(rp);
-            s_q1[t] = __ldg(rp + 1);
+            const float4 a = __ldg(rp), b = __ldg(rp + 1);
+            s_q0[t] = a;
+            s_uv[t] = make_float2(b.x, b.y);
+            s_bb[t] = make_uint2(__float_as_uint(b.z), __float_as_uint(b.w));
             s_q2[t] = __ldg(rp + 2);
         }
         __syncthreads();
+        // each warp compacts the chunk to the splats whose bbox touches its 8x4 pixels (order kept)
+        uint32_t nl = 0;
+        if (!__all_sync(0xffffffffu, done)) {
+            for (uint32_t j0 = 0; j0 < cnt; j0 += 32) {
+                const uint32_t j = j0 + lane;
+                bool hit = false;
+                if (j < cnt) {
+                    const uint2 bb = s_bb[j];
+                    hit = !((int)(bb.x >> 16) < wx0 || (int)(bb.x & 0xFFFFu) > wx0 + 7 || (int)(bb.y >> 16) < wy0 ||
+                            (int)(bb.y & 0xFFFFu) > wy0 + 3);
+                }
+                const uint32_t m = __ballot_sync(0xffffffffu, hit);
+                if (hit) s_list[warp][nl + __popc(m & lanemask_lt())] = (uint8_t)j;
+                nl += __popc(m);
+            }
+            __syncwarp();
+        }
         if (!done) {
-            for (uint32_t j = 0; j < cnt; ++j) {
-                const float4 q1 = s_q1[j];
-                const uint32_t bx = __float_as_uint(q1.z), by = __float_as_uint(q1.w);
-                // warp-uniform reject: splat bbox vs this warp's 8x4 pixel rectangle
-                if ((int)(bx >> 16) < wx0 || (int)(bx & 0xFFFFu) > wx0 + 7 || (int)(by >> 16) < wy0 ||
-                    (int)(by & 0xFFFFu) > wy0 + 3)
-                    continue;
+            for (uint32_t i = 0; i < nl; ++i) {
+                const uint32_t j = s_list[warp][i];
                 const float4 q0 = s_q0[j];
+                const float2 q1 = s_uv[j];
                 const float dx = __fsub_rn(fx, q0.x), dy = __fsub_rn(fy, q0.y);
                 const float u = __fmaf_rn(q0.w, dy, __fmul_rn(q0.z, dx));
                 const float v = __fmaf_rn(q1.y, dy, __fmul_rn(q1.x, dx));

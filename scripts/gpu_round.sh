@@ -4,7 +4,7 @@
 TAG=${1:-r1}
 mkdir -p gpurun_out
 if [ -z "$2" ]; then
-  timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -15 | tee gpurun_out/pytest_gpu_$TAG.log
+  timeout 1500 python -m pytest tests -x -q -m gpu > gpurun_out/pytest_gpu_$TAG.log 2>&1; tail -5 gpurun_out/pytest_gpu_$TAG.log
 fi
 timeout 900 python bench.py 2> gpurun_out/bench_$TAG.err | tee gpurun_out/bench_$TAG.json
 # launch list: 3 warm-up frames (12 launches each) skipped, then 2 frames; cold-cache serialised times

@@ -127,7 +127,7 @@ def test_edge_cases(plugin, oracle):
     cloud = B.random_gaussians_3d_seeded(5000, 2)
     cloud.position_visibility[:, 2] = np.abs(cloud.position_visibility[:, 2]) + 6.0
     img, til = check_against_oracle(plugin, oracle, cloud, s, view)
-    assert plugin.frame_stats().n_visible == 0 and np.all(img[..., :3] == 0) and np.all(img[..., 3] == 1)
+    assert til["n_vis"] == 0 and til["n_pairs"] == 0 and np.all(img[..., :3] == 0) and np.all(img[..., 3] == 1)
     # degenerate inputs: zero opacity, zero scale, NaN position, identity rotation (NaN eigenvector quirk)
     deg = B.random_gaussians_3d_seeded(3000, 4)
     deg.scale_opacity[::5, 3] = 0.0
