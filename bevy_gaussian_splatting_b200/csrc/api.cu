@@ -37,8 +37,8 @@ void launch_bin_emit(const SplatRec* recs, FrameCounters* ctr, uint32_t* status,
 uint32_t bin_num_tiles(uint32_t n);
 int bin_coop_blocks_per_sm();
 cudaError_t launch_bin_emit_coop(const SplatRec* recs, FrameCounters* ctr, uint32_t* block_cnt, int tiles_x,
-                                 uint32_t capacity, uint32_t* pair_keys, uint32_t* pair_vals, uint32_t grid,
-                                 cudaStream_t stream);
+                                 uint32_t capacity, uint32_t* pair_keys, uint32_t* pair_vals, uint32_t* q_rank,
+                                 uint32_t* q_off, uint32_t grid, cudaStream_t stream);
 void launch_tile_ranges(const uint32_t* sorted_tile_ids, const FrameCounters* ctr, uint2* ranges, uint32_t capacity,
                         int sm_count, cudaStream_t stream);
 // raster.cu
@@ -389,8 +389,9 @@ bgs_status bgs_render(bgs_context* c, const bgs_cloud* cloud, const bgs_view* vi
         CU(c, cudaEventRecord(c->ev[3], q));
         // ---- stage 4: tile binning -> stable tile-id sort -> ranges
         if (c->coop) {
+            // the depth sort's spare ping-pong buffers (N words each) hold the large-footprint queue
             CU(c, launch_bin_emit_coop(c->recs, c->ctr, c->status_bin, tiles_x, c->cap_pairs, c->pkeys[0], c->pvals[0],
-                                       c->bin_grid, q));
+                                       c->keys[cur ^ 1], c->vals[cur ^ 1], c->bin_grid, q));
         } else {
             launch_bin_emit(c->recs, c->ctr, c->status_bin, tiles_x, c->cap_pairs, c->pkeys[0], c->pvals[0], n, c->sm_count, q);
         }

@@ -119,16 +119,24 @@ bin_emit_kernel(const SplatRec* __restrict__ recs, FrameCounters* __restrict__ c
     // n_vis == 0: nothing was published; counters stay zero from the per-frame clear
 }
 
-// Cooperative variant (all CTAs co-resident): phase 1 counts the tiles touched by this CTA's
-// contiguous rank range; one grid barrier; phase 2 sums the earlier CTAs' counts in parallel and emits.
+// Cooperative variant (all CTAs co-resident).
+//   phase 1: count the tiles touched by this CTA's contiguous rank range, publish the CTA total
+//   -- grid barrier --
+//   phase 2: sum the earlier CTAs' totals in parallel (no chained look-back); emit small footprints
+//            directly; push large footprints (rank, pair offset) to a global queue
+//   -- grid barrier --
+//   phase 3: all warps of the grid drain the queue (front-most splats cover hundreds of tiles and all
+//            sit in the first CTAs' ranges: without this the frame waits on a handful of CTAs)
 __global__ void __launch_bounds__(BIN_THREADS)
 bin_emit_coop_kernel(const SplatRec* __restrict__ recs, FrameCounters* __restrict__ ctr, uint32_t* __restrict__ block_cnt,
-                     int tiles_x, uint32_t capacity, uint32_t* __restrict__ pair_keys, uint32_t* __restrict__ pair_vals) {
+                     int tiles_x, uint32_t capacity, uint32_t* __restrict__ pair_keys, uint32_t* __restrict__ pair_vals,
+                     uint32_t* __restrict__ q_rank, uint32_t* __restrict__ q_off) {
     __shared__ uint32_t s_wtot[BIN_THREADS / 32];
+    __shared__ uint32_t s_wbig[BIN_THREADS / 32];
     __shared__ uint32_t s_red[BIN_THREADS / 32];
+    __shared__ unsigned long long s_red64[BIN_THREADS / 32];
     __shared__ uint32_t s_total;
-    __shared__ uint32_t s_nbig;
-    __shared__ uint4 s_big[BIN_TILE];
+    __shared__ uint32_t s_qbase;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const uint32_t G = gridDim.x, b = blockIdx.x;
     const uint32_t n_vis = ctr->n_vis;
@@ -173,7 +181,6 @@ bin_emit_coop_kernel(const SplatRec* __restrict__ recs, FrameCounters* __restric
         for (uint32_t p = t; p < b; p += BIN_THREADS) v += ld_volatile(block_cnt + p);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        __shared__ unsigned long long s_red64[BIN_THREADS / 32];
         if (lane == 0) s_red64[warp] = v;
         __syncthreads();
 #pragma unroll
@@ -187,39 +194,42 @@ bin_emit_coop_kernel(const SplatRec* __restrict__ recs, FrameCounters* __restric
     }
     uint32_t run = run64 > LB_VMASK ? LB_VMASK : (uint32_t)run64;
     for (uint32_t tile = t0; tile < t1; ++tile) {
-        if (t == 0) s_nbig = 0u;
         const uint32_t r0 = tile * BIN_TILE + t * BIN_ITEMS;
         uint32_t bx[BIN_ITEMS], by[BIN_ITEMS], cnt[BIN_ITEMS];
-        uint32_t tmine = 0u;
+        uint32_t tmine = 0u, nbig = 0u;
 #pragma unroll
         for (int j = 0; j < BIN_ITEMS; ++j) {
             bx[j] = 0u; by[j] = 0u;
             cnt[j] = tiles_of(r0 + j, bx[j], by[j]);
             tmine += cnt[j];
+            nbig += cnt[j] > BIN_BIG ? 1u : 0u;
         }
-        uint32_t incl = tmine;
+        uint32_t incl = tmine, bincl = nbig;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += y;
+            const uint32_t z = __shfl_up_sync(0xffffffffu, bincl, o);
+            if (lane >= o) { incl += y; bincl += z; }
         }
-        if (lane == 31) s_wtot[warp] = incl;
+        if (lane == 31) { s_wtot[warp] = incl; s_wbig[warp] = bincl; }
         __syncthreads();
-        uint32_t wprefix = 0u, ttotal = 0u;
+        uint32_t wprefix = 0u, ttotal = 0u, bprefix = 0u, btotal = 0u;
 #pragma unroll
         for (int w = 0; w < BIN_THREADS / 32; ++w) {
-            const uint32_t c = s_wtot[w];
-            if (w < warp) wprefix += c;
-            ttotal += c;
+            const uint32_t c = s_wtot[w], d = s_wbig[w];
+            if (w < warp) { wprefix += c; bprefix += d; }
+            ttotal += c; btotal += d;
         }
+        if (t == 0 && btotal) s_qbase = atomicAdd(&ctr->big_count, btotal);   // one reservation per tile
+        __syncthreads();
         uint32_t off = run + wprefix + incl - tmine;
+        uint32_t qat = s_qbase + bprefix + bincl - nbig;
 #pragma unroll
         for (int j = 0; j < BIN_ITEMS; ++j) {
             if (cnt[j] == 0u) continue;
             const uint32_t r = r0 + j;
             if (cnt[j] > BIN_BIG) {
-                const uint32_t q = atomicAdd(&s_nbig, 1u);
-                s_big[q] = make_uint4(r, off, bx[j], by[j]);
+                q_rank[qat] = r; q_off[qat] = off; ++qat;
             } else {
                 const uint32_t txlo = (bx[j] & 0xFFFFu) >> 4, txhi = (bx[j] >> 16) >> 4;
                 const uint32_t tylo = (by[j] & 0xFFFFu) >> 4, tyhi = (by[j] >> 16) >> 4;
@@ -235,23 +245,34 @@ bin_emit_coop_kernel(const SplatRec* __restrict__ recs, FrameCounters* __restric
             }
             off += cnt[j];
         }
-        __syncthreads();
-        const uint32_t nbig = s_nbig;
-        for (uint32_t q = 0; q < nbig; ++q) {
-            const uint4 bg = s_big[q];
-            const uint32_t txlo = (bg.z & 0xFFFFu) >> 4, txhi = (bg.z >> 16) >> 4;
-            const uint32_t tylo = (bg.w & 0xFFFFu) >> 4, tyhi = (bg.w >> 16) >> 4;
-            const uint32_t w = txhi - txlo + 1u, total = w * (tyhi - tylo + 1u);
-            for (uint32_t i = t; i < total; i += BIN_THREADS) {
-                const uint32_t o = bg.y + i;
-                if (o < capacity) {
-                    pair_keys[o] = (tylo + i / w) * (uint32_t)tiles_x + (txlo + i % w);
-                    pair_vals[o] = bg.x;
-                }
-            }
-        }
         run += ttotal;
         __syncthreads();
+    }
+    grid_barrier(&ctr->barrier[1], 2u * G);
+
+    // ---- phase 3: warps pull large-footprint splats from the queue
+    const uint32_t nq = ld_volatile(&ctr->big_count);
+    while (true) {
+        uint32_t q = 0u;
+        if (lane == 0) q = atomicAdd(&ctr->big_head, 1u);
+        q = __shfl_sync(0xffffffffu, q, 0);
+        if (q >= nq) break;
+        const uint32_t r = __ldcg(q_rank + q), off = __ldcg(q_off + q);
+        const uint2 bb = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const char*>(recs + r) + 24));
+        const uint32_t txlo = (bb.x & 0xFFFFu) >> 4, txhi = (bb.x >> 16) >> 4;
+        const uint32_t tylo = (bb.y & 0xFFFFu) >> 4, tyhi = (bb.y >> 16) >> 4;
+        const uint32_t w = txhi - txlo + 1u, total = w * (tyhi - tylo + 1u);
+        uint32_t ty = tylo + (uint32_t)lane / w, tx = txlo + (uint32_t)lane % w;
+        const uint32_t dy = 32u / w, dxr = 32u % w;
+        for (uint32_t i = lane; i < total; i += 32) {
+            const uint32_t o = off + i;
+            if (o < capacity) {
+                pair_keys[o] = ty * (uint32_t)tiles_x + tx;
+                pair_vals[o] = r;
+            }
+            ty += dy; tx += dxr;
+            if (tx > txhi) { tx -= w; ++ty; }
+        }
     }
 }
 
@@ -281,10 +302,10 @@ int bin_coop_blocks_per_sm() {
     return b;
 }
 cudaError_t launch_bin_emit_coop(const SplatRec* recs, FrameCounters* ctr, uint32_t* block_cnt, int tiles_x,
-                                 uint32_t capacity, uint32_t* pair_keys, uint32_t* pair_vals, uint32_t grid,
-                                 cudaStream_t stream) {
+                                 uint32_t capacity, uint32_t* pair_keys, uint32_t* pair_vals, uint32_t* q_rank,
+                                 uint32_t* q_off, uint32_t grid, cudaStream_t stream) {
     void* args[] = {(void*)&recs, (void*)&ctr, (void*)&block_cnt, (void*)&tiles_x, (void*)&capacity, (void*)&pair_keys,
-                    (void*)&pair_vals};
+                    (void*)&pair_vals, (void*)&q_rank, (void*)&q_off};
     return cudaLaunchCooperativeKernel((const void*)bin_emit_coop_kernel, dim3(grid), dim3(BIN_THREADS), args, 0, stream);
 }
 

@@ -48,6 +48,8 @@ struct FrameCounters {
     uint32_t culled_min, culled_min2, culled_max;   // for RasterizeMode::Depth's sorted[1]/[N-1]
     uint32_t pad;
     uint32_t barrier[8];        // grid barriers of the cooperative kernels: [0] keygen, [1] bin
+    uint32_t big_count, big_head;   // bin: queue of large-footprint splats (filled, then drained grid-wide)
+    uint32_t pad2[2];
 };
 
 __device__ __forceinline__ uint32_t ld_volatile(const uint32_t* p) {

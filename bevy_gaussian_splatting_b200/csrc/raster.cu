@@ -26,15 +26,24 @@ __device__ __forceinline__ float linear_to_srgb(float c) {
     return c <= 0.0031308f ? 12.92f * c : 1.055f * powf(c, 1.0f / 2.4f) - 0.055f;
 }
 
+// shared-memory layout (byte offsets from one base so the hot loop needs a single address register)
+constexpr uint32_t SM_Q0 = 0;                         // float4 [256]: cx, cy, ux, uy
+constexpr uint32_t SM_UV = SM_Q0 + RT_CHUNK * 16;     // float4 [256]: vx, vy, bbox x, bbox y
+constexpr uint32_t SM_Q2 = SM_UV + RT_CHUNK * 16;     // float4 [256]: r, g, b, opacity
+constexpr uint32_t SM_LIST = SM_Q2 + RT_CHUNK * 16;   // u16 [8][256]: per-warp candidates, stored as index * 16
+constexpr uint32_t SM_BYTES = SM_LIST + (RT_THREADS / 32) * RT_CHUNK * 2;
+
 __global__ void __launch_bounds__(RT_THREADS)
 raster_kernel(const SplatRec* __restrict__ recs, const uint32_t* __restrict__ tile_entries,
               const uint2* __restrict__ ranges, int W, int H, int tiles_x, void* __restrict__ out, uint32_t format) {
-    __shared__ float4 s_q0[RT_CHUNK];            // cx, cy, ux, uy
-    __shared__ float2 s_uv[RT_CHUNK];            // vx, vy
-    __shared__ uint2 s_bb[RT_CHUNK];             // pixel bbox: lo | hi << 16 (x, y)
-    __shared__ float4 s_q2[RT_CHUNK];            // r, g, b, opacity
-    __shared__ uint8_t s_list[RT_THREADS / 32][RT_CHUNK];   // per-warp candidates (indices into the chunk)
+    __shared__ __align__(16) unsigned char s_mem[SM_BYTES];
+    float4* s_q0 = reinterpret_cast<float4*>(s_mem + SM_Q0);
+    float4* s_uv = reinterpret_cast<float4*>(s_mem + SM_UV);
+    float4* s_q2 = reinterpret_cast<float4*>(s_mem + SM_Q2);
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    unsigned short* s_list = reinterpret_cast<unsigned short*>(s_mem + SM_LIST) + warp * RT_CHUNK;
+    const uint32_t a_base = (uint32_t)__cvta_generic_to_shared(s_mem);
+    const uint32_t a_list = a_base + SM_LIST + (uint32_t)warp * RT_CHUNK * 2u;
     const int tile = blockIdx.x;
     const int tile_x = tile % tiles_x, tile_y = tile / tiles_x;
     // warp w covers the 8x4 rectangle at ((w & 1) * 8, (w >> 1) * 4) of the tile
@@ -44,54 +53,60 @@ raster_kernel(const SplatRec* __restrict__ recs, const uint32_t* __restrict__ ti
     const float fx = (float)px + 0.5f, fy = (float)py + 0.5f;
     const uint2 range = ranges[tile];
 
-    float T = 1.0f, cr = 0.0f, cg = 0.0f, cb = 0.0f;
-    bool done = !inside;
+    float T = inside ? 1.0f : 0.0f, cr = 0.0f, cg = 0.0f, cb = 0.0f;   // T < T_STOP <=> this pixel is done
     for (uint32_t base = range.x; base < range.y; base += RT_CHUNK) {
-        if (__syncthreads_count(done ? 0 : 1) == 0) break;   // also fences reuse of the staging buffers
+        if (__syncthreads_count(T < T_STOP ? 0 : 1) == 0) break;   // also fences reuse of the staging buffers
         const uint32_t cnt = min((uint32_t)RT_CHUNK, range.y - base);
         if ((uint32_t)t < cnt) {
             const uint32_t r = __ldg(tile_entries + base + t);
             const float4* rp = reinterpret_cast<const float4*>(recs + r);
-            const float4 a = __ldg(rp), b = __ldg(rp + 1);
-            s_q0[t] = a;
-            s_uv[t] = make_float2(b.x, b.y);
-            s_bb[t] = make_uint2(__float_as_uint(b.z), __float_as_uint(b.w));
+            s_q0[t] = __ldg(rp);
+            s_uv[t] = __ldg(rp + 1);
             s_q2[t] = __ldg(rp + 2);
         }
         __syncthreads();
         // each warp compacts the chunk to the splats whose bbox touches its 8x4 pixels (order kept)
         uint32_t nl = 0;
-        if (!__all_sync(0xffffffffu, done)) {
+        if (__any_sync(0xffffffffu, !(T < T_STOP))) {
             for (uint32_t j0 = 0; j0 < cnt; j0 += 32) {
                 const uint32_t j = j0 + lane;
                 bool hit = false;
                 if (j < cnt) {
-                    const uint2 bb = s_bb[j];
-                    hit = !((int)(bb.x >> 16) < wx0 || (int)(bb.x & 0xFFFFu) > wx0 + 7 || (int)(bb.y >> 16) < wy0 ||
-                            (int)(bb.y & 0xFFFFu) > wy0 + 3);
+                    const float4 q = s_uv[j];
+                    const uint32_t bx = __float_as_uint(q.z), by = __float_as_uint(q.w);
+                    hit = !((int)(bx >> 16) < wx0 || (int)(bx & 0xFFFFu) > wx0 + 7 || (int)(by >> 16) < wy0 ||
+                            (int)(by & 0xFFFFu) > wy0 + 3);
                 }
                 const uint32_t m = __ballot_sync(0xffffffffu, hit);
-                if (hit) s_list[warp][nl + __popc(m & lanemask_lt())] = (uint8_t)j;
+                if (hit) s_list[nl + __popc(m & lanemask_lt())] = (unsigned short)(j * 16u);
                 nl += __popc(m);
             }
             __syncwarp();
         }
-        if (!done) {
-            for (uint32_t i = 0; i < nl; ++i) {
-                const uint32_t j = s_list[warp][i];
-                const float4 q0 = s_q0[j];
-                const float2 q1 = s_uv[j];
+        if (!(T < T_STOP)) {
+            const uint32_t a_end = a_list + nl * 2u;
+            for (uint32_t a_it = a_list; a_it != a_end; a_it += 2u) {
+                uint32_t off;
+                asm volatile("ld.shared.u16 %0, [%1];" : "=r"(off) : "r"(a_it));
+                const uint32_t a_rec = a_base + off;
+                float4 q0; float2 q1;
+                asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(q0.x), "=f"(q0.y), "=f"(q0.z), "=f"(q0.w) : "r"(a_rec));
+                asm volatile("ld.shared.v2.f32 {%0,%1}, [%2+4096];" : "=f"(q1.x), "=f"(q1.y) : "r"(a_rec));
                 const float dx = __fsub_rn(fx, q0.x), dy = __fsub_rn(fy, q0.y);
                 const float u = __fmaf_rn(q0.w, dy, __fmul_rn(q0.z, dx));
                 const float v = __fmaf_rn(q1.y, dy, __fmul_rn(q1.x, dx));
                 if (fabsf(u) <= 1.0f && fabsf(v) <= 1.0f) {
                     const float qd = __fmaf_rn(v, v, __fmul_rn(u, u));
-                    const float4 q2 = s_q2[j];
-                    const float a = fminf(__expf(-4.5f * qd) * q2.w, 0.999f);
+                    float4 q2;
+                    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4+8192];" : "=f"(q2.x), "=f"(q2.y), "=f"(q2.z), "=f"(q2.w) : "r"(a_rec));
+                    // exp(-4.5 qd) = 2^(qd * -4.5 log2 e); qd <= 2 so the argument stays >= -13 (no range fix-up)
+                    float e;
+                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(qd * -6.492127684f));
+                    const float a = fminf(e * q2.w, 0.999f);
                     const float w = a * T;
                     cr = fmaf(w, q2.x, cr); cg = fmaf(w, q2.y, cg); cb = fmaf(w, q2.z, cb);
-                    T *= (1.0f - a);
-                    if (T < T_STOP) { done = true; break; }
+                    T = fmaf(-a, T, T);
+                    if (T < T_STOP) break;
                 }
             }
         }
