@@ -59,12 +59,18 @@ class View:
         return (self.clip_from_view.astype(np.float32) @ self.view_from_world.astype(np.float32)).astype(np.float32)
 
     def to_abi(self) -> abi.bgs_view:
+        key = (self.view_from_world.tobytes(), self.clip_from_view.tobytes(), bytes(np.asarray(self.world_position, np.float32)),
+               self.width, self.height)
+        cached = getattr(self, "_abi_cache", None)
+        if cached is not None and cached[0] == key:
+            return cached[1]
         v = abi.bgs_view()
         v.view_from_world[:] = self.view_from_world.astype(np.float32).T.reshape(-1).tolist()
         v.clip_from_view[:] = self.clip_from_view.astype(np.float32).T.reshape(-1).tolist()
         v.clip_from_world[:] = self.clip_from_world.T.reshape(-1).tolist()
         v.world_position[:] = np.asarray(self.world_position, np.float32).tolist()
         v.viewport[:] = [0.0, 0.0, float(self.width), float(self.height)]
+        self._abi_cache = (key, v)
         return v
 
 

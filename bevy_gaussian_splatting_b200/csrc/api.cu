@@ -101,6 +101,7 @@ struct bgs_context {
     int depth_result = 0, pair_result = 0;   // which ping-pong buffer holds the sorted result
     bgs_frame_stats stats = {};
     float stage_us[6] = {0, 0, 0, 0, 0, 0};
+    bool stage_valid = false;
     uint32_t launches = 0;
 };
 
@@ -432,14 +433,7 @@ bgs_status bgs_render(bgs_context* c, const bgs_cloud* cloud, const bgs_view* vi
             continue;
         }
         // success
-        for (int i = 0; i < 5; ++i) {
-            float ms = 0.f;
-            cudaEventElapsedTime(&ms, c->ev[i], c->ev[i + 1]);
-            c->stage_us[i] = ms * 1000.f;
-        }
-        float ms = 0.f;
-        cudaEventElapsedTime(&ms, c->ev[0], c->ev[5]);
-        c->stage_us[5] = ms * 1000.f;
+        c->stage_valid = false;   // stage times are read back lazily (bgs_stage_times_us)
         c->stats.n = n; c->stats.n_visible = c->h_ctr->n_vis; c->stats.n_pairs = c->h_ctr->n_pairs;
         c->stats.tiles_x = (uint32_t)tiles_x; c->stats.tiles_y = (uint32_t)tiles_y;
         c->stats.width = (uint32_t)W; c->stats.height = (uint32_t)H;
@@ -524,6 +518,17 @@ bgs_status bgs_frame_stats_get(bgs_context* c, bgs_frame_stats* out) {
 bgs_status bgs_stage_times_us(bgs_context* c, float out[6]) {
     if (!c || !out) return BGS_EINVAL;
     if (!c->have_frame) return fail(c, BGS_NOT_READY, "no frame rendered yet");
+    if (!c->stage_valid) {
+        for (int i = 0; i < 5; ++i) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, c->ev[i], c->ev[i + 1]);
+            c->stage_us[i] = ms * 1000.f;
+        }
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, c->ev[0], c->ev[5]);
+        c->stage_us[5] = ms * 1000.f;
+        c->stage_valid = true;
+    }
     for (int i = 0; i < 6; ++i) out[i] = c->stage_us[i];
     return BGS_OK;
 }

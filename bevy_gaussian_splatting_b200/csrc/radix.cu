@@ -64,7 +64,7 @@ radix_hist_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict_
 }
 
 // ---- one digit place ------------------------------------------------------------------------
-__global__ void __launch_bounds__(RS_THREADS)
+__global__ void __launch_bounds__(RS_THREADS, 4)
 onesweep_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                 uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
                 const uint32_t* __restrict__ n_ptr, const uint32_t* __restrict__ hist /* raw counts [256] */,
