@@ -13,12 +13,12 @@
 namespace bgs {
 // keygen.cu
 void launch_keygen(const float4* pos, uint32_t n, const FrameConsts& fc, int sort_all, uint32_t* keys_out,
-                   uint32_t* ids_out, uint32_t* status, FrameCounters* ctr, cudaStream_t stream);
+                   uint32_t* ids_out, uint32_t* slots_out, uint32_t* status, FrameCounters* ctr, cudaStream_t stream);
 uint32_t keygen_num_tiles(uint32_t n);
 int keygen_coop_blocks_per_sm();
 cudaError_t launch_keygen_coop(const float4* pos, uint32_t n, const FrameConsts& fc, uint32_t* keys_tmp, uint32_t* keys_out,
-                               uint32_t* ids_out, uint32_t* block_cnt, FrameCounters* ctr, uint32_t grid,
-                               cudaStream_t stream);
+                               uint32_t* ids_out, uint32_t* slots_out, uint32_t* block_cnt, FrameCounters* ctr,
+                               uint32_t grid, cudaStream_t stream);
 void launch_culled_flags(const float4* pos, uint32_t n, const FrameConsts& fc, uint32_t* flags, cudaStream_t stream);
 // radix.cu
 uint32_t radix_num_tiles(uint32_t capacity);
@@ -29,16 +29,17 @@ void launch_onesweep(const uint32_t* keys_in, const uint32_t* vals_in, uint32_t*
                      uint32_t* tile_ctr, int shift, int sm_count, cudaStream_t stream);
 // project.cu
 void launch_project(bool f16, const float4* pos, const void* sh, const void* rot, const void* so,
-                    const uint32_t* sorted_ids, const FrameCounters* ctr, const FrameConsts& fc, SplatRec* recs,
-                    uint32_t n_upper, int sm_count, cudaStream_t stream);
+                    const uint32_t* index_list, int by_slot, const FrameCounters* ctr, const FrameConsts& fc,
+                    SplatRec* recs, uint32_t n_hint, cudaStream_t stream);
 // bin.cu
-void launch_bin_emit(const SplatRec* recs, FrameCounters* ctr, uint32_t* status, int tiles_x, uint32_t capacity,
-                     uint32_t* pair_keys, uint32_t* pair_vals, uint32_t n_upper, int sm_count, cudaStream_t stream);
+void launch_bin_emit(const SplatRec* recs, const uint32_t* perm, FrameCounters* ctr, uint32_t* status, int tiles_x,
+                     uint32_t capacity, uint32_t* pair_keys, uint32_t* pair_vals, uint32_t n_upper, int sm_count,
+                     cudaStream_t stream);
 uint32_t bin_num_tiles(uint32_t n);
 int bin_coop_blocks_per_sm();
-cudaError_t launch_bin_emit_coop(const SplatRec* recs, FrameCounters* ctr, uint32_t* block_cnt, int tiles_x,
-                                 uint32_t capacity, uint32_t* pair_keys, uint32_t* pair_vals, uint32_t* q_rank,
-                                 uint32_t* q_off, uint32_t grid, cudaStream_t stream);
+cudaError_t launch_bin_emit_coop(const SplatRec* recs, const uint32_t* perm, FrameCounters* ctr, uint32_t* block_cnt,
+                                 int tiles_x, uint32_t capacity, uint32_t* pair_keys, uint32_t* pair_vals,
+                                 uint32_t* q_rank, uint32_t* q_off, uint32_t grid, cudaStream_t stream);
 void launch_tile_ranges(const uint32_t* sorted_tile_ids, const FrameCounters* ctr, uint2* ranges, uint32_t capacity,
                         int sm_count, cudaStream_t stream);
 // raster.cu
@@ -63,14 +64,18 @@ struct bgs_context {
     int sm_count = 148;
     int coop = 0;                 // device supports cooperative launch
     uint32_t kg_grid = 0, bin_grid = 0;   // co-resident grid sizes of the cooperative kernels
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;    // render stream (high priority): everything but the projection
+    cudaStream_t stream2 = nullptr;   // projection runs here, beside the depth sort
     cudaEvent_t ev[6] = {};
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_p0 = nullptr, ev_p1 = nullptr;
+    uint32_t n_vis_hint = 0;          // last frame's visible count (sizes the projection grid)
     char err[512] = {0};
 
     // scratch sized by the cloud (grow-only)
     uint32_t cap_n = 0;
     uint32_t* keys[2] = {nullptr, nullptr};
     uint32_t* vals[2] = {nullptr, nullptr};
+    uint32_t* slot_ids = nullptr;     // compact slot -> gaussian index (key-gen output, index order)
     SplatRec* recs = nullptr;
     // scratch sized by the pair capacity (grow-only)
     uint32_t cap_pairs = 0;
@@ -98,6 +103,7 @@ struct bgs_context {
     const bgs_cloud* last_cloud = nullptr;
     FrameConsts last_fc;
     bool last_sort_all = false;
+    bool last_by_slot = false;        // records indexed by compact slot (else by front-to-back rank)
     int depth_result = 0, pair_result = 0;   // which ping-pong buffer holds the sorted result
     bgs_frame_stats stats = {};
     float stage_us[6] = {0, 0, 0, 0, 0, 0};
@@ -140,11 +146,13 @@ bgs_status ensure_cloud_scratch(bgs_context* c, uint32_t n) {
         c->keys[i] = c->vals[i] = nullptr;
     }
     cudaFree(c->recs); c->recs = nullptr;
+    cudaFree(c->slot_ids); c->slot_ids = nullptr;
     c->cap_n = 0;
     for (int i = 0; i < 2; ++i) {
         CU(c, cudaMalloc(&c->keys[i], (size_t)n * 4));
         CU(c, cudaMalloc(&c->vals[i], (size_t)n * 4));
     }
+    CU(c, cudaMalloc(&c->slot_ids, (size_t)n * 4));
     CU(c, cudaMalloc(&c->recs, (size_t)n * sizeof(SplatRec)));
     c->cap_n = n;
     return BGS_OK;
@@ -213,8 +221,15 @@ bgs_status bgs_context_create(int cuda_device, bgs_context** out) {
     if (!c) return BGS_ENOMEM;
     c->device = cuda_device;
     cudaError_t e = cudaSetDevice(cuda_device);
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    int prio_lo = 0, prio_hi = 0;
+    if (e == cudaSuccess) e = cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_hi);
+    if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, prio_lo);
     for (int i = 0; i < 6 && e == cudaSuccess; ++i) e = cudaEventCreate(&c->ev[i]);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->ev_p0);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->ev_p1);
     if (e == cudaSuccess) e = cudaMallocHost(&c->h_ctr, sizeof(FrameCounters));
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, cuda_device);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&c->coop, cudaDevAttrCooperativeLaunch, cuda_device);
@@ -238,13 +253,16 @@ void bgs_context_destroy(bgs_context* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->stream2) cudaStreamSynchronize(c->stream2);
     for (int i = 0; i < 2; ++i) {
         cudaFree(c->keys[i]); cudaFree(c->vals[i]); cudaFree(c->pkeys[i]); cudaFree(c->pvals[i]);
     }
-    cudaFree(c->recs); cudaFree(c->arena); cudaFree(c->frame);
+    cudaFree(c->recs); cudaFree(c->slot_ids); cudaFree(c->arena); cudaFree(c->frame);
     if (c->h_ctr) cudaFreeHost(c->h_ctr);
     for (int i = 0; i < 6; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    for (cudaEvent_t e : {c->ev_fork, c->ev_join, c->ev_p0, c->ev_p1}) if (e) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->stream2) cudaStreamDestroy(c->stream2);
     delete c;
 }
 
@@ -360,15 +378,32 @@ bgs_status bgs_render(bgs_context* c, const bgs_cloud* cloud, const bgs_view* vi
         CU(c, cudaMemsetAsync(c->arena, 0, c->arena_bytes, q));
         CU(c, cudaEventRecord(c->ev[0], q));
         // ---- stage 1: key-gen (+ stable compaction of the visible set)
+        // compact mode: keys[0][slot], slot_ids[slot] = gaussian index, vals[0][slot] = slot (sort payload)
+        // SORT_ALL    : keys[0][i], vals[0][i] = i (payload is the gaussian index itself)
+        const bool by_slot = !sort_all;
         if (!sort_all && c->coop) {
             // cooperative: uncompacted keys go through keys[1] (scratch until the first sort pass overwrites it)
-            CU(c, launch_keygen_coop(cloud->pos, n, fc, c->keys[1], c->keys[0], c->vals[0], c->status_keygen, c->ctr,
-                                     c->kg_grid, q));
+            CU(c, launch_keygen_coop(cloud->pos, n, fc, c->keys[1], c->keys[0], c->slot_ids, c->vals[0], c->status_keygen,
+                                     c->ctr, c->kg_grid, q));
         } else {
-            launch_keygen(cloud->pos, n, fc, sort_all ? 1 : 0, c->keys[0], c->vals[0], c->status_keygen, c->ctr, q);
+            launch_keygen(cloud->pos, n, fc, sort_all ? 1 : 0, c->keys[0], sort_all ? c->vals[0] : c->slot_ids,
+                          sort_all ? c->slot_ids : c->vals[0], c->status_keygen, c->ctr, q);
         }
         ++launches;
         CU(c, cudaEventRecord(c->ev[1], q));
+        // ---- stage 3 (compact mode): projection + colour in slot order on the second stream, concurrently
+        //      with the depth sort (it only needs slot_ids); records land at recs[slot]
+        const uint32_t n_hint = c->n_vis_hint ? c->n_vis_hint + c->n_vis_hint / 4 + 1024 : n;
+        if (by_slot) {
+            CU(c, cudaEventRecord(c->ev_fork, q));
+            CU(c, cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
+            CU(c, cudaEventRecord(c->ev_p0, c->stream2));
+            launch_project(cloud->f16, cloud->pos, cloud->sh, cloud->rot, cloud->so, c->slot_ids, 1, c->ctr, fc, c->recs,
+                           n_hint < n ? n_hint : n, c->stream2);
+            ++launches;
+            CU(c, cudaEventRecord(c->ev_p1, c->stream2));
+            CU(c, cudaEventRecord(c->ev_join, c->stream2));
+        }
         // ---- stage 2: depth radix sort (P = depth_bits / 8 onesweep passes)
         launch_radix_hist(c->keys[0], &c->ctr->n_sort, n, depth_passes, c->hist, c->sm_count, q);
         ++launches;
@@ -383,18 +418,26 @@ bgs_status bgs_render(bgs_context* c, const bgs_cloud* cloud, const bgs_view* vi
         }
         c->depth_result = cur;
         CU(c, cudaEventRecord(c->ev[2], q));
-        // ---- stage 3: projection + colour, front-to-back rank order
-        launch_project(cloud->f16, cloud->pos, cloud->sh, cloud->rot, cloud->so, c->vals[cur], c->ctr, fc, c->recs, n,
-                       c->sm_count, q);
-        ++launches;
+        if (by_slot) {
+            CU(c, cudaStreamWaitEvent(q, c->ev_join, 0));
+        } else {
+            // ---- stage 3 (SORT_ALL): projection in front-to-back rank order after the sort; recs[rank]
+            CU(c, cudaEventRecord(c->ev_p0, q));
+            launch_project(cloud->f16, cloud->pos, cloud->sh, cloud->rot, cloud->so, c->vals[cur], 0, c->ctr, fc, c->recs,
+                           n_hint < n ? n_hint : n, q);
+            ++launches;
+            CU(c, cudaEventRecord(c->ev_p1, q));
+        }
         CU(c, cudaEventRecord(c->ev[3], q));
         // ---- stage 4: tile binning -> stable tile-id sort -> ranges
         if (c->coop) {
             // the depth sort's spare ping-pong buffers (N words each) hold the large-footprint queue
-            CU(c, launch_bin_emit_coop(c->recs, c->ctr, c->status_bin, tiles_x, c->cap_pairs, c->pkeys[0], c->pvals[0],
-                                       c->keys[cur ^ 1], c->vals[cur ^ 1], c->bin_grid, q));
+            CU(c, launch_bin_emit_coop(c->recs, by_slot ? c->vals[cur] : nullptr, c->ctr, c->status_bin, tiles_x,
+                                       c->cap_pairs, c->pkeys[0], c->pvals[0], c->keys[cur ^ 1], c->vals[cur ^ 1],
+                                       c->bin_grid, q));
         } else {
-            launch_bin_emit(c->recs, c->ctr, c->status_bin, tiles_x, c->cap_pairs, c->pkeys[0], c->pvals[0], n, c->sm_count, q);
+            launch_bin_emit(c->recs, by_slot ? c->vals[cur] : nullptr, c->ctr, c->status_bin, tiles_x, c->cap_pairs,
+                            c->pkeys[0], c->pvals[0], n, c->sm_count, q);
         }
         ++launches;
         launch_radix_hist(c->pkeys[0], &c->ctr->n_pairs, c->cap_pairs, tile_passes, c->hist + 4 * 256, c->sm_count, q);
@@ -438,6 +481,7 @@ bgs_status bgs_render(bgs_context* c, const bgs_cloud* cloud, const bgs_view* vi
         c->stats.tiles_x = (uint32_t)tiles_x; c->stats.tiles_y = (uint32_t)tiles_y;
         c->stats.width = (uint32_t)W; c->stats.height = (uint32_t)H;
         c->have_frame = true; c->last_cloud = cloud; c->last_fc = fc; c->last_sort_all = sort_all;
+        c->last_by_slot = by_slot; c->n_vis_hint = c->h_ctr->n_vis;
         c->last_frame = target;
         c->err[0] = 0;
         return BGS_OK;
@@ -454,6 +498,11 @@ bgs_status bgs_debug_sorted_entries(bgs_context* c, uint32_t* out) {
     std::vector<uint32_t> k(n_sorted), v(n_sorted);
     CU(c, cudaMemcpy(k.data(), c->keys[c->depth_result], (size_t)n_sorted * 4, cudaMemcpyDeviceToHost));
     CU(c, cudaMemcpy(v.data(), c->vals[c->depth_result], (size_t)n_sorted * 4, cudaMemcpyDeviceToHost));
+    if (c->last_by_slot) {   // the sort's payload is the compact slot: map it to the gaussian index
+        std::vector<uint32_t> ids(n_sorted);
+        CU(c, cudaMemcpy(ids.data(), c->slot_ids, (size_t)n_sorted * 4, cudaMemcpyDeviceToHost));
+        for (uint32_t i = 0; i < n_sorted; ++i) v[i] = ids[v[i]];
+    }
     for (uint32_t i = 0; i < n_sorted; ++i) { out[2 * i] = k[i]; out[2 * i + 1] = v[i]; }
     if (!c->last_sort_all) {
         // culled tail: key = all-ones >> shift, indices ascending (what a stable sort leaves there)
@@ -491,6 +540,13 @@ bgs_status bgs_debug_tile_entries(bgs_context* c, uint32_t* ranks, uint64_t capa
     CU(c, cudaSetDevice(c->device));
     const uint64_t cnt = c->stats.n_pairs < capacity ? c->stats.n_pairs : capacity;
     CU(c, cudaMemcpy(ranks, c->pvals[c->pair_result], (size_t)cnt * 4, cudaMemcpyDeviceToHost));
+    if (c->last_by_slot) {   // pair payload = record index = compact slot: convert to front-to-back rank
+        const uint32_t n_vis = c->stats.n_visible;
+        std::vector<uint32_t> perm(n_vis), inv(n_vis);
+        CU(c, cudaMemcpy(perm.data(), c->vals[c->depth_result], (size_t)n_vis * 4, cudaMemcpyDeviceToHost));
+        for (uint32_t r = 0; r < n_vis; ++r) inv[perm[n_vis - 1 - r]] = r;
+        for (uint64_t i = 0; i < cnt; ++i) ranks[i] = ranks[i] < n_vis ? inv[ranks[i]] : 0xFFFFFFFFu;
+    }
     return BGS_OK;
 }
 
@@ -499,12 +555,22 @@ bgs_status bgs_debug_projected(bgs_context* c, float* records, uint32_t* rank_to
     if (!c->have_frame) return fail(c, BGS_NOT_READY, "no frame rendered yet");
     CU(c, cudaSetDevice(c->device));
     const uint32_t n_vis = c->stats.n_visible;
-    if (records) CU(c, cudaMemcpy(records, c->recs, (size_t)n_vis * sizeof(SplatRec), cudaMemcpyDeviceToHost));
-    if (rank_to_index) {
-        std::vector<uint32_t> v(n_vis);
-        CU(c, cudaMemcpy(v.data(), c->vals[c->depth_result], (size_t)n_vis * 4, cudaMemcpyDeviceToHost));
-        for (uint32_t r = 0; r < n_vis; ++r) rank_to_index[r] = v[n_vis - 1 - r];
+    std::vector<uint32_t> v(n_vis), ids;
+    CU(c, cudaMemcpy(v.data(), c->vals[c->depth_result], (size_t)n_vis * 4, cudaMemcpyDeviceToHost));
+    if (c->last_by_slot) {
+        ids.resize(n_vis);
+        CU(c, cudaMemcpy(ids.data(), c->slot_ids, (size_t)n_vis * 4, cudaMemcpyDeviceToHost));
     }
+    if (records) {
+        std::vector<SplatRec> tmp(n_vis);
+        CU(c, cudaMemcpy(tmp.data(), c->recs, (size_t)n_vis * sizeof(SplatRec), cudaMemcpyDeviceToHost));
+        for (uint32_t r = 0; r < n_vis; ++r) {
+            const uint32_t ri = c->last_by_slot ? v[n_vis - 1 - r] : r;   // rank -> record index
+            memcpy(records + (size_t)r * 12, &tmp[ri], sizeof(SplatRec));
+        }
+    }
+    if (rank_to_index)
+        for (uint32_t r = 0; r < n_vis; ++r) rank_to_index[r] = c->last_by_slot ? ids[v[n_vis - 1 - r]] : v[n_vis - 1 - r];
     return BGS_OK;
 }
 
@@ -523,6 +589,11 @@ bgs_status bgs_stage_times_us(bgs_context* c, float out[6]) {
             float ms = 0.f;
             cudaEventElapsedTime(&ms, c->ev[i], c->ev[i + 1]);
             c->stage_us[i] = ms * 1000.f;
+        }
+        {   // the projection may overlap the sort (second stream): report its own duration
+            float pms = 0.f;
+            cudaEventElapsedTime(&pms, c->ev_p0, c->ev_p1);
+            c->stage_us[2] = pms * 1000.f;
         }
         float ms = 0.f;
         cudaEventElapsedTime(&ms, c->ev[0], c->ev[5]);

@@ -2,7 +2,7 @@
 // reference, which rasterises one instanced quad per gaussian: src/render/mod.rs:1562-1566).
 //
 // For every visible splat in front-to-back rank order, emit one (tile id, rank) pair per 16x16
-// tile its conservative pixel bbox touches.  Pair offsets come from a single-pass chained scan
+// tile its conservative pixel bbox touches (payload = the splat's record index).  Pair offsets come from a single-pass chained scan
 // (decoupled look-back) over the per-splat tile counts, so pairs are emitted in rank order and
 // the stable tile-id radix sort that follows yields, per tile, a slice of the GLOBAL depth order.
 // range build: boundaries of equal tile ids in the sorted pair keys.
@@ -16,8 +16,9 @@ constexpr int BIN_TILE = BIN_THREADS * BIN_ITEMS;
 constexpr uint32_t BIN_BIG = 16u;   // splats touching more tiles than this are emitted by the whole block
 
 __global__ void __launch_bounds__(BIN_THREADS)
-bin_emit_kernel(const SplatRec* __restrict__ recs, FrameCounters* __restrict__ ctr, uint32_t* __restrict__ status,
-                int tiles_x, uint32_t capacity, uint32_t* __restrict__ pair_keys, uint32_t* __restrict__ pair_vals) {
+bin_emit_kernel(const SplatRec* __restrict__ recs, const uint32_t* __restrict__ perm, FrameCounters* __restrict__ ctr,
+                uint32_t* __restrict__ status, int tiles_x, uint32_t capacity, uint32_t* __restrict__ pair_keys,
+                uint32_t* __restrict__ pair_vals) {
     __shared__ uint32_t s_wtot[BIN_THREADS / 32];
     __shared__ uint32_t s_base;
     __shared__ uint32_t s_tile;
@@ -32,14 +33,15 @@ bin_emit_kernel(const SplatRec* __restrict__ recs, FrameCounters* __restrict__ c
         const uint32_t tile = s_tile;
         if (tile >= num_tiles) break;
         const uint32_t r0 = tile * BIN_TILE + t * BIN_ITEMS;   // blocked: 4 consecutive ranks per thread
-        uint32_t bx[BIN_ITEMS], by[BIN_ITEMS], cnt[BIN_ITEMS];
+        uint32_t bx[BIN_ITEMS], by[BIN_ITEMS], cnt[BIN_ITEMS], ri[BIN_ITEMS];
         uint32_t mine = 0u;
 #pragma unroll
         for (int j = 0; j < BIN_ITEMS; ++j) {
             const uint32_t r = r0 + j;
-            cnt[j] = 0u;
+            cnt[j] = 0u; ri[j] = 0u;
             if (r < n_vis) {
-                const uint2 b = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const char*>(recs + r) + 24));
+                ri[j] = perm ? __ldg(perm + (n_vis - 1u - r)) : r;   // rank -> record index
+                const uint2 b = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const char*>(recs + ri[j]) + 24));
                 bx[j] = b.x; by[j] = b.y;
                 const uint32_t xlo = b.x & 0xFFFFu, xhi = b.x >> 16, ylo = b.y & 0xFFFFu, yhi = b.y >> 16;
                 if (xlo <= xhi && ylo <= yhi)
@@ -79,7 +81,7 @@ bin_emit_kernel(const SplatRec* __restrict__ recs, FrameCounters* __restrict__ c
 #pragma unroll
         for (int j = 0; j < BIN_ITEMS; ++j) {
             if (cnt[j] == 0u) continue;
-            const uint32_t r = r0 + j;
+            const uint32_t r = ri[j];
             if (cnt[j] > BIN_BIG) {
                 // large footprint: hand it to the whole block (coalesced, parallel emission below)
                 const uint32_t q = atomicAdd(&s_nbig, 1u);
@@ -128,9 +130,9 @@ bin_emit_kernel(const SplatRec* __restrict__ recs, FrameCounters* __restrict__ c
 //   phase 3: all warps of the grid drain the queue (front-most splats cover hundreds of tiles and all
 //            sit in the first CTAs' ranges: without this the frame waits on a handful of CTAs)
 __global__ void __launch_bounds__(BIN_THREADS)
-bin_emit_coop_kernel(const SplatRec* __restrict__ recs, FrameCounters* __restrict__ ctr, uint32_t* __restrict__ block_cnt,
-                     int tiles_x, uint32_t capacity, uint32_t* __restrict__ pair_keys, uint32_t* __restrict__ pair_vals,
-                     uint32_t* __restrict__ q_rank, uint32_t* __restrict__ q_off) {
+bin_emit_coop_kernel(const SplatRec* __restrict__ recs, const uint32_t* __restrict__ perm, FrameCounters* __restrict__ ctr,
+                     uint32_t* __restrict__ block_cnt, int tiles_x, uint32_t capacity, uint32_t* __restrict__ pair_keys,
+                     uint32_t* __restrict__ pair_vals, uint32_t* __restrict__ q_rank, uint32_t* __restrict__ q_off) {
     __shared__ uint32_t s_wtot[BIN_THREADS / 32];
     __shared__ uint32_t s_wbig[BIN_THREADS / 32];
     __shared__ uint32_t s_red[BIN_THREADS / 32];
@@ -143,9 +145,10 @@ bin_emit_coop_kernel(const SplatRec* __restrict__ recs, FrameCounters* __restric
     const uint32_t tiles_total = (n_vis + BIN_TILE - 1) / BIN_TILE;
     const uint32_t t0 = (uint32_t)((uint64_t)b * tiles_total / G), t1 = (uint32_t)((uint64_t)(b + 1) * tiles_total / G);
 
-    auto tiles_of = [&](uint32_t r, uint32_t& bx, uint32_t& by) -> uint32_t {
+    auto tiles_of = [&](uint32_t r, uint32_t& bx, uint32_t& by, uint32_t& ri) -> uint32_t {
         if (r >= n_vis) return 0u;
-        const uint2 bb = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const char*>(recs + r) + 24));
+        ri = perm ? __ldg(perm + (n_vis - 1u - r)) : r;   // rank -> record index
+        const uint2 bb = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const char*>(recs + ri) + 24));
         bx = bb.x; by = bb.y;
         const uint32_t xlo = bb.x & 0xFFFFu, xhi = bb.x >> 16, ylo = bb.y & 0xFFFFu, yhi = bb.y >> 16;
         if (xlo <= xhi && ylo <= yhi) return ((xhi >> 4) - (xlo >> 4) + 1u) * ((yhi >> 4) - (ylo >> 4) + 1u);
@@ -157,8 +160,8 @@ bin_emit_coop_kernel(const SplatRec* __restrict__ recs, FrameCounters* __restric
     for (uint32_t tile = t0; tile < t1; ++tile) {
 #pragma unroll
         for (int j = 0; j < BIN_ITEMS; ++j) {
-            uint32_t bx, by;
-            mine += tiles_of(tile * BIN_TILE + t * BIN_ITEMS + j, bx, by);
+            uint32_t bx, by, ri;
+            mine += tiles_of(tile * BIN_TILE + t * BIN_ITEMS + j, bx, by, ri);
         }
     }
 #pragma unroll
@@ -195,12 +198,12 @@ bin_emit_coop_kernel(const SplatRec* __restrict__ recs, FrameCounters* __restric
     uint32_t run = run64 > LB_VMASK ? LB_VMASK : (uint32_t)run64;
     for (uint32_t tile = t0; tile < t1; ++tile) {
         const uint32_t r0 = tile * BIN_TILE + t * BIN_ITEMS;
-        uint32_t bx[BIN_ITEMS], by[BIN_ITEMS], cnt[BIN_ITEMS];
+        uint32_t bx[BIN_ITEMS], by[BIN_ITEMS], cnt[BIN_ITEMS], ri[BIN_ITEMS];
         uint32_t tmine = 0u, nbig = 0u;
 #pragma unroll
         for (int j = 0; j < BIN_ITEMS; ++j) {
-            bx[j] = 0u; by[j] = 0u;
-            cnt[j] = tiles_of(r0 + j, bx[j], by[j]);
+            bx[j] = 0u; by[j] = 0u; ri[j] = 0u;
+            cnt[j] = tiles_of(r0 + j, bx[j], by[j], ri[j]);
             tmine += cnt[j];
             nbig += cnt[j] > BIN_BIG ? 1u : 0u;
         }
@@ -227,7 +230,7 @@ bin_emit_coop_kernel(const SplatRec* __restrict__ recs, FrameCounters* __restric
 #pragma unroll
         for (int j = 0; j < BIN_ITEMS; ++j) {
             if (cnt[j] == 0u) continue;
-            const uint32_t r = r0 + j;
+            const uint32_t r = ri[j];
             if (cnt[j] > BIN_BIG) {
                 q_rank[qat] = r; q_off[qat] = off; ++qat;
             } else {
@@ -286,13 +289,14 @@ __global__ void tile_ranges_kernel(const uint32_t* __restrict__ sorted_tile_ids,
     }
 }
 
-void launch_bin_emit(const SplatRec* recs, FrameCounters* ctr, uint32_t* status, int tiles_x, uint32_t capacity,
-                     uint32_t* pair_keys, uint32_t* pair_vals, uint32_t n_upper, int sm_count, cudaStream_t stream) {
+void launch_bin_emit(const SplatRec* recs, const uint32_t* perm, FrameCounters* ctr, uint32_t* status, int tiles_x,
+                     uint32_t capacity, uint32_t* pair_keys, uint32_t* pair_vals, uint32_t n_upper, int sm_count,
+                     cudaStream_t stream) {
     uint32_t blocks = (n_upper + BIN_TILE - 1) / BIN_TILE;
     const uint32_t cap_blocks = (uint32_t)sm_count * 4u;
     if (blocks > cap_blocks) blocks = cap_blocks;
     if (blocks == 0) blocks = 1;
-    bin_emit_kernel<<<blocks, BIN_THREADS, 0, stream>>>(recs, ctr, status, tiles_x, capacity, pair_keys, pair_vals);
+    bin_emit_kernel<<<blocks, BIN_THREADS, 0, stream>>>(recs, perm, ctr, status, tiles_x, capacity, pair_keys, pair_vals);
 }
 uint32_t bin_num_tiles(uint32_t n) { return (n + BIN_TILE - 1) / BIN_TILE; }
 
@@ -301,10 +305,10 @@ int bin_coop_blocks_per_sm() {
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, bin_emit_coop_kernel, BIN_THREADS, 0) != cudaSuccess) return 0;
     return b;
 }
-cudaError_t launch_bin_emit_coop(const SplatRec* recs, FrameCounters* ctr, uint32_t* block_cnt, int tiles_x,
-                                 uint32_t capacity, uint32_t* pair_keys, uint32_t* pair_vals, uint32_t* q_rank,
-                                 uint32_t* q_off, uint32_t grid, cudaStream_t stream) {
-    void* args[] = {(void*)&recs, (void*)&ctr, (void*)&block_cnt, (void*)&tiles_x, (void*)&capacity, (void*)&pair_keys,
+cudaError_t launch_bin_emit_coop(const SplatRec* recs, const uint32_t* perm, FrameCounters* ctr, uint32_t* block_cnt,
+                                 int tiles_x, uint32_t capacity, uint32_t* pair_keys, uint32_t* pair_vals,
+                                 uint32_t* q_rank, uint32_t* q_off, uint32_t grid, cudaStream_t stream) {
+    void* args[] = {(void*)&recs, (void*)&perm, (void*)&ctr, (void*)&block_cnt, (void*)&tiles_x, (void*)&capacity, (void*)&pair_keys,
                     (void*)&pair_vals, (void*)&q_rank, (void*)&q_off};
     return cudaLaunchCooperativeKernel((const void*)bin_emit_coop_kernel, dim3(grid), dim3(BIN_THREADS), args, 0, stream);
 }

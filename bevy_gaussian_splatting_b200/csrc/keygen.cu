@@ -19,7 +19,7 @@ constexpr int KG_TILE = KG_THREADS * KG_ITEMS;
 
 __global__ void __launch_bounds__(KG_THREADS)
 keygen_compact_kernel(const float4* __restrict__ pos, uint32_t n, FrameConsts fc, int sort_all,
-                      uint32_t* __restrict__ keys_out, uint32_t* __restrict__ ids_out,
+                      uint32_t* __restrict__ keys_out, uint32_t* __restrict__ ids_out, uint32_t* __restrict__ slots_out,
                       uint32_t* __restrict__ status, FrameCounters* __restrict__ ctr) {
     __shared__ uint32_t s_cnt[KG_ITEMS * (KG_THREADS / 32)];
     __shared__ uint32_t s_off[KG_ITEMS * (KG_THREADS / 32)];
@@ -97,6 +97,7 @@ keygen_compact_kernel(const float4* __restrict__ pos, uint32_t n, FrameConsts fc
             const uint32_t dst = base + s_off[j * (KG_THREADS / 32) + warp] + prefix[j];
             keys_out[dst] = key[j];
             ids_out[dst] = tile_base + j * KG_THREADS + t;
+            slots_out[dst] = dst;
         }
     }
 }
@@ -108,8 +109,8 @@ keygen_compact_kernel(const float4* __restrict__ pos, uint32_t n, FrameConsts fc
 // its own keys from L2 and writes the visible (key, index) pairs compacted in index order.
 __global__ void __launch_bounds__(KG_THREADS)
 keygen_coop_kernel(const float4* __restrict__ pos, uint32_t n, FrameConsts fc, uint32_t* __restrict__ keys_tmp,
-                   uint32_t* __restrict__ keys_out, uint32_t* __restrict__ ids_out, uint32_t* __restrict__ block_cnt,
-                   FrameCounters* __restrict__ ctr) {
+                   uint32_t* __restrict__ keys_out, uint32_t* __restrict__ ids_out, uint32_t* __restrict__ slots_out,
+                   uint32_t* __restrict__ block_cnt, FrameCounters* __restrict__ ctr) {
     __shared__ uint32_t s_cnt[KG_ITEMS * (KG_THREADS / 32)];
     __shared__ uint32_t s_off[KG_ITEMS * (KG_THREADS / 32)];
     __shared__ uint32_t s_red[KG_THREADS / 32];
@@ -194,7 +195,8 @@ keygen_coop_kernel(const float4* __restrict__ pos, uint32_t n, FrameConsts fc, u
             if (vis_bits & (1u << j)) {
                 const uint32_t dst = run + s_off[j * (KG_THREADS / 32) + warp] + prefix[j];
                 keys_out[dst] = key[j];
-                ids_out[dst] = tile_base + j * KG_THREADS + t;
+                ids_out[dst] = tile_base + j * KG_THREADS + t;   // compact slot -> gaussian index
+                slots_out[dst] = dst;                            // the sort's payload: the compact slot
             }
         }
         run += s_total;
@@ -214,9 +216,9 @@ __global__ void culled_flags_kernel(const float4* __restrict__ pos, uint32_t n, 
 }
 
 void launch_keygen(const float4* pos, uint32_t n, const FrameConsts& fc, int sort_all, uint32_t* keys_out,
-                   uint32_t* ids_out, uint32_t* status, FrameCounters* ctr, cudaStream_t stream) {
+                   uint32_t* ids_out, uint32_t* slots_out, uint32_t* status, FrameCounters* ctr, cudaStream_t stream) {
     const uint32_t tiles = (n + KG_TILE - 1) / KG_TILE;
-    keygen_compact_kernel<<<tiles, KG_THREADS, 0, stream>>>(pos, n, fc, sort_all, keys_out, ids_out, status, ctr);
+    keygen_compact_kernel<<<tiles, KG_THREADS, 0, stream>>>(pos, n, fc, sort_all, keys_out, ids_out, slots_out, status, ctr);
 }
 uint32_t keygen_num_tiles(uint32_t n) { return (n + KG_TILE - 1) / KG_TILE; }
 
@@ -226,11 +228,11 @@ int keygen_coop_blocks_per_sm() {
     return b;
 }
 cudaError_t launch_keygen_coop(const float4* pos, uint32_t n, const FrameConsts& fc, uint32_t* keys_tmp, uint32_t* keys_out,
-                               uint32_t* ids_out, uint32_t* block_cnt, FrameCounters* ctr, uint32_t grid,
-                               cudaStream_t stream) {
+                               uint32_t* ids_out, uint32_t* slots_out, uint32_t* block_cnt, FrameCounters* ctr,
+                               uint32_t grid, cudaStream_t stream) {
     FrameConsts fcc = fc;
     void* args[] = {(void*)&pos, (void*)&n, (void*)&fcc, (void*)&keys_tmp, (void*)&keys_out, (void*)&ids_out,
-                    (void*)&block_cnt, (void*)&ctr};
+                    (void*)&slots_out, (void*)&block_cnt, (void*)&ctr};
     return cudaLaunchCooperativeKernel((const void*)keygen_coop_kernel, dim3(grid), dim3(KG_THREADS), args, 0, stream);
 }
 

@@ -97,11 +97,13 @@ struct Attr<true> {    // f16 planes: src/gaussian/f16.rs:30-56,244-263; planar.
 template <bool F16>
 __global__ void __launch_bounds__(128)
 project_kernel(const float4* __restrict__ pos, const void* __restrict__ sh_p, const void* __restrict__ rot_p,
-               const void* __restrict__ so_p, const uint32_t* __restrict__ sorted_ids,
+               const void* __restrict__ so_p, const uint32_t* __restrict__ index_list, int by_slot,
                const FrameCounters* __restrict__ ctr, FrameConsts fc, SplatRec* __restrict__ recs) {
     const uint32_t n_vis = ctr->n_vis;
     for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n_vis; r += gridDim.x * blockDim.x) {
-        const uint32_t id = __ldg(sorted_ids + (n_vis - 1u - r));
+        // by_slot: r is a compact slot (ascending gaussian index; runs concurrently with the depth sort)
+        // else   : r is a front-to-back rank, the list is the far->near sorted index list
+        const uint32_t id = by_slot ? __ldg(index_list + r) : __ldg(index_list + (n_vis - 1u - r));
         const float4 p4 = __ldg(pos + id);
         float sh[48], q[4], so[4];
         const bool need_sh = fc.rasterize_mode == BGS_RASTERIZE_COLOR;
@@ -281,14 +283,15 @@ project_kernel(const float4* __restrict__ pos, const void* __restrict__ sh_p, co
 }
 
 void launch_project(bool f16, const float4* pos, const void* sh, const void* rot, const void* so,
-                    const uint32_t* sorted_ids, const FrameCounters* ctr, const FrameConsts& fc, SplatRec* recs,
-                    uint32_t n_upper, int sm_count, cudaStream_t stream) {
-    uint32_t blocks = (n_upper + 127) / 128;
-    const uint32_t cap_blocks = (uint32_t)sm_count * 8u;
-    if (blocks > cap_blocks) blocks = cap_blocks;
-    if (blocks == 0) blocks = 1;
-    if (f16) project_kernel<true><<<blocks, 128, 0, stream>>>(pos, sh, rot, so, sorted_ids, ctr, fc, recs);
-    else project_kernel<false><<<blocks, 128, 0, stream>>>(pos, sh, rot, so, sorted_ids, ctr, fc, recs);
+                    const uint32_t* index_list, int by_slot, const FrameCounters* ctr, const FrameConsts& fc,
+                    SplatRec* recs, uint32_t n_hint, cudaStream_t stream) {
+    // grid sized from a hint (last frame's visible count + head-room); the grid-stride loop keeps any
+    // n_vis correct.  Short-lived CTAs (not a persistent grid) so a concurrent sort can interleave.
+    uint32_t blocks = (n_hint + 127) / 128;
+    if (blocks > 65535u * 8u) blocks = 65535u * 8u;
+    if (blocks < 148u) blocks = 148u;
+    if (f16) project_kernel<true><<<blocks, 128, 0, stream>>>(pos, sh, rot, so, index_list, by_slot, ctr, fc, recs);
+    else project_kernel<false><<<blocks, 128, 0, stream>>>(pos, sh, rot, so, index_list, by_slot, ctr, fc, recs);
 }
 
 }  // namespace bgs
