@@ -25,7 +25,7 @@ uint32_t radix_num_tiles(uint32_t capacity);
 void launch_radix_hist(const uint32_t* keys, const uint32_t* n_ptr, uint32_t capacity, int passes, uint32_t* hist,
                        int sm_count, cudaStream_t stream);
 void launch_onesweep(const uint32_t* keys_in, const uint32_t* vals_in, uint32_t* keys_out, uint32_t* vals_out,
-                     const uint32_t* n_ptr, uint32_t capacity, const uint32_t* hist, uint32_t* status,
+                     const uint32_t* n_ptr, uint32_t capacity, uint32_t n_hint, const uint32_t* hist, uint32_t* status,
                      uint32_t* tile_ctr, int shift, int sm_count, cudaStream_t stream);
 // project.cu
 void launch_project(bool f16, const float4* pos, const void* sh, const void* rot, const void* so,
@@ -69,6 +69,7 @@ struct bgs_context {
     cudaEvent_t ev[6] = {};
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_p0 = nullptr, ev_p1 = nullptr;
     uint32_t n_vis_hint = 0;          // last frame's visible count (sizes the projection grid)
+    uint32_t n_pairs_hint = 0;        // last frame's pair count (picks the pair sort's tile size)
     char err[512] = {0};
 
     // scratch sized by the cloud (grow-only)
@@ -85,6 +86,9 @@ struct bgs_context {
     uint8_t* arena = nullptr;
     size_t arena_bytes = 0;
     uint32_t arena_n = 0, arena_pairs = 0, arena_tiles = 0;
+    size_t arena_small_bytes = 0;      // [0, small): cleared at frame start; [small, end): look-back status rows,
+    bool status_clean_pending = false; // cleared right AFTER a frame on stream2 (off the critical path)
+    cudaEvent_t ev_done = nullptr, ev_clean = nullptr;
     FrameCounters* ctr = nullptr;
     uint32_t* hist = nullptr;          // [8][256]: depth passes 0..3, pair passes 4..7
     uint32_t* status_keygen = nullptr;
@@ -189,6 +193,8 @@ bgs_status ensure_arena(bgs_context* c, uint32_t n, uint32_t pairs, uint32_t til
     const size_t o_sp = off; off = align_up(off + (size_t)4 * radix_num_tiles(pairs) * 256 * 4, 256);
     CU(c, cudaMalloc(&c->arena, off));
     c->arena_bytes = off;
+    c->arena_small_bytes = o_sd;
+    c->status_clean_pending = false;
     c->ctr = reinterpret_cast<FrameCounters*>(c->arena + o_ctr);
     c->hist = reinterpret_cast<uint32_t*>(c->arena + o_hist);
     c->status_keygen = reinterpret_cast<uint32_t*>(c->arena + o_skg);
@@ -228,6 +234,8 @@ bgs_status bgs_context_create(int cuda_device, bgs_context** out) {
     for (int i = 0; i < 6 && e == cudaSuccess; ++i) e = cudaEventCreate(&c->ev[i]);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_done, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_clean, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev_p0);
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev_p1);
     if (e == cudaSuccess) e = cudaMallocHost(&c->h_ctr, sizeof(FrameCounters));
@@ -260,7 +268,7 @@ void bgs_context_destroy(bgs_context* c) {
     cudaFree(c->recs); cudaFree(c->slot_ids); cudaFree(c->arena); cudaFree(c->frame);
     if (c->h_ctr) cudaFreeHost(c->h_ctr);
     for (int i = 0; i < 6; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
-    for (cudaEvent_t e : {c->ev_fork, c->ev_join, c->ev_p0, c->ev_p1}) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : {c->ev_fork, c->ev_join, c->ev_p0, c->ev_p1, c->ev_done, c->ev_clean}) if (e) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
     if (c->stream2) cudaStreamDestroy(c->stream2);
     delete c;
@@ -375,7 +383,14 @@ bgs_status bgs_render(bgs_context* c, const bgs_cloud* cloud, const bgs_view* vi
         if (s != BGS_OK) return s;
         cudaStream_t q = c->stream;
         uint32_t launches = 0;
-        CU(c, cudaMemsetAsync(c->arena, 0, c->arena_bytes, q));
+        if (c->status_clean_pending) {
+            // the big look-back status rows were cleared on stream2 right after the previous frame
+            CU(c, cudaStreamWaitEvent(q, c->ev_clean, 0));
+            CU(c, cudaMemsetAsync(c->arena, 0, c->arena_small_bytes, q));
+        } else {
+            CU(c, cudaMemsetAsync(c->arena, 0, c->arena_bytes, q));
+        }
+        c->status_clean_pending = false;
         CU(c, cudaEventRecord(c->ev[0], q));
         // ---- stage 1: key-gen (+ stable compaction of the visible set)
         // compact mode: keys[0][slot], slot_ids[slot] = gaussian index, vals[0][slot] = slot (sort payload)
@@ -411,7 +426,7 @@ bgs_status bgs_render(bgs_context* c, const bgs_cloud* cloud, const bgs_view* vi
         const size_t depth_status_stride = (size_t)radix_num_tiles(c->arena_n) * 256;
         for (int p = 0; p < depth_passes; ++p) {
             launch_onesweep(c->keys[cur], c->vals[cur], c->keys[cur ^ 1], c->vals[cur ^ 1], &c->ctr->n_sort, n,
-                            c->hist + p * 256, c->status_depth + p * depth_status_stride, &c->ctr->tile_ctr[1 + p],
+                            sort_all ? n : (c->n_vis_hint ? c->n_vis_hint : n), c->hist + p * 256, c->status_depth + p * depth_status_stride, &c->ctr->tile_ctr[1 + p],
                             8 * p, c->sm_count, q);
             ++launches;
             cur ^= 1;
@@ -446,7 +461,7 @@ bgs_status bgs_render(bgs_context* c, const bgs_cloud* cloud, const bgs_view* vi
         const size_t pair_status_stride = (size_t)radix_num_tiles(c->arena_pairs) * 256;
         for (int p = 0; p < tile_passes; ++p) {
             launch_onesweep(c->pkeys[pcur], c->pvals[pcur], c->pkeys[pcur ^ 1], c->pvals[pcur ^ 1], &c->ctr->n_pairs,
-                            c->cap_pairs, c->hist + (4 + p) * 256, c->status_pairs + p * pair_status_stride,
+                            c->cap_pairs, c->n_pairs_hint ? c->n_pairs_hint : c->cap_pairs, c->hist + (4 + p) * 256, c->status_pairs + p * pair_status_stride,
                             &c->ctr->tile_ctr[6 + p], 8 * p, c->sm_count, q);
             ++launches;
             pcur ^= 1;
@@ -459,9 +474,15 @@ bgs_status bgs_render(bgs_context* c, const bgs_cloud* cloud, const bgs_view* vi
         launch_raster(c->recs, c->pvals[pcur], c->ranges, W, H, tiles_x, tiles_y, target, out_format, q);
         ++launches;
         CU(c, cudaEventRecord(c->ev[5], q));
+        CU(c, cudaEventRecord(c->ev_done, q));
         CU(c, cudaMemcpyAsync(c->h_ctr, c->ctr, sizeof(FrameCounters), cudaMemcpyDeviceToHost, q));
         if (out_rgba && !out_is_device_ptr)
             CU(c, cudaMemcpyAsync(out_rgba, target, frame_bytes, cudaMemcpyDeviceToHost, q));
+        // pre-clean the status rows for the next frame, off the critical path
+        CU(c, cudaStreamWaitEvent(c->stream2, c->ev_done, 0));
+        CU(c, cudaMemsetAsync(c->arena + c->arena_small_bytes, 0, c->arena_bytes - c->arena_small_bytes, c->stream2));
+        CU(c, cudaEventRecord(c->ev_clean, c->stream2));
+        c->status_clean_pending = true;
         CU(c, cudaStreamSynchronize(q));
         CU(c, cudaGetLastError());
         c->launches = launches;
@@ -481,7 +502,7 @@ bgs_status bgs_render(bgs_context* c, const bgs_cloud* cloud, const bgs_view* vi
         c->stats.tiles_x = (uint32_t)tiles_x; c->stats.tiles_y = (uint32_t)tiles_y;
         c->stats.width = (uint32_t)W; c->stats.height = (uint32_t)H;
         c->have_frame = true; c->last_cloud = cloud; c->last_fc = fc; c->last_sort_all = sort_all;
-        c->last_by_slot = by_slot; c->n_vis_hint = c->h_ctr->n_vis;
+        c->last_by_slot = by_slot; c->n_vis_hint = c->h_ctr->n_vis; c->n_pairs_hint = c->h_ctr->n_pairs;
         c->last_frame = target;
         c->err[0] = 0;
         return BGS_OK;

@@ -13,7 +13,7 @@ namespace bgs {
 constexpr int BIN_THREADS = 256;
 constexpr int BIN_ITEMS = 4;
 constexpr int BIN_TILE = BIN_THREADS * BIN_ITEMS;
-constexpr uint32_t BIN_BIG = 16u;   // splats touching more tiles than this are emitted by the whole block
+constexpr uint32_t BIN_BIG = 48u;   // splats touching more tiles than this are emitted by the whole block
 
 __global__ void __launch_bounds__(BIN_THREADS)
 bin_emit_kernel(const SplatRec* __restrict__ recs, const uint32_t* __restrict__ perm, FrameCounters* __restrict__ ctr,

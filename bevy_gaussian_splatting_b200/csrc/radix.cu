@@ -15,8 +15,7 @@ namespace bgs {
 
 constexpr int RS_THREADS = 256;
 constexpr int RS_WARPS = RS_THREADS / 32;
-constexpr int RS_ITEMS = 16;
-constexpr int RS_TILE = RS_THREADS * RS_ITEMS;   // 4096 entries per tile
+constexpr int RS_ITEMS_MIN = 8;                  // small sorts: 2048-entry tiles (latency), large: 4096 (throughput)
 constexpr int LB_BATCH = 8;                       // look-back loads in flight per thread
 
 // ---- digit histograms for all passes in one read of the keys -----------------------------
@@ -64,12 +63,14 @@ radix_hist_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict_
 }
 
 // ---- one digit place ------------------------------------------------------------------------
+template <int RS_ITEMS>
 __global__ void __launch_bounds__(RS_THREADS, 4)
 onesweep_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                 uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
                 const uint32_t* __restrict__ n_ptr, const uint32_t* __restrict__ hist /* raw counts [256] */,
                 uint32_t* __restrict__ status /* [tiles][256], zeroed */, uint32_t* __restrict__ tile_ctr,
                 int shift) {
+    constexpr int RS_TILE = RS_THREADS * RS_ITEMS;
     __shared__ uint32_t s_keys[RS_TILE];
     __shared__ uint32_t s_vals[RS_TILE];
     __shared__ uint32_t s_whist[RS_WARPS][256];   // per-warp digit counts -> per-warp exclusive offsets
@@ -218,7 +219,11 @@ onesweep_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict
 }
 
 // ---- host-side launch helpers ------------------------------------------------------------------
-uint32_t radix_num_tiles(uint32_t capacity) { return (capacity + RS_TILE - 1) / RS_TILE; }
+// status rows are sized for the smallest tile so either variant fits
+uint32_t radix_num_tiles(uint32_t capacity) {
+    const uint32_t t = RS_THREADS * RS_ITEMS_MIN;
+    return (capacity + t - 1) / t;
+}
 
 void launch_radix_hist(const uint32_t* keys, const uint32_t* n_ptr, uint32_t capacity, int passes, uint32_t* hist,
                        int sm_count, cudaStream_t stream) {
@@ -231,14 +236,21 @@ void launch_radix_hist(const uint32_t* keys, const uint32_t* n_ptr, uint32_t cap
 }
 
 void launch_onesweep(const uint32_t* keys_in, const uint32_t* vals_in, uint32_t* keys_out, uint32_t* vals_out,
-                     const uint32_t* n_ptr, uint32_t capacity, const uint32_t* hist, uint32_t* status,
+                     const uint32_t* n_ptr, uint32_t capacity, uint32_t n_hint, const uint32_t* hist, uint32_t* status,
                      uint32_t* tile_ctr, int shift, int sm_count, cudaStream_t stream) {
-    uint32_t blocks = radix_num_tiles(capacity);
+    // n_hint (expected entry count, e.g. last frame's) only picks the tile size; correctness never depends on it
+    const bool small = n_hint <= (uint32_t)sm_count * 4u * (RS_THREADS * 16u);
+    const uint32_t tile = RS_THREADS * (small ? 8u : 16u);
+    uint32_t blocks = (capacity + tile - 1) / tile;
     const uint32_t cap_blocks = (uint32_t)sm_count * 4u;   // persistent: blocks pull tiles from the ticket counter
     if (blocks > cap_blocks) blocks = cap_blocks;
     if (blocks == 0) blocks = 1;
-    onesweep_kernel<<<blocks, RS_THREADS, 0, stream>>>(keys_in, vals_in, keys_out, vals_out, n_ptr, hist, status,
-                                                        tile_ctr, shift);
+    if (small)
+        onesweep_kernel<8><<<blocks, RS_THREADS, 0, stream>>>(keys_in, vals_in, keys_out, vals_out, n_ptr, hist, status,
+                                                               tile_ctr, shift);
+    else
+        onesweep_kernel<16><<<blocks, RS_THREADS, 0, stream>>>(keys_in, vals_in, keys_out, vals_out, n_ptr, hist, status,
+                                                                tile_ctr, shift);
 }
 
 }  // namespace bgs
