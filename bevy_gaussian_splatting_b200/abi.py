@@ -17,6 +17,7 @@ STATUS_NAMES = ["BGS_OK", "BGS_NOT_READY", "BGS_EINVAL", "BGS_ECUDA", "BGS_ENOME
 
 BGS_FORMAT_RGBA8_SRGB, BGS_FORMAT_RGBA16F, BGS_FORMAT_RGBA32F = 0, 1, 2
 BGS_FLAG_SORT_ALL = 1
+BGS_FLAG_ASYNC = 2
 
 
 class bgs_view(C.Structure):
@@ -74,6 +75,7 @@ SYMBOLS = [
     ("bgs_cloud_destroy", None, [_P]),
     ("bgs_render", C.c_int, [_P, _P, C.POINTER(bgs_view), C.POINTER(bgs_cloud_uniform), C.POINTER(bgs_settings), _P,
                              C.c_uint32, C.c_int]),
+    ("bgs_sync", C.c_int, [_P]),
     ("bgs_debug_sorted_entries", C.c_int, [_P, _P]),
     ("bgs_debug_tile_ranges", C.c_int, [_P, _P]),
     ("bgs_debug_tile_entries", C.c_int, [_P, _P, C.c_uint64]),

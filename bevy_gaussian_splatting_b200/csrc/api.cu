@@ -88,6 +88,9 @@ struct bgs_context {
     uint32_t arena_n = 0, arena_pairs = 0, arena_tiles = 0;
     size_t arena_small_bytes = 0;      // [0, small): cleared at frame start; [small, end): look-back status rows,
     bool status_clean_pending = false; // cleared right AFTER a frame on stream2 (off the critical path)
+    bool async_pending = false;        // a BGS_FLAG_ASYNC frame has been enqueued and not yet completed
+    const bgs_cloud* pend_cloud = nullptr; FrameConsts pend_fc; bool pend_sort_all = false, pend_by_slot = false;
+    int pend_tiles_x = 0, pend_tiles_y = 0, pend_W = 0, pend_H = 0; const void* pend_target = nullptr;
     cudaEvent_t ev_done = nullptr, ev_clean = nullptr;
     FrameCounters* ctr = nullptr;
     uint32_t* hist = nullptr;          // [8][256]: depth passes 0..3, pair passes 4..7
@@ -323,6 +326,42 @@ void bgs_cloud_destroy(bgs_cloud* cl) {
     delete cl;
 }
 
+// Bookkeeping once a frame's counters are back on the host (sync render, or bgs_sync after async ones).
+static bgs_status finish_frame(bgs_context* c) {
+    if (c->h_ctr->n_pairs_needed > c->cap_pairs) {
+        // the pair list did not fit: grow (x1.25 head-room); the caller redoes the frame
+        uint64_t want = (uint64_t)c->h_ctr->n_pairs_needed + c->h_ctr->n_pairs_needed / 4 + 1024;
+        if (want >= (1ull << 30)) want = (1ull << 30) - 1;
+        if (c->h_ctr->n_pairs_needed >= LB_VMASK || want <= c->cap_pairs)
+            return fail(c, BGS_ENOMEM, "render: frame needs >= 2^30 (splat, tile) pairs");
+        bgs_status s = ensure_pair_scratch(c, (uint32_t)want);
+        if (s != BGS_OK) return s;
+        return BGS_NOT_READY;
+    }
+    const uint32_t n = c->pend_cloud ? c->pend_cloud->n : 0;
+    c->stage_valid = false;
+    c->stats.n = n; c->stats.n_visible = c->h_ctr->n_vis; c->stats.n_pairs = c->h_ctr->n_pairs;
+    c->stats.tiles_x = (uint32_t)c->pend_tiles_x; c->stats.tiles_y = (uint32_t)c->pend_tiles_y;
+    c->stats.width = (uint32_t)c->pend_W; c->stats.height = (uint32_t)c->pend_H;
+    c->have_frame = true; c->last_cloud = c->pend_cloud; c->last_fc = c->pend_fc; c->last_sort_all = c->pend_sort_all;
+    c->last_by_slot = c->pend_by_slot; c->n_vis_hint = c->h_ctr->n_vis; c->n_pairs_hint = c->h_ctr->n_pairs;
+    c->last_frame = c->pend_target;
+    c->err[0] = 0;
+    return BGS_OK;
+}
+
+bgs_status bgs_sync(bgs_context* c) {
+    if (!c) return BGS_EINVAL;
+    if (!c->async_pending) return BGS_OK;
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaStreamSynchronize(c->stream));
+    CU(c, cudaGetLastError());
+    c->async_pending = false;
+    const bgs_status s = finish_frame(c);
+    if (s == BGS_NOT_READY) return fail(c, BGS_NOT_READY, "the last async frame outgrew the pair buffer (now grown): render it again");
+    return s;
+}
+
 bgs_status bgs_render(bgs_context* c, const bgs_cloud* cloud, const bgs_view* view, const bgs_cloud_uniform* uni,
                       const bgs_settings* st, void* out_rgba, uint32_t out_format, int out_is_device_ptr) {
     if (!c) return BGS_EINVAL;
@@ -340,6 +379,10 @@ bgs_status bgs_render(bgs_context* c, const bgs_cloud* cloud, const bgs_view* vi
     const int W = (int)view->viewport[2], H = (int)view->viewport[3];
     if (W <= 0 || H <= 0 || W > 65535 || H > 65535) return fail(c, BGS_EINVAL, "render: viewport %dx%d out of range", W, H);
     CU(c, cudaSetDevice(c->device));
+    if (c->async_pending && !(st->flags & BGS_FLAG_ASYNC)) {
+        const bgs_status ps = bgs_sync(c);
+        if (ps != BGS_OK && ps != BGS_NOT_READY) return ps;
+    }
 
     const uint32_t n = cloud->n;
     const int tiles_x = (W + TILE_PX - 1) / TILE_PX, tiles_y = (H + TILE_PX - 1) / TILE_PX;
@@ -478,34 +521,25 @@ bgs_status bgs_render(bgs_context* c, const bgs_cloud* cloud, const bgs_view* vi
         CU(c, cudaMemcpyAsync(c->h_ctr, c->ctr, sizeof(FrameCounters), cudaMemcpyDeviceToHost, q));
         if (out_rgba && !out_is_device_ptr)
             CU(c, cudaMemcpyAsync(out_rgba, target, frame_bytes, cudaMemcpyDeviceToHost, q));
+        c->pend_cloud = cloud; c->pend_fc = fc; c->pend_sort_all = sort_all; c->pend_by_slot = by_slot;
+        c->pend_tiles_x = tiles_x; c->pend_tiles_y = tiles_y; c->pend_W = W; c->pend_H = H; c->pend_target = target;
         // pre-clean the status rows for the next frame, off the critical path
         CU(c, cudaStreamWaitEvent(c->stream2, c->ev_done, 0));
         CU(c, cudaMemsetAsync(c->arena + c->arena_small_bytes, 0, c->arena_bytes - c->arena_small_bytes, c->stream2));
         CU(c, cudaEventRecord(c->ev_clean, c->stream2));
         c->status_clean_pending = true;
+        if (st->flags & BGS_FLAG_ASYNC) {
+            c->launches = launches;
+            c->async_pending = true;
+            c->have_frame = false;     // hooks need bgs_sync() first
+            return BGS_OK;
+        }
         CU(c, cudaStreamSynchronize(q));
         CU(c, cudaGetLastError());
         c->launches = launches;
-        if (c->h_ctr->n_pairs_needed > c->cap_pairs) {
-            // the pair list did not fit: grow (x1.25 head-room) and redo the frame
-            uint64_t want = (uint64_t)c->h_ctr->n_pairs_needed + c->h_ctr->n_pairs_needed / 4 + 1024;
-            if (want >= (1ull << 30)) want = (1ull << 30) - 1;
-            if (c->h_ctr->n_pairs_needed >= LB_VMASK || want <= c->cap_pairs)
-                return fail(c, BGS_ENOMEM, "render: frame needs >= 2^30 (splat, tile) pairs");
-            s = ensure_pair_scratch(c, (uint32_t)want);
-            if (s != BGS_OK) return s;
-            continue;
-        }
-        // success
-        c->stage_valid = false;   // stage times are read back lazily (bgs_stage_times_us)
-        c->stats.n = n; c->stats.n_visible = c->h_ctr->n_vis; c->stats.n_pairs = c->h_ctr->n_pairs;
-        c->stats.tiles_x = (uint32_t)tiles_x; c->stats.tiles_y = (uint32_t)tiles_y;
-        c->stats.width = (uint32_t)W; c->stats.height = (uint32_t)H;
-        c->have_frame = true; c->last_cloud = cloud; c->last_fc = fc; c->last_sort_all = sort_all;
-        c->last_by_slot = by_slot; c->n_vis_hint = c->h_ctr->n_vis; c->n_pairs_hint = c->h_ctr->n_pairs;
-        c->last_frame = target;
-        c->err[0] = 0;
-        return BGS_OK;
+        const bgs_status fs = finish_frame(c);
+        if (fs == BGS_NOT_READY) continue;   // pair buffer grown: redo the frame
+        return fs;
     }
     return fail(c, BGS_ENOMEM, "render: pair list kept overflowing");
 }
@@ -627,7 +661,10 @@ bgs_status bgs_stage_times_us(bgs_context* c, float out[6]) {
 
 const char* bgs_last_error(const bgs_context* c) { return c ? c->err : "null context"; }
 void* bgs_context_stream(bgs_context* c) { return c ? (void*)c->stream : nullptr; }
-const void* bgs_frame_device_ptr(bgs_context* c) { return (c && c->have_frame) ? c->last_frame : nullptr; }
+const void* bgs_frame_device_ptr(bgs_context* c) {
+    if (!c) return nullptr;
+    return c->have_frame ? c->last_frame : (c->async_pending ? c->pend_target : nullptr);
+}
 uint32_t bgs_last_launch_count(const bgs_context* c) { return c ? c->launches : 0; }
 
 }  // extern "C"

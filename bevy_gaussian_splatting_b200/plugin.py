@@ -100,14 +100,21 @@ class GaussianSplattingPlugin:
     # -- the per-view, per-frame call
     def render_view(self, handle: PlanarGaussian3dHandle, settings: CloudSettings, view: View,
                     camera: GaussianCamera | None = None, transform: CloudTransform | None = None,
-                    fmt: str = "rgba32f", out: np.ndarray | None = None, to_host: bool = True):
-        """Returns the (H, W, 4) frame (host) or None when `to_host` is False / the camera is warming up."""
+                    fmt: str = "rgba32f", out: np.ndarray | None = None, to_host: bool = True,
+                    asynchronous: bool = False):
+        """Returns the (H, W, 4) frame (host) or None when `to_host` is False / the camera is warming up.
+        `asynchronous`: only enqueue the frame (BGS_FLAG_ASYNC); call `sync()` before reading anything."""
         if camera is not None and camera.warmup:   # queue_gaussians skips warm-up cameras (render/mod.rs:361-371)
             return None
         code, dtype, ch = self.FORMATS[fmt]
         v = view.to_abi()
-        u = self.cloud_uniform(settings, transform)
-        s = settings.to_abi()
+        key = (dataclasses.astuple(settings), None if transform is None else transform.matrix.tobytes(), asynchronous)
+        if getattr(self, "_us_cache", (None,))[0] != key:
+            s_ = settings.to_abi()
+            if asynchronous:
+                s_.flags |= abi.BGS_FLAG_ASYNC
+            self._us_cache = (key, self.cloud_uniform(settings, transform), s_)
+        _, u, s = self._us_cache
         if to_host:
             if out is None:
                 out = np.empty((view.height, view.width, ch), dtype)
@@ -117,6 +124,15 @@ class GaussianSplattingPlugin:
             st = self._lib.bgs_render(self._ctx, handle._h, C.byref(v), C.byref(u), C.byref(s), None, code, 0)
         self._check(st)
         return out if to_host else None
+
+    def sync(self) -> bool:
+        """Complete the frames enqueued with `asynchronous=True`.  False = the last frame must be rendered again
+        (its pair list outgrew the buffer, which has been grown)."""
+        st = self._lib.bgs_sync(self._ctx)
+        if st == abi.BGS_NOT_READY:
+            return False
+        self._check(st)
+        return True
 
     # -- parity / measurement hooks
     def frame_stats(self) -> abi.bgs_frame_stats:

@@ -59,8 +59,11 @@ enum { BGS_GAUSSIAN_2D = 0, BGS_GAUSSIAN_3D = 1 };
 enum { BGS_RASTERIZE_COLOR = 0, BGS_RASTERIZE_DEPTH = 1, BGS_RASTERIZE_NORMAL = 2 };
 enum { BGS_DRAW_ALL = 0, BGS_DRAW_SELECTED = 1, BGS_DRAW_HIGHLIGHT_SELECTED = 2 };
 enum {
-    BGS_FLAG_SORT_ALL = 1u /* sort all N entries like the reference (culled keyed 0xFFFFFFFF)
-                              instead of stream-compacting the visible ones first; same output */
+    BGS_FLAG_SORT_ALL = 1u, /* sort all N entries like the reference (culled keyed 0xFFFFFFFF)
+                               instead of stream-compacting the visible ones first; same output */
+    BGS_FLAG_ASYNC = 2u     /* bgs_render only enqueues the frame on the context stream and returns;
+                               bgs_sync() completes it (frames may be queued back to back, like the
+                               reference's command-buffer submission: radix.rs / mod.rs never read back) */
 };
 typedef struct {
     uint32_t gaussian_mode;           /* BGS_GAUSSIAN_* */
@@ -107,7 +110,12 @@ bgs_status bgs_render(bgs_context* ctx, const bgs_cloud* cloud, const bgs_view* 
                       const bgs_cloud_uniform* uniform, const bgs_settings* settings, void* out_rgba,
                       uint32_t out_format, int out_is_device_ptr);
 
-/* Parity / debug hooks (valid after a bgs_render on this context). */
+/* Wait for every frame enqueued with BGS_FLAG_ASYNC.  BGS_OK: the last frame is complete and valid.
+ * BGS_NOT_READY: the last frame's (splat, tile) pair list outgrew its buffer (scene/camera changed a
+ * lot); the buffer has been grown -- render that frame again.  A no-op after a synchronous render. */
+bgs_status bgs_sync(bgs_context* ctx);
+
+/* Parity / debug hooks (valid after a completed bgs_render on this context). */
 /* n*2 words (key, index): the reference's sorted_entry_buffer (sort/mod.rs:323-329). */
 bgs_status bgs_debug_sorted_entries(bgs_context* ctx, uint32_t* key_index_pairs);
 /* tiles*2 words (start, end) into the per-tile entry list. */

@@ -214,3 +214,42 @@ def test_full_size_properties(plugin, n, f16, scale):
         assert np.isfinite(img).all() and img[..., :3].max() > 0.05
     finally:
         h.destroy()
+
+
+def test_async_frames_and_deferred_overflow(plugin):
+    """BGS_FLAG_ASYNC: frames queue back to back; bgs_sync completes them; a pair-list overflow is reported at
+    sync time (BGS_NOT_READY), the buffer grows, and the re-rendered frame is exact."""
+    cloud = B.random_gaussians_3d_seeded(40000, 3)
+    view = B.headless_view(640, 360)
+    h = plugin.add_cloud(cloud)
+    try:
+        s = B.CloudSettings(global_scale=0.05)
+        ref = plugin.render_view(h, s, view, fmt="rgba32f")
+        for _ in range(3):
+            plugin.render_view(h, s, view, fmt="rgba32f", to_host=False, asynchronous=True)
+        out = np.empty_like(ref)
+        plugin.render_view(h, s, view, fmt="rgba32f", out=out, asynchronous=True)
+        assert plugin.sync()
+        assert np.array_equal(out, ref)
+        assert plugin.frame_stats().n_visible > 0
+        # a much heavier frame (huge splats -> far more (splat, tile) pairs than the buffer holds)
+        big = B.CloudSettings(global_scale=3.0)
+        ref_big = None
+        p2 = B.GaussianSplattingPlugin(0)
+        try:
+            h2 = p2.add_cloud(cloud)
+            p2.render_view(h2, s, view, fmt="rgba32f", to_host=False)              # sizes the pair buffer small
+            p2.render_view(h2, big, view, fmt="rgba32f", to_host=False, asynchronous=True)
+            ok = p2.sync()
+            pairs_needed_more = not ok
+            out2 = np.empty_like(ref)
+            p2.render_view(h2, big, view, fmt="rgba32f", out=out2, asynchronous=True)
+            assert p2.sync()
+            ref_big = plugin.render_view(h, big, view, fmt="rgba32f")              # synchronous path grows internally
+            assert np.array_equal(out2, ref_big)
+            assert pairs_needed_more or p2.frame_stats().n_pairs <= (1 << 20)
+            h2.destroy()
+        finally:
+            p2.destroy()
+    finally:
+        h.destroy()
