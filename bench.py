@@ -218,15 +218,19 @@ def run_cuda(args):
 
     # ---- end to end through the C ABI with HOST buffers: per step the view/uniform/settings structs go
     #      host->device as kernel arguments and the finished RGBA8 frame comes back into pinned host memory
-    host_frame = torch.empty((HEIGHT, WIDTH, 4), dtype=torch.uint8).pin_memory().numpy()
-    for _ in range(min(3, args.warmup)):
-        plugin.render_view(handle, settings, view, fmt="rgba8_srgb", out=host_frame)
+    # K frames in, K frames out: each frame's D2H copy (copy stream) overlaps the next frame's kernels; two pinned
+    # host buffers alternate, plugin.sync() (all frames delivered) closes the timed region.
+    host_frames = [torch.empty((HEIGHT, WIDTH, 4), dtype=torch.uint8).pin_memory().numpy() for _ in range(2)]
+    for i in range(min(3, args.warmup)):
+        plugin.render_view(handle, settings, view, fmt="rgba8_srgb", out=host_frames[i & 1], asynchronous=True)
+    assert plugin.sync()
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        plugin.render_view(handle, settings, view, fmt="rgba8_srgb", out=host_frame)
+    for i in range(args.steps):
+        plugin.render_view(handle, settings, view, fmt="rgba8_srgb", out=host_frames[i & 1], asynchronous=True)
         if world > 1:
             sess.gather_device(plugin.frame_device_ptr, all_frames.data_ptr() if all_frames is not None else 0, frame_bytes)
+    assert plugin.sync()
     barrier()
     e2e_ms = 1000.0 * (time.perf_counter() - t0) / args.steps
     if dist is not None:

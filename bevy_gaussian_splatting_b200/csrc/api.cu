@@ -100,8 +100,13 @@ struct bgs_context {
     uint32_t* status_depth = nullptr;  // [4][tiles(n)][256]
     uint32_t* status_pairs = nullptr;  // [4][tiles(cap_pairs)][256]
     // frame
-    void* frame = nullptr;
-    size_t frame_bytes = 0;
+    void* frame = nullptr;            // frames[0]
+    void* frame_alt = nullptr;        // frames[1]: async frames delivered to host memory alternate targets so
+    size_t frame_bytes = 0;           //            frame k's D2H copy (copy stream) overlaps frame k+1's kernels
+    int frame_toggle = 0;
+    cudaStream_t stream_copy = nullptr;
+    cudaEvent_t ev_raster[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
+    bool copy_pending[2] = {false, false};
     const void* last_frame = nullptr;
     FrameCounters* h_ctr = nullptr;    // pinned
 
@@ -211,9 +216,11 @@ bgs_status ensure_arena(bgs_context* c, uint32_t n, uint32_t pairs, uint32_t til
 
 bgs_status ensure_frame(bgs_context* c, size_t bytes) {
     if (bytes <= c->frame_bytes) return BGS_OK;
-    cudaFree(c->frame); c->frame = nullptr; c->frame_bytes = 0;
+    cudaFree(c->frame); cudaFree(c->frame_alt); c->frame = c->frame_alt = nullptr; c->frame_bytes = 0;
     CU(c, cudaMalloc(&c->frame, bytes));
+    CU(c, cudaMalloc(&c->frame_alt, bytes));
     c->frame_bytes = bytes;
+    c->copy_pending[0] = c->copy_pending[1] = false;
     return BGS_OK;
 }
 
@@ -239,6 +246,11 @@ bgs_status bgs_context_create(int cuda_device, bgs_context** out) {
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_done, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_clean, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream_copy, cudaStreamNonBlocking);
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+        e = cudaEventCreateWithFlags(&c->ev_raster[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming);
+    }
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev_p0);
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev_p1);
     if (e == cudaSuccess) e = cudaMallocHost(&c->h_ctr, sizeof(FrameCounters));
@@ -265,6 +277,9 @@ void bgs_context_destroy(bgs_context* c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->stream2) cudaStreamSynchronize(c->stream2);
+    if (c->stream_copy) { cudaStreamSynchronize(c->stream_copy); cudaStreamDestroy(c->stream_copy); }
+    for (int i = 0; i < 2; ++i) { if (c->ev_raster[i]) cudaEventDestroy(c->ev_raster[i]); if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]); }
+    cudaFree(c->frame_alt);
     for (int i = 0; i < 2; ++i) {
         cudaFree(c->keys[i]); cudaFree(c->vals[i]); cudaFree(c->pkeys[i]); cudaFree(c->pvals[i]);
     }
@@ -355,6 +370,8 @@ bgs_status bgs_sync(bgs_context* c) {
     if (!c->async_pending) return BGS_OK;
     CU(c, cudaSetDevice(c->device));
     CU(c, cudaStreamSynchronize(c->stream));
+    CU(c, cudaStreamSynchronize(c->stream_copy));
+    c->copy_pending[0] = c->copy_pending[1] = false;
     CU(c, cudaGetLastError());
     c->async_pending = false;
     const bgs_status s = finish_frame(c);
@@ -419,6 +436,12 @@ bgs_status bgs_render(bgs_context* c, const bgs_cloud* cloud, const bgs_view* vi
         s = ensure_frame(c, frame_bytes);
         if (s != BGS_OK) return s;
         target = c->frame;
+    }
+    const bool async_host = (st->flags & BGS_FLAG_ASYNC) && out_rgba && !out_is_device_ptr;
+    int fslot = 0;
+    if (async_host) {   // alternate device frames; the D2H copy runs on the copy stream
+        fslot = c->frame_toggle; c->frame_toggle ^= 1;
+        target = fslot ? c->frame_alt : c->frame;
     }
 
     for (int attempt = 0; attempt < 4; ++attempt) {
@@ -514,13 +537,21 @@ bgs_status bgs_render(bgs_context* c, const bgs_cloud* cloud, const bgs_view* vi
         ++launches;
         CU(c, cudaEventRecord(c->ev[4], q));
         // ---- stage 5: per-tile front-to-back blend
+        if (async_host && c->copy_pending[fslot]) CU(c, cudaStreamWaitEvent(q, c->ev_copied[fslot], 0));   // target free again
         launch_raster(c->recs, c->pvals[pcur], c->ranges, W, H, tiles_x, tiles_y, target, out_format, q);
         ++launches;
         CU(c, cudaEventRecord(c->ev[5], q));
         CU(c, cudaEventRecord(c->ev_done, q));
         CU(c, cudaMemcpyAsync(c->h_ctr, c->ctr, sizeof(FrameCounters), cudaMemcpyDeviceToHost, q));
-        if (out_rgba && !out_is_device_ptr)
+        if (async_host) {
+            CU(c, cudaEventRecord(c->ev_raster[fslot], q));
+            CU(c, cudaStreamWaitEvent(c->stream_copy, c->ev_raster[fslot], 0));
+            CU(c, cudaMemcpyAsync(out_rgba, target, frame_bytes, cudaMemcpyDeviceToHost, c->stream_copy));
+            CU(c, cudaEventRecord(c->ev_copied[fslot], c->stream_copy));
+            c->copy_pending[fslot] = true;
+        } else if (out_rgba && !out_is_device_ptr) {
             CU(c, cudaMemcpyAsync(out_rgba, target, frame_bytes, cudaMemcpyDeviceToHost, q));
+        }
         c->pend_cloud = cloud; c->pend_fc = fc; c->pend_sort_all = sort_all; c->pend_by_slot = by_slot;
         c->pend_tiles_x = tiles_x; c->pend_tiles_y = tiles_y; c->pend_W = W; c->pend_H = H; c->pend_target = target;
         // pre-clean the status rows for the next frame, off the critical path
