@@ -4,6 +4,7 @@
 // No PyTorch, no wgpu, no CPU fallback: every stage is a hand-written sm_100a kernel.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -39,7 +40,8 @@ uint32_t bin_num_tiles(uint32_t n);
 int bin_coop_blocks_per_sm();
 cudaError_t launch_bin_emit_coop(const SplatRec* recs, const uint32_t* perm, FrameCounters* ctr, uint32_t* block_cnt,
                                  int tiles_x, uint32_t capacity, uint32_t* pair_keys, uint32_t* pair_vals,
-                                 uint32_t* q_rank, uint32_t* q_off, uint32_t grid, cudaStream_t stream);
+                                 uint32_t* q_rank, uint32_t* q_off, uint32_t q_cap, unsigned long long* timeline,
+                                 uint32_t grid, cudaStream_t stream);
 void launch_tile_ranges(const uint32_t* sorted_tile_ids, const FrameCounters* ctr, uint2* ranges, uint32_t capacity,
                         int sm_count, cudaStream_t stream);
 // raster.cu
@@ -68,6 +70,7 @@ struct bgs_context {
     cudaStream_t stream2 = nullptr;   // projection runs here, beside the depth sort
     cudaEvent_t ev[6] = {};
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_p0 = nullptr, ev_p1 = nullptr;
+    unsigned long long* timeline = nullptr;   // BGS_TIMELINE=1: per-CTA phase stamps of bin_emit_coop (debug)
     uint32_t n_vis_hint = 0;          // last frame's visible count (sizes the projection grid)
     uint32_t n_pairs_hint = 0;        // last frame's pair count (picks the pair sort's tile size)
     char err[512] = {0};
@@ -255,6 +258,7 @@ bgs_status bgs_context_create(int cuda_device, bgs_context** out) {
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev_p1);
     if (e == cudaSuccess) e = cudaMallocHost(&c->h_ctr, sizeof(FrameCounters));
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, cuda_device);
+    if (e == cudaSuccess && getenv("BGS_TIMELINE")) e = cudaMalloc(&c->timeline, 4096 * 8 * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&c->coop, cudaDevAttrCooperativeLaunch, cuda_device);
     if (e == cudaSuccess && c->coop) {
         const int kb = keygen_coop_blocks_per_sm(), bb = bin_coop_blocks_per_sm();
@@ -515,7 +519,7 @@ bgs_status bgs_render(bgs_context* c, const bgs_cloud* cloud, const bgs_view* vi
             // the depth sort's spare ping-pong buffers (N words each) hold the large-footprint queue
             CU(c, launch_bin_emit_coop(c->recs, by_slot ? c->vals[cur] : nullptr, c->ctr, c->status_bin, tiles_x,
                                        c->cap_pairs, c->pkeys[0], c->pvals[0], c->keys[cur ^ 1], c->vals[cur ^ 1],
-                                       c->bin_grid, q));
+                                       c->cap_n, c->timeline, c->bin_grid, q));
         } else {
             launch_bin_emit(c->recs, by_slot ? c->vals[cur] : nullptr, c->ctr, c->status_bin, tiles_x, c->cap_pairs,
                             c->pkeys[0], c->pvals[0], n, c->sm_count, q);
@@ -687,6 +691,14 @@ bgs_status bgs_stage_times_us(bgs_context* c, float out[6]) {
         c->stage_valid = true;
     }
     for (int i = 0; i < 6; ++i) out[i] = c->stage_us[i];
+    return BGS_OK;
+}
+
+// undocumented debug aid (not in bgs.h): copy the bin_emit_coop per-CTA timeline (grid x 8 u64 ns stamps)
+bgs_status bgs_debug_timeline_(bgs_context* c, unsigned long long* out, uint32_t* grid) {
+    if (!c || !out || !grid || !c->timeline) return BGS_EINVAL;
+    *grid = c->bin_grid;
+    CU(c, cudaMemcpy(out, c->timeline, (size_t)c->bin_grid * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     return BGS_OK;
 }
 

@@ -13,7 +13,9 @@ namespace bgs {
 constexpr int BIN_THREADS = 256;
 constexpr int BIN_ITEMS = 4;
 constexpr int BIN_TILE = BIN_THREADS * BIN_ITEMS;
-constexpr uint32_t BIN_BIG = 48u;   // splats touching more tiles than this are emitted by the whole block
+constexpr int COOP_ITEMS = 8;        // cooperative kernel: up to 8 ranks per thread per round
+constexpr uint32_t BIN_TINY = 4u;   // footprints up to this many tiles: written by the owning thread
+constexpr uint32_t BIN_BIG = 128u;   // larger than this: global queue, drained by the whole grid   // splats touching more tiles than this are emitted by the whole block
 
 __global__ void __launch_bounds__(BIN_THREADS)
 bin_emit_kernel(const SplatRec* __restrict__ recs, const uint32_t* __restrict__ perm, FrameCounters* __restrict__ ctr,
@@ -132,9 +134,13 @@ bin_emit_kernel(const SplatRec* __restrict__ recs, const uint32_t* __restrict__ 
 __global__ void __launch_bounds__(BIN_THREADS)
 bin_emit_coop_kernel(const SplatRec* __restrict__ recs, const uint32_t* __restrict__ perm, FrameCounters* __restrict__ ctr,
                      uint32_t* __restrict__ block_cnt, int tiles_x, uint32_t capacity, uint32_t* __restrict__ pair_keys,
-                     uint32_t* __restrict__ pair_vals, uint32_t* __restrict__ q_rank, uint32_t* __restrict__ q_off) {
+                     uint32_t* __restrict__ pair_vals, uint32_t* __restrict__ q_rank, uint32_t* __restrict__ q_off,
+                     uint32_t q_cap, unsigned long long* __restrict__ tl) {
+    timeline_stamp(tl, 0);
     __shared__ uint32_t s_wtot[BIN_THREADS / 32];
     __shared__ uint32_t s_wbig[BIN_THREADS / 32];
+    __shared__ uint32_t s_wmed[BIN_THREADS / 32];
+    __shared__ uint32_t s_mbase;
     __shared__ uint32_t s_red[BIN_THREADS / 32];
     __shared__ unsigned long long s_red64[BIN_THREADS / 32];
     __shared__ uint32_t s_total;
@@ -142,11 +148,17 @@ bin_emit_coop_kernel(const SplatRec* __restrict__ recs, const uint32_t* __restri
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const uint32_t G = gridDim.x, b = blockIdx.x;
     const uint32_t n_vis = ctr->n_vis;
-    const uint32_t tiles_total = (n_vis + BIN_TILE - 1) / BIN_TILE;
-    const uint32_t t0 = (uint32_t)((uint64_t)b * tiles_total / G), t1 = (uint32_t)((uint64_t)(b + 1) * tiles_total / G);
+    // this CTA's contiguous rank range, cut into sub-tiles of 256 * ipt ranks (ipt chosen so that the whole
+    // range is ONE sub-tile whenever it fits 8 items per thread: every CTA then does the same number of rounds)
+    const uint32_t rlo = (uint32_t)((uint64_t)b * n_vis / G), rhi = (uint32_t)((uint64_t)(b + 1) * n_vis / G);
+    const uint32_t chunk = (n_vis + G - 1) / G;
+    uint32_t ipt = (chunk + BIN_THREADS - 1) / BIN_THREADS;
+    if (ipt > COOP_ITEMS) ipt = COOP_ITEMS;
+    if (ipt == 0) ipt = 1;
+    const uint32_t sub = BIN_THREADS * ipt;
 
     auto tiles_of = [&](uint32_t r, uint32_t& bx, uint32_t& by, uint32_t& ri) -> uint32_t {
-        if (r >= n_vis) return 0u;
+        if (r >= rhi) return 0u;
         ri = perm ? __ldg(perm + (n_vis - 1u - r)) : r;   // rank -> record index
         const uint2 bb = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const char*>(recs + ri) + 24));
         bx = bb.x; by = bb.y;
@@ -157,11 +169,11 @@ bin_emit_coop_kernel(const SplatRec* __restrict__ recs, const uint32_t* __restri
 
     // ---- phase 1
     uint32_t mine = 0u;
-    for (uint32_t tile = t0; tile < t1; ++tile) {
+    for (uint32_t base = rlo; base < rhi; base += sub) {
 #pragma unroll
-        for (int j = 0; j < BIN_ITEMS; ++j) {
+        for (int j = 0; j < COOP_ITEMS; ++j) {
             uint32_t bx, by, ri;
-            mine += tiles_of(tile * BIN_TILE + t * BIN_ITEMS + j, bx, by, ri);
+            if ((uint32_t)j < ipt) mine += tiles_of(base + t * ipt + j, bx, by, ri);
         }
     }
 #pragma unroll
@@ -175,7 +187,9 @@ bin_emit_coop_kernel(const SplatRec* __restrict__ recs, const uint32_t* __restri
         s_total = tot > LB_VMASK ? LB_VMASK : tot;
         st_volatile(block_cnt + b, s_total);
     }
+    timeline_stamp(tl, 1);
     grid_barrier(&ctr->barrier[1], G);
+    timeline_stamp(tl, 2);
 
     // ---- phase 2 (sums saturate at 2^30 - 1: such a frame is rejected by the host)
     uint64_t run64 = 0;
@@ -196,43 +210,55 @@ bin_emit_coop_kernel(const SplatRec* __restrict__ recs, const uint32_t* __restri
         ctr->n_pairs = need < capacity ? need : capacity;
     }
     uint32_t run = run64 > LB_VMASK ? LB_VMASK : (uint32_t)run64;
-    for (uint32_t tile = t0; tile < t1; ++tile) {
-        const uint32_t r0 = tile * BIN_TILE + t * BIN_ITEMS;
-        uint32_t bx[BIN_ITEMS], by[BIN_ITEMS], cnt[BIN_ITEMS], ri[BIN_ITEMS];
+    for (uint32_t base = rlo; base < rhi; base += sub) {
+        const uint32_t r0 = base + t * ipt;
+        uint32_t bx[COOP_ITEMS], by[COOP_ITEMS], cnt[COOP_ITEMS], ri[COOP_ITEMS];
         uint32_t tmine = 0u, nbig = 0u;
 #pragma unroll
-        for (int j = 0; j < BIN_ITEMS; ++j) {
+        for (int j = 0; j < COOP_ITEMS; ++j) {
             bx[j] = 0u; by[j] = 0u; ri[j] = 0u;
-            cnt[j] = tiles_of(r0 + j, bx[j], by[j], ri[j]);
+            cnt[j] = ((uint32_t)j < ipt) ? tiles_of(r0 + j, bx[j], by[j], ri[j]) : 0u;
             tmine += cnt[j];
             nbig += cnt[j] > BIN_BIG ? 1u : 0u;
         }
-        uint32_t incl = tmine, bincl = nbig;
+        uint32_t nmed = 0u;
+#pragma unroll
+        for (int j = 0; j < COOP_ITEMS; ++j) nmed += (cnt[j] > BIN_TINY && cnt[j] <= BIN_BIG) ? 1u : 0u;
+        uint32_t incl = tmine, bincl = nbig, mincl = nmed;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
             const uint32_t z = __shfl_up_sync(0xffffffffu, bincl, o);
-            if (lane >= o) { incl += y; bincl += z; }
+            const uint32_t x = __shfl_up_sync(0xffffffffu, mincl, o);
+            if (lane >= o) { incl += y; bincl += z; mincl += x; }
         }
-        if (lane == 31) { s_wtot[warp] = incl; s_wbig[warp] = bincl; }
+        if (lane == 31) { s_wtot[warp] = incl; s_wbig[warp] = bincl; s_wmed[warp] = mincl; }
         __syncthreads();
-        uint32_t wprefix = 0u, ttotal = 0u, bprefix = 0u, btotal = 0u;
+        uint32_t wprefix = 0u, ttotal = 0u, bprefix = 0u, btotal = 0u, mprefix = 0u, mtotal = 0u;
 #pragma unroll
         for (int w = 0; w < BIN_THREADS / 32; ++w) {
-            const uint32_t c = s_wtot[w], d = s_wbig[w];
-            if (w < warp) { wprefix += c; bprefix += d; }
-            ttotal += c; btotal += d;
+            const uint32_t c = s_wtot[w], d = s_wbig[w], e = s_wmed[w];
+            if (w < warp) { wprefix += c; bprefix += d; mprefix += e; }
+            ttotal += c; btotal += d; mtotal += e;
         }
-        if (t == 0 && btotal) s_qbase = atomicAdd(&ctr->big_count, btotal);   // one reservation per tile
+        if (t == 0) {   // one reservation per round in each global queue
+            if (btotal) s_qbase = atomicAdd(&ctr->big_count, btotal);
+            if (mtotal) s_mbase = atomicAdd(&ctr->med_count, mtotal);
+        }
         __syncthreads();
+        // footprint classes:  <= BIN_TINY tiles: written right here by the owning thread;
+        //   <= BIN_BIG: medium queue (front of the queue arrays), drained 32 splats per warp in phase 3;
+        //   larger: big queue (back of the queue arrays), one splat per warp in phase 3
         uint32_t off = run + wprefix + incl - tmine;
         uint32_t qat = s_qbase + bprefix + bincl - nbig;
+        uint32_t mat = s_mbase + mprefix + mincl - nmed;
 #pragma unroll
-        for (int j = 0; j < BIN_ITEMS; ++j) {
+        for (int j = 0; j < COOP_ITEMS; ++j) {
             if (cnt[j] == 0u) continue;
-            const uint32_t r = ri[j];
             if (cnt[j] > BIN_BIG) {
-                q_rank[qat] = r; q_off[qat] = off; ++qat;
+                q_rank[q_cap - 1u - qat] = ri[j]; q_off[q_cap - 1u - qat] = off; ++qat;
+            } else if (cnt[j] > BIN_TINY) {
+                q_rank[mat] = ri[j]; q_off[mat] = off; ++mat;
             } else {
                 const uint32_t txlo = (bx[j] & 0xFFFFu) >> 4, txhi = (bx[j] >> 16) >> 4;
                 const uint32_t tylo = (by[j] & 0xFFFFu) >> 4, tyhi = (by[j] >> 16) >> 4;
@@ -241,7 +267,7 @@ bin_emit_coop_kernel(const SplatRec* __restrict__ recs, const uint32_t* __restri
                     for (uint32_t tx = txlo; tx <= txhi; ++tx) {
                         if (o < capacity) {
                             pair_keys[o] = ty * (uint32_t)tiles_x + tx;
-                            pair_vals[o] = r;
+                            pair_vals[o] = ri[j];
                         }
                         ++o;
                     }
@@ -251,16 +277,51 @@ bin_emit_coop_kernel(const SplatRec* __restrict__ recs, const uint32_t* __restri
         run += ttotal;
         __syncthreads();
     }
+    timeline_stamp(tl, 3);
     grid_barrier(&ctr->barrier[1], 2u * G);
+    timeline_stamp(tl, 4);
 
-    // ---- phase 3: warps pull large-footprint splats from the queue
+    // ---- phase 3a: medium footprints, 32 per warp: each lane fetches one splat's (record, offset, bbox)
+    //      so the memory latency is paid once per 32 splats; then the warp writes them one after another
+    const uint32_t nm = ld_volatile(&ctr->med_count);
+    while (true) {
+        uint32_t mb = 0u;
+        if (lane == 0) mb = atomicAdd(&ctr->med_head, 32u);
+        mb = __shfl_sync(0xffffffffu, mb, 0);
+        if (mb >= nm) break;
+        const uint32_t i = mb + lane;
+        uint32_t m_ri = 0u, m_off = 0u, m_txlo = 0u, m_tylo = 0u, m_w = 1u, m_total = 0u;
+        if (i < nm) {
+            m_ri = __ldcg(q_rank + i); m_off = __ldcg(q_off + i);
+            const uint2 bb = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const char*>(recs + m_ri) + 24));
+            m_txlo = (bb.x & 0xFFFFu) >> 4; m_tylo = (bb.y & 0xFFFFu) >> 4;
+            m_w = ((bb.x >> 16) >> 4) - m_txlo + 1u;
+            m_total = m_w * (((bb.y >> 16) >> 4) - m_tylo + 1u);
+        }
+        for (int sI = 0; sI < 32; ++sI) {
+            const uint32_t total = __shfl_sync(0xffffffffu, m_total, sI);
+            if (total == 0u) continue;
+            const uint32_t r = __shfl_sync(0xffffffffu, m_ri, sI), off = __shfl_sync(0xffffffffu, m_off, sI);
+            const uint32_t txlo = __shfl_sync(0xffffffffu, m_txlo, sI), tylo = __shfl_sync(0xffffffffu, m_tylo, sI);
+            const uint32_t w = __shfl_sync(0xffffffffu, m_w, sI);
+            for (uint32_t k = lane; k < total; k += 32) {
+                const uint32_t o = off + k;
+                if (o < capacity) {
+                    const uint32_t qy = k / w;
+                    pair_keys[o] = (tylo + qy) * (uint32_t)tiles_x + (txlo + (k - qy * w));
+                    pair_vals[o] = r;
+                }
+            }
+        }
+    }
+    // ---- phase 3b: warps pull large-footprint splats from the back queue, one at a time
     const uint32_t nq = ld_volatile(&ctr->big_count);
     while (true) {
         uint32_t q = 0u;
         if (lane == 0) q = atomicAdd(&ctr->big_head, 1u);
         q = __shfl_sync(0xffffffffu, q, 0);
         if (q >= nq) break;
-        const uint32_t r = __ldcg(q_rank + q), off = __ldcg(q_off + q);
+        const uint32_t r = __ldcg(q_rank + (q_cap - 1u - q)), off = __ldcg(q_off + (q_cap - 1u - q));
         const uint2 bb = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const char*>(recs + r) + 24));
         const uint32_t txlo = (bb.x & 0xFFFFu) >> 4, txhi = (bb.x >> 16) >> 4;
         const uint32_t tylo = (bb.y & 0xFFFFu) >> 4, tyhi = (bb.y >> 16) >> 4;
@@ -277,6 +338,7 @@ bin_emit_coop_kernel(const SplatRec* __restrict__ recs, const uint32_t* __restri
             if (tx > txhi) { tx -= w; ++ty; }
         }
     }
+    timeline_stamp(tl, 5);
 }
 
 __global__ void tile_ranges_kernel(const uint32_t* __restrict__ sorted_tile_ids, const FrameCounters* __restrict__ ctr,
@@ -307,9 +369,10 @@ int bin_coop_blocks_per_sm() {
 }
 cudaError_t launch_bin_emit_coop(const SplatRec* recs, const uint32_t* perm, FrameCounters* ctr, uint32_t* block_cnt,
                                  int tiles_x, uint32_t capacity, uint32_t* pair_keys, uint32_t* pair_vals,
-                                 uint32_t* q_rank, uint32_t* q_off, uint32_t grid, cudaStream_t stream) {
+                                 uint32_t* q_rank, uint32_t* q_off, uint32_t q_cap, unsigned long long* timeline,
+                                 uint32_t grid, cudaStream_t stream) {
     void* args[] = {(void*)&recs, (void*)&perm, (void*)&ctr, (void*)&block_cnt, (void*)&tiles_x, (void*)&capacity, (void*)&pair_keys,
-                    (void*)&pair_vals, (void*)&q_rank, (void*)&q_off};
+                    (void*)&pair_vals, (void*)&q_rank, (void*)&q_off, (void*)&q_cap, (void*)&timeline};
     return cudaLaunchCooperativeKernel((const void*)bin_emit_coop_kernel, dim3(grid), dim3(BIN_THREADS), args, 0, stream);
 }
 

@@ -48,8 +48,8 @@ struct FrameCounters {
     uint32_t culled_min, culled_min2, culled_max;   // for RasterizeMode::Depth's sorted[1]/[N-1]
     uint32_t pad;
     uint32_t barrier[8];        // grid barriers of the cooperative kernels: [0] keygen, [1] bin
-    uint32_t big_count, big_head;   // bin: queue of large-footprint splats (filled, then drained grid-wide)
-    uint32_t pad2[2];
+    uint32_t big_count, big_head;   // bin: queue of large footprints (grows from the back of the queue arrays)
+    uint32_t med_count, med_head;   // bin: queue of medium footprints (grows from the front), drained 32 per warp
 };
 
 __device__ __forceinline__ uint32_t ld_volatile(const uint32_t* p) {
@@ -69,6 +69,15 @@ __device__ __forceinline__ uint32_t lanemask_le() {
     uint32_t m;
     asm("mov.u32 %0, %%lanemask_le;" : "=r"(m));
     return m;
+}
+
+// Optional per-CTA timeline (debug builds of a run: BGS_TIMELINE=1): %globaltimer stamps at phase boundaries.
+__device__ __forceinline__ void timeline_stamp(unsigned long long* tl, int slot) {
+    if (tl != nullptr && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        tl[(size_t)blockIdx.x * 8 + slot] = t;
+    }
 }
 
 // Grid-wide barrier for kernels launched with cudaLaunchCooperativeKernel (all CTAs co-resident).
