@@ -31,7 +31,7 @@ void launch_onesweep(const uint32_t* keys_in, const uint32_t* vals_in, uint32_t*
 // project.cu
 void launch_project(bool f16, const float4* pos, const void* sh, const void* rot, const void* so,
                     const uint32_t* index_list, int by_slot, const FrameCounters* ctr, const FrameConsts& fc,
-                    SplatRec* recs, uint32_t n_hint, cudaStream_t stream);
+                    SplatRec* recs, float4* extra, uint32_t n_hint, cudaStream_t stream);
 // bin.cu
 void launch_bin_emit(const SplatRec* recs, const uint32_t* perm, FrameCounters* ctr, uint32_t* status, int tiles_x,
                      uint32_t capacity, uint32_t* pair_keys, uint32_t* pair_vals, uint32_t n_upper, int sm_count,
@@ -45,8 +45,8 @@ cudaError_t launch_bin_emit_coop(const SplatRec* recs, const uint32_t* perm, Fra
 void launch_tile_ranges(const uint32_t* sorted_tile_ids, const FrameCounters* ctr, uint2* ranges, uint32_t capacity,
                         int sm_count, cudaStream_t stream);
 // raster.cu
-void launch_raster(const SplatRec* recs, const uint32_t* tile_entries, const uint2* ranges, int W, int H, int tiles_x,
-                   int tiles_y, void* out, uint32_t format, cudaStream_t stream);
+void launch_raster(int mode, const SplatRec* recs, const float4* extra, const uint32_t* tile_entries, const uint2* ranges,
+                   int W, int H, int tiles_x, int tiles_y, void* out, uint32_t format, cudaStream_t stream);
 }  // namespace bgs
 
 using namespace bgs;
@@ -81,6 +81,8 @@ struct bgs_context {
     uint32_t* vals[2] = {nullptr, nullptr};
     uint32_t* slot_ids = nullptr;     // compact slot -> gaussian index (key-gen output, index order)
     SplatRec* recs = nullptr;
+    float4* extra = nullptr;          // 4 x float4 per record: 2DGS + USE_AABB only (allocated on first use)
+    uint32_t cap_extra = 0;
     // scratch sized by the pair capacity (grow-only)
     uint32_t cap_pairs = 0;
     uint32_t* pkeys[2] = {nullptr, nullptr};
@@ -287,7 +289,7 @@ void bgs_context_destroy(bgs_context* c) {
     for (int i = 0; i < 2; ++i) {
         cudaFree(c->keys[i]); cudaFree(c->vals[i]); cudaFree(c->pkeys[i]); cudaFree(c->pvals[i]);
     }
-    cudaFree(c->recs); cudaFree(c->slot_ids); cudaFree(c->arena); cudaFree(c->frame);
+    cudaFree(c->recs); cudaFree(c->extra); cudaFree(c->slot_ids); cudaFree(c->arena); cudaFree(c->frame);
     if (c->h_ctr) cudaFreeHost(c->h_ctr);
     for (int i = 0; i < 6; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     for (cudaEvent_t e : {c->ev_fork, c->ev_join, c->ev_p0, c->ev_p1, c->ev_done, c->ev_clean}) if (e) cudaEventDestroy(e);
@@ -392,8 +394,8 @@ bgs_status bgs_render(bgs_context* c, const bgs_cloud* cloud, const bgs_view* vi
     if (out_format > BGS_FORMAT_RGBA32F) return fail(c, BGS_EINVAL, "render: unknown out_format %u", out_format);
     if (st->radix_sort_depth_bits != 16 && st->radix_sort_depth_bits != 24 && st->radix_sort_depth_bits != 32)
         return fail(c, BGS_EINVAL, "render: radix_sort_depth_bits must be 16, 24 or 32");
-    if (st->gaussian_mode != BGS_GAUSSIAN_3D) return fail(c, BGS_EINVAL, "render: gaussian_mode %u not supported yet", st->gaussian_mode);
-    if (st->aabb) return fail(c, BGS_EINVAL, "render: aabb (USE_AABB) not supported yet");
+    if (st->gaussian_mode != BGS_GAUSSIAN_3D && st->gaussian_mode != BGS_GAUSSIAN_2D)
+        return fail(c, BGS_EINVAL, "render: gaussian_mode %u not supported (Gaussian4d is out of scope)", st->gaussian_mode);
     if (st->rasterize_mode != BGS_RASTERIZE_COLOR && st->rasterize_mode != BGS_RASTERIZE_NORMAL)
         return fail(c, BGS_EINVAL, "render: rasterize_mode %u not supported yet", st->rasterize_mode);
     if (st->draw_mode > BGS_DRAW_HIGHLIGHT_SELECTED) return fail(c, BGS_EINVAL, "render: bad draw_mode");
@@ -428,6 +430,13 @@ bgs_status bgs_render(bgs_context* c, const bgs_cloud* cloud, const bgs_view* vi
 
     bgs_status s = ensure_cloud_scratch(c, n);
     if (s != BGS_OK) return s;
+    // raster variant: 0 = quad-uv falloff (USE_OBB, 3DGS and 2DGS), 1 = 3DGS conic (USE_AABB), 2 = 2DGS ray-splat (USE_AABB)
+    const int raster_mode = !st->aabb ? 0 : (st->gaussian_mode == BGS_GAUSSIAN_3D ? 1 : 2);
+    if (raster_mode == 2 && c->cap_extra < c->cap_n) {
+        cudaFree(c->extra); c->extra = nullptr; c->cap_extra = 0;
+        CU(c, cudaMalloc(&c->extra, (size_t)c->cap_n * 64));
+        c->cap_extra = c->cap_n;
+    }
     if (c->cap_pairs == 0) {
         uint32_t init = n < (1u << 20) ? (1u << 20) : n;   // first guess; grows on demand
         s = ensure_pair_scratch(c, init);
@@ -484,7 +493,7 @@ bgs_status bgs_render(bgs_context* c, const bgs_cloud* cloud, const bgs_view* vi
             CU(c, cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
             CU(c, cudaEventRecord(c->ev_p0, c->stream2));
             launch_project(cloud->f16, cloud->pos, cloud->sh, cloud->rot, cloud->so, c->slot_ids, 1, c->ctr, fc, c->recs,
-                           n_hint < n ? n_hint : n, c->stream2);
+                           raster_mode == 2 ? c->extra : nullptr, n_hint < n ? n_hint : n, c->stream2);
             ++launches;
             CU(c, cudaEventRecord(c->ev_p1, c->stream2));
             CU(c, cudaEventRecord(c->ev_join, c->stream2));
@@ -509,7 +518,7 @@ bgs_status bgs_render(bgs_context* c, const bgs_cloud* cloud, const bgs_view* vi
             // ---- stage 3 (SORT_ALL): projection in front-to-back rank order after the sort; recs[rank]
             CU(c, cudaEventRecord(c->ev_p0, q));
             launch_project(cloud->f16, cloud->pos, cloud->sh, cloud->rot, cloud->so, c->vals[cur], 0, c->ctr, fc, c->recs,
-                           n_hint < n ? n_hint : n, q);
+                           raster_mode == 2 ? c->extra : nullptr, n_hint < n ? n_hint : n, q);
             ++launches;
             CU(c, cudaEventRecord(c->ev_p1, q));
         }
@@ -542,7 +551,7 @@ bgs_status bgs_render(bgs_context* c, const bgs_cloud* cloud, const bgs_view* vi
         CU(c, cudaEventRecord(c->ev[4], q));
         // ---- stage 5: per-tile front-to-back blend
         if (async_host && c->copy_pending[fslot]) CU(c, cudaStreamWaitEvent(q, c->ev_copied[fslot], 0));   // target free again
-        launch_raster(c->recs, c->pvals[pcur], c->ranges, W, H, tiles_x, tiles_y, target, out_format, q);
+        launch_raster(raster_mode, c->recs, c->extra, c->pvals[pcur], c->ranges, W, H, tiles_x, tiles_y, target, out_format, q);
         ++launches;
         CU(c, cudaEventRecord(c->ev[5], q));
         CU(c, cudaEventRecord(c->ev_done, q));

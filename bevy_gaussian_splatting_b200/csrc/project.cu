@@ -98,7 +98,8 @@ template <bool F16>
 __global__ void __launch_bounds__(128)
 project_kernel(const float4* __restrict__ pos, const void* __restrict__ sh_p, const void* __restrict__ rot_p,
                const void* __restrict__ so_p, const uint32_t* __restrict__ index_list, int by_slot,
-               const FrameCounters* __restrict__ ctr, FrameConsts fc, SplatRec* __restrict__ recs) {
+               const FrameCounters* __restrict__ ctr, FrameConsts fc, SplatRec* __restrict__ recs,
+               float4* __restrict__ extra /* 4 x float4 per record, 2DGS + USE_AABB only */) {
     const uint32_t n_vis = ctr->n_vis;
     for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n_vis; r += gridDim.x * blockDim.x) {
         // by_slot: r is a compact slot (ascending gaussian index; runs concurrently with the depth sort)
@@ -151,6 +152,7 @@ project_kernel(const float4* __restrict__ pos, const void* __restrict__ sh_p, co
                 const float a = 9.0f + 2.0f * det_ln(opacity);
                 cutoff = sqrtf(a > 0.000001f ? a : 0.000001f);
             }
+            if (fc.gaussian_mode == BGS_GAUSSIAN_3D) {
             // gaussian_3d.wgsl:49-72
             float M[3][3], Sg[3][3], X[3][3], TS[3][3];
 #pragma unroll
@@ -194,12 +196,23 @@ project_kernel(const float4* __restrict__ pos, const void* __restrict__ sh_p, co
             const float a = ((Tm[0][0] * Y[0][0] + Tm[1][0] * Y[1][0]) + Tm[2][0] * Y[2][0]) + 0.3f;
             const float b = (Tm[0][1] * Y[0][0] + Tm[1][1] * Y[1][0]) + Tm[2][1] * Y[2][0];
             const float c = ((Tm[0][1] * Y[0][1] + Tm[1][1] * Y[1][1]) + Tm[2][1] * Y[2][1]) + 0.3f;
-            // helpers.wgsl:49-67,81-119 (USE_OBB)
+            // helpers.wgsl:49-67
             const float det = a * c - b * b;
             const float mid = 0.5f * (a + c);
             const float disc = fmaxf(0.0f, mid * mid - det);
             const float term = sqrtf(disc);
             const float l1 = mid + term;
+            if (fc.aabb) {
+                // helpers.wgsl:69-79 + gaussian.wgsl:299-309: square of half-side cutoff*sqrt(l1), conic
+                // record (USE_AABB): ux,uy,vx = conic.x,.y,.z; vy = quad half-side (half-pixels)
+                const float l2 = fmaxf(mid - term, 0.0f);
+                const float Rq = cutoff * fmaxf(sqrtf(l1), sqrtf(l2));
+                const float dinv = 1.0f / det;
+                rec.ux = c * dinv; rec.uy = -b * dinv; rec.vx = a * dinv; rec.vy = Rq;
+                const float h = 0.5f * Rq;
+                make_bbox(cx, cy, h, h, fc.Wi, fc.Hi, rec.bx, rec.by);
+            } else {
+            // helpers.wgsl:81-119 (USE_OBB)
             const float aa = (a - c) * (a - c);
             const float bb = sqrtf(aa + (4.0f * b) * b);
             const float major = sqrtf(((a + c) + bb) * 0.5f);
@@ -215,6 +228,61 @@ project_kernel(const float4* __restrict__ pos, const void* __restrict__ sh_p, co
             const float hy = 0.5f * (fabsf(e1y) * Bx + fabsf(e2y) * By);
             if (rec.ux == rec.ux && rec.uy == rec.uy && rec.vx == rec.vx && rec.vy == rec.vy)
                 make_bbox(cx, cy, hx, hy, fc.Wi, fc.Hi, rec.bx, rec.by);
+            }
+            } else {
+                // ---- 2DGS surfel: gaussian_2d.wgsl:77-132 (homography) + :49-75 (quad)
+                float L[3][2];   // first two columns of A * R_std * S, R_std = transpose(Rm)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const float rc[3] = {Rm[j][0] * sc[j], Rm[j][1] * sc[j], Rm[j][2] * sc[j]};
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) L[i][j] = (A[i][0] * rc[0] + A[i][1] * rc[1]) + A[i][2] * rc[2];
+                }
+                float G[3][4];
+                mat4_dir(fc.clip_from_world, L[0][0], L[1][0], L[2][0], G[0]);
+                mat4_dir(fc.clip_from_world, L[0][1], L[1][1], L[2][1], G[1]);
+                mat4_point(fc.clip_from_world, k.pw[0], k.pw[1], k.pw[2], G[2]);
+                const float fxk = fc.p00 * W / 2.0f, fyk = fc.p11 * H / 2.0f;     // helpers.wgsl:122-135
+                const float cxk = (W - 1.0f) / 2.0f, cyk = (H - 1.0f) / 2.0f;
+                float T0[3], T1[3], T2[3];
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    T0[j] = fxk * G[j][0] + cxk * G[j][3];
+                    T1[j] = fyk * G[j][1] + cyk * G[j][3];
+                    T2[j] = G[j][3];
+                }
+                const float c2 = cutoff * cutoff;
+                const float test[3] = {c2, c2, -1.0f};
+                const float tt[3] = {test[0] * T2[0], test[1] * T2[1], test[2] * T2[2]};
+                const float d = dot3(tt, T2);
+                float Rq = 0.0f, mean0 = 0.0f, mean1 = 0.0f;
+                bool ok = !(fabsf(d) < 1.0e-4f);
+                if (ok) {
+                    const float inv = 1.0f / d;
+                    const float f[3] = {inv * test[0], inv * test[1], inv * test[2]};
+                    const float t02[3] = {T0[0] * T2[0], T0[1] * T2[1], T0[2] * T2[2]};
+                    const float t12[3] = {T1[0] * T2[0], T1[1] * T2[1], T1[2] * T2[2]};
+                    mean0 = dot3(f, t02); mean1 = dot3(f, t12);
+                    const float f0[3] = {f[0] * T0[0], f[1] * T0[1], f[2] * T0[2]};
+                    const float f1[3] = {f[0] * T1[0], f[1] * T1[1], f[2] * T1[2]};
+                    const float ex = mean0 * mean0 - dot3(f0, T0);
+                    const float ey = mean1 * mean1 - dot3(f1, T1);
+                    if (ex < 1.0e-4f || ey < 1.0e-4f) ok = false;
+                    else Rq = fmaxf(fmaxf(sqrtf(ex), sqrtf(ey)), cutoff * 0.707106f);
+                }
+                if (ok) {
+                    rec.ux = 2.0f / Rq; rec.uy = 0.0f; rec.vx = 0.0f; rec.vy = -2.0f / Rq;   // OBB branch: e1=(1,0), e2=(0,1)
+                    const float h = 0.5f * Rq;
+                    if (Rq == Rq) make_bbox(cx, cy, h, h, fc.Wi, fc.Hi, rec.bx, rec.by);
+                    if (fc.aabb && extra != nullptr) {
+                        float4* e = extra + (size_t)r * 4;
+                        e[0] = make_float4(Rq, mean0, mean1, W / H);
+                        e[1] = make_float4(T0[0], T0[1], T0[2], 0.0f);
+                        e[2] = make_float4(T1[0], T1[1], T1[2], 0.0f);
+                        e[3] = make_float4(T2[0], T2[1], T2[2], 0.0f);
+                    }
+                }
+            }
 
             // colour source
             float rgb[3] = {0.f, 0.f, 0.f};
@@ -284,14 +352,14 @@ project_kernel(const float4* __restrict__ pos, const void* __restrict__ sh_p, co
 
 void launch_project(bool f16, const float4* pos, const void* sh, const void* rot, const void* so,
                     const uint32_t* index_list, int by_slot, const FrameCounters* ctr, const FrameConsts& fc,
-                    SplatRec* recs, uint32_t n_hint, cudaStream_t stream) {
+                    SplatRec* recs, float4* extra, uint32_t n_hint, cudaStream_t stream) {
     // grid sized from a hint (last frame's visible count + head-room); the grid-stride loop keeps any
     // n_vis correct.  Short-lived CTAs (not a persistent grid) so a concurrent sort can interleave.
     uint32_t blocks = (n_hint + 127) / 128;
     if (blocks > 65535u * 8u) blocks = 65535u * 8u;
     if (blocks < 148u) blocks = 148u;
-    if (f16) project_kernel<true><<<blocks, 128, 0, stream>>>(pos, sh, rot, so, index_list, by_slot, ctr, fc, recs);
-    else project_kernel<false><<<blocks, 128, 0, stream>>>(pos, sh, rot, so, index_list, by_slot, ctr, fc, recs);
+    if (f16) project_kernel<true><<<blocks, 128, 0, stream>>>(pos, sh, rot, so, index_list, by_slot, ctr, fc, recs, extra);
+    else project_kernel<false><<<blocks, 128, 0, stream>>>(pos, sh, rot, so, index_list, by_slot, ctr, fc, recs, extra);
 }
 
 }  // namespace bgs

@@ -31,12 +31,18 @@ constexpr uint32_t SM_Q0 = 0;                         // float4 [256]: cx, cy, u
 constexpr uint32_t SM_UV = SM_Q0 + RT_CHUNK * 16;     // float4 [256]: vx, vy, bbox x, bbox y
 constexpr uint32_t SM_Q2 = SM_UV + RT_CHUNK * 16;     // float4 [256]: r, g, b, opacity
 constexpr uint32_t SM_LIST = SM_Q2 + RT_CHUNK * 16;   // u16 [8][256]: per-warp candidates, stored as index * 16
-constexpr uint32_t SM_BYTES = SM_LIST + (RT_THREADS / 32) * RT_CHUNK * 2;
+constexpr uint32_t SM_EXTRA = SM_LIST + (RT_THREADS / 32) * RT_CHUNK * 2;   // MODE 2 only: 4 x float4 [256]
+constexpr uint32_t SM_BYTES = SM_EXTRA;
+constexpr uint32_t SM_BYTES_2D = SM_EXTRA + 4 * RT_CHUNK * 16;
 
+// MODE 0: USE_OBB quad-uv falloff (3DGS, and 2DGS without aabb)   gaussian.wgsl:474-504
+// MODE 1: 3DGS USE_AABB conic falloff                              gaussian.wgsl:459-471
+// MODE 2: 2DGS USE_AABB ray-splat intersection                     gaussian.wgsl:441-458, gaussian_2d.wgsl:134-156
+template <int MODE>
 __global__ void __launch_bounds__(RT_THREADS)
-raster_kernel(const SplatRec* __restrict__ recs, const uint32_t* __restrict__ tile_entries,
+raster_kernel(const SplatRec* __restrict__ recs, const float4* __restrict__ extra, const uint32_t* __restrict__ tile_entries,
               const uint2* __restrict__ ranges, int W, int H, int tiles_x, void* __restrict__ out, uint32_t format) {
-    __shared__ __align__(16) unsigned char s_mem[SM_BYTES];
+    __shared__ __align__(16) unsigned char s_mem[MODE == 2 ? SM_BYTES_2D : SM_BYTES];
     float4* s_q0 = reinterpret_cast<float4*>(s_mem + SM_Q0);
     float4* s_uv = reinterpret_cast<float4*>(s_mem + SM_UV);
     float4* s_q2 = reinterpret_cast<float4*>(s_mem + SM_Q2);
@@ -63,6 +69,12 @@ raster_kernel(const SplatRec* __restrict__ recs, const uint32_t* __restrict__ ti
             s_q0[t] = __ldg(rp);
             s_uv[t] = __ldg(rp + 1);
             s_q2[t] = __ldg(rp + 2);
+            if (MODE == 2) {
+                float4* s_ex = reinterpret_cast<float4*>(s_mem + SM_EXTRA);
+                const float4* ep = extra + (size_t)r * 4;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) s_ex[q * RT_CHUNK + t] = __ldg(ep + q);
+            }
         }
         __syncthreads();
         // each warp compacts the chunk to the splats whose bbox touches its 8x4 pixels (order kept)
@@ -93,21 +105,60 @@ raster_kernel(const SplatRec* __restrict__ recs, const uint32_t* __restrict__ ti
                 asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(q0.x), "=f"(q0.y), "=f"(q0.z), "=f"(q0.w) : "r"(a_rec));
                 asm volatile("ld.shared.v2.f32 {%0,%1}, [%2+4096];" : "=f"(q1.x), "=f"(q1.y) : "r"(a_rec));
                 const float dx = __fsub_rn(fx, q0.x), dy = __fsub_rn(fy, q0.y);
-                const float u = __fmaf_rn(q0.w, dy, __fmul_rn(q0.z, dx));
-                const float v = __fmaf_rn(q1.y, dy, __fmul_rn(q1.x, dx));
-                if (fabsf(u) <= 1.0f && fabsf(v) <= 1.0f) {
+                float e, opac;
+                float4 q2;
+                if (MODE == 0) {
+                    const float u = __fmaf_rn(q0.w, dy, __fmul_rn(q0.z, dx));
+                    const float v = __fmaf_rn(q1.y, dy, __fmul_rn(q1.x, dx));
+                    if (!(fabsf(u) <= 1.0f && fabsf(v) <= 1.0f)) continue;
                     const float qd = __fmaf_rn(v, v, __fmul_rn(u, u));
-                    float4 q2;
                     asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4+8192];" : "=f"(q2.x), "=f"(q2.y), "=f"(q2.z), "=f"(q2.w) : "r"(a_rec));
                     // exp(-4.5 qd) = 2^(qd * -4.5 log2 e); qd <= 2 so the argument stays >= -13 (no range fix-up)
-                    float e;
                     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(qd * -6.492127684f));
-                    const float a = fminf(e * q2.w, 0.999f);
-                    const float w = a * T;
-                    cr = fmaf(w, q2.x, cr); cg = fmaf(w, q2.y, cg); cb = fmaf(w, q2.z, cb);
-                    T = fmaf(-a, T, T);
-                    if (T < T_STOP) break;
+                } else {
+                    // quad-space offset in half-pixels (x right, y up); the quad is the square |m| <= Rq
+                    const float mx = __fadd_rn(dx, dx), my = -__fadd_rn(dy, dy);
+                    const float Rq = q1.y;   // MODE 1: quad half-side in half-pixels
+                    float power;
+                    if (MODE == 1) {
+                        if (!(fabsf(mx) <= Rq && fabsf(my) <= Rq)) continue;
+                        // q0.z, q0.w, q1.x = conic x, y, z;  d = -m  (gaussian.wgsl:459-462)
+                        const float ddx = -mx, ddy = -my;
+                        const float t1 = __fmul_rn(__fmul_rn(q0.z, ddx), ddx), t2 = __fmul_rn(__fmul_rn(q1.x, ddy), ddy);
+                        power = __fadd_rn(__fmul_rn(-0.5f, __fadd_rn(t1, t2)), __fmul_rn(__fmul_rn(q0.w, ddx), ddy));
+                    } else {
+                        float4 e0, e1, e2, e3;
+                        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(e0.x), "=f"(e0.y), "=f"(e0.z), "=f"(e0.w) : "r"(a_rec + SM_EXTRA));
+                        if (!(fabsf(mx) <= e0.x && fabsf(my) <= e0.x)) continue;
+                        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(e1.x), "=f"(e1.y), "=f"(e1.z), "=f"(e1.w) : "r"(a_rec + SM_EXTRA + RT_CHUNK * 16));
+                        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(e2.x), "=f"(e2.y), "=f"(e2.z), "=f"(e2.w) : "r"(a_rec + SM_EXTRA + 2 * RT_CHUNK * 16));
+                        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(e3.x), "=f"(e3.y), "=f"(e3.z), "=f"(e3.w) : "r"(a_rec + SM_EXTRA + 3 * RT_CHUNK * 16));
+                        // pixel_coord = uv * radius * (1, W/H) + mean   (gaussian.wgsl:441-447; uv * radius == m)
+                        const float pcx = __fadd_rn(mx, e0.y), pcy = __fadd_rn(__fmul_rn(my, e0.w), e0.z);
+                        // gaussian_2d.wgsl:134-156: hu = px*T2 - T0, hv = py*T2 - T1, p = hu x hv
+                        const float hux = __fsub_rn(__fmul_rn(pcx, e3.x), e1.x), huy = __fsub_rn(__fmul_rn(pcx, e3.y), e1.y),
+                                    huz = __fsub_rn(__fmul_rn(pcx, e3.z), e1.z);
+                        const float hvx = __fsub_rn(__fmul_rn(pcy, e3.x), e2.x), hvy = __fsub_rn(__fmul_rn(pcy, e3.y), e2.y),
+                                    hvz = __fsub_rn(__fmul_rn(pcy, e3.z), e2.z);
+                        const float cpx = __fsub_rn(__fmul_rn(huy, hvz), __fmul_rn(huz, hvy));
+                        const float cpy = __fsub_rn(__fmul_rn(huz, hvx), __fmul_rn(hux, hvz));
+                        const float cpz = __fsub_rn(__fmul_rn(hux, hvy), __fmul_rn(huy, hvx));
+                        const float us = __fdiv_rn(cpx, cpz), vs = __fdiv_rn(cpy, cpz);
+                        const float s3 = __fadd_rn(__fmul_rn(us, us), __fmul_rn(vs, vs));
+                        const float ex = __fsub_rn(e0.y, pcx), ey = __fsub_rn(e0.z, pcy);
+                        const float s2 = __fmul_rn(2.0f, __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)));
+                        power = -__fmul_rn(0.5f, fminf(s3, s2));
+                    }
+                    if (power > 0.0f) continue;                      // gaussian.wgsl:468-470
+                    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4+8192];" : "=f"(q2.x), "=f"(q2.y), "=f"(q2.z), "=f"(q2.w) : "r"(a_rec));
+                    e = __expf(power);
                 }
+                opac = q2.w;
+                const float a = fminf(e * opac, 0.999f);
+                const float w = a * T;
+                cr = fmaf(w, q2.x, cr); cg = fmaf(w, q2.y, cg); cb = fmaf(w, q2.z, cb);
+                T = fmaf(-a, T, T);
+                if (T < T_STOP) break;
             }
         }
     }
@@ -129,9 +180,14 @@ raster_kernel(const SplatRec* __restrict__ recs, const uint32_t* __restrict__ ti
     }
 }
 
-void launch_raster(const SplatRec* recs, const uint32_t* tile_entries, const uint2* ranges, int W, int H, int tiles_x,
-                   int tiles_y, void* out, uint32_t format, cudaStream_t stream) {
-    raster_kernel<<<tiles_x * tiles_y, RT_THREADS, 0, stream>>>(recs, tile_entries, ranges, W, H, tiles_x, out, format);
+void launch_raster(int mode, const SplatRec* recs, const float4* extra, const uint32_t* tile_entries, const uint2* ranges,
+                   int W, int H, int tiles_x, int tiles_y, void* out, uint32_t format, cudaStream_t stream) {
+    if (mode == 0)
+        raster_kernel<0><<<tiles_x * tiles_y, RT_THREADS, 0, stream>>>(recs, extra, tile_entries, ranges, W, H, tiles_x, out, format);
+    else if (mode == 1)
+        raster_kernel<1><<<tiles_x * tiles_y, RT_THREADS, 0, stream>>>(recs, extra, tile_entries, ranges, W, H, tiles_x, out, format);
+    else
+        raster_kernel<2><<<tiles_x * tiles_y, RT_THREADS, 0, stream>>>(recs, extra, tile_entries, ranges, W, H, tiles_x, out, format);
 }
 
 }  // namespace bgs

@@ -9,6 +9,8 @@
 // -ffp-contract=off is REQUIRED: every a*b+c below is a rounded multiply then a rounded add.
 //
 // Conventions: matrices arrive column-major as Bevy/WGSL store them: m[c*4 + r].
+// min()/max() on floats follow IEEE minNum/maxNum (fmin/fmax: a NaN operand is ignored), the same as the
+// CUDA fminf/fmaxf the kernels use; WGSL leaves the NaN case implementation-defined.
 #include "bgs_oracle.h"
 
 #include <algorithm>
@@ -217,8 +219,8 @@ inline void set_bbox(orc_splat& o, float cx, float cy, float hx, float hy, int W
     float y0 = std::ceil((cy - hy) - (0.5f + sy));
     float y1 = std::floor((cy + hy) - (0.5f - sy));
     if (!(x0 <= x1) || !(y0 <= y1)) return;
-    x0 = std::max(x0, 0.0f); y0 = std::max(y0, 0.0f);
-    x1 = std::min(x1, (float)(Wi - 1)); y1 = std::min(y1, (float)(Hi - 1));
+    x0 = std::fmax(x0, 0.0f); y0 = std::fmax(y0, 0.0f);
+    x1 = std::fmin(x1, (float)(Wi - 1)); y1 = std::fmin(y1, (float)(Hi - 1));
     if (!(x0 <= x1) || !(y0 <= y1)) return;
     o.xlo = (int)x0; o.xhi = (int)x1; o.ylo = (int)y0; o.yhi = (int)y1;
 }
@@ -291,13 +293,13 @@ void project_one(const Ctx& C, const float* p4, const float* sh, const float* q,
         // ---- helpers.wgsl:49-67
         const float det = a * c - b * b;
         const float mid = 0.5f * (a + c);
-        const float disc = std::max(0.0f, mid * mid - det);
+        const float disc = std::fmax(0.0f, mid * mid - det);
         const float term = std::sqrt(disc);
         const float l1 = mid + term;
         if (s.aabb) {
             // ---- helpers.wgsl:69-79, gaussian.wgsl:299-309: square of half-side cutoff*sqrt(l1)
-            const float l2 = std::max(mid - term, 0.0f);
-            const float Rq = cutoff * std::max(std::sqrt(l1), std::sqrt(l2));
+            const float l2 = std::fmax(mid - term, 0.0f);
+            const float Rq = cutoff * std::fmax(std::sqrt(l1), std::sqrt(l2));
             const float dinv = 1.0f / det;
             o.extra[0] = c * dinv; o.extra[1] = -b * dinv; o.extra[2] = a * dinv; o.extra[3] = Rq;
             const float h = 0.5f * Rq;
@@ -357,7 +359,7 @@ void project_one(const Ctx& C, const float* p4, const float* sh, const float* q,
             const float ex = mean[0] * mean[0] - dot3(f0, T0);
             const float ey = mean[1] * mean[1] - dot3(f1, T1);
             if (ex < 1.0e-4f || ey < 1.0e-4f) ok = false;   // NaN extents fall through (NaN quad)
-            else Rq = std::max(std::max(std::sqrt(ex), std::sqrt(ey)), cutoff * 0.707106f);
+            else Rq = std::fmax(std::fmax(std::sqrt(ex), std::sqrt(ey)), cutoff * 0.707106f);
         }
         if (ok) {
             o.extra[3] = Rq; o.extra[4] = mean[0]; o.extra[5] = mean[1]; o.extra[6] = W / H;
@@ -405,10 +407,10 @@ void project_one(const Ctx& C, const float* p4, const float* sh, const float* q,
 // ---- material/depth.wgsl:3-11
 inline void depth_to_rgb(float depth, float dmin, float dmax, float rgb[3]) {
     float nd = (depth - dmin) / (dmax - dmin);
-    nd = std::min(std::max(nd, 0.0f), 1.0f);
+    nd = std::fmin(std::fmax(nd, 0.0f), 1.0f);
     auto smooth = [](float e0, float e1, float x) {
         float t = (x - e0) / (e1 - e0);
-        t = std::min(std::max(t, 0.0f), 1.0f);
+        t = std::fmin(std::fmax(t, 0.0f), 1.0f);
         return t * t * (3.0f - 2.0f * t);
     };
     rgb[0] = smooth(0.5f, 1.0f, nd);
@@ -448,11 +450,11 @@ inline bool eval_alpha(const orc_splat& sp, const orc_settings& s, float fx, flo
             const float s3 = us * us + vs * vs;
             const float ex = sp.extra[4] - pcx, ey = sp.extra[5] - pcy;
             const float s2 = 2.0f * (ex * ex + ey * ey);
-            power = -(0.5f * std::min(s3, s2));
+            power = -(0.5f * std::fmin(s3, s2));
         }
         if (power > 0.0f) return false;                  // gaussian.wgsl:468-470
     }
-    *alpha = std::min(std::exp(power) * sp.op, 0.999f);
+    *alpha = std::fmin(std::exp(power) * sp.op, 0.999f);
     return true;
 }
 

@@ -45,7 +45,12 @@ def check_against_oracle(plugin, oracle, cloud, settings, view, f16=False, pixel
         assert np.array_equal(ids, til["rank_to_id"])
         orec = oracle.project(oc, view.to_abi(), u, settings.to_abi(), til["rank_to_id"])
         drawn = orec["xlo"] <= orec["xhi"]
-        geo = np.stack([orec[k] for k in ("cx", "cy", "ux", "uy", "vx", "vy")], 1)
+        if settings.aabb and settings.gaussian_mode == B.GaussianMode.Gaussian3d:
+            # USE_AABB record: centre, conic x/y/z, quad half-side
+            geo = np.stack([orec["cx"], orec["cy"], orec["extra"][:, 0], orec["extra"][:, 1], orec["extra"][:, 2],
+                            orec["extra"][:, 3]], 1)
+        else:
+            geo = np.stack([orec[k] for k in ("cx", "cy", "ux", "uy", "vx", "vy")], 1)
         assert np.array_equal(rec[drawn, :6].view(np.uint32), geo[drawn].view(np.uint32)), "projected geometry not bit-exact"
         bb = rec[:, 6:8].view(np.uint32)
         assert np.array_equal(bb[drawn, 0], (orec["xlo"][drawn].astype(np.uint32) | (orec["xhi"][drawn].astype(np.uint32) << 16)))
@@ -90,6 +95,16 @@ def test_parity_settings_variants(plugin, oracle):
                dict(rasterize_mode=B.RasterizeMode.Normal), dict(draw_mode=B.DrawMode.HighlightSelected)):
         s = B.CloudSettings(global_scale=0.2, **kw)
         check_against_oracle(plugin, oracle, cloud, s, view)
+
+
+@pytest.mark.parametrize("gm,aabb,f16", [(B.GaussianMode.Gaussian3d, True, False), (B.GaussianMode.Gaussian2d, True, False),
+                                         (B.GaussianMode.Gaussian2d, False, False), (B.GaussianMode.Gaussian2d, True, True)])
+def test_parity_aabb_and_2dgs(plugin, oracle, gm, aabb, f16):
+    """Rows a8 (2DGS surfels, gaussian_2d.wgsl:49-156) and the USE_AABB conic variant (gaussian.wgsl:459-471)."""
+    cloud = B.random_gaussians_3d_seeded(25000, 13)
+    for scale, view in ((0.25, B.headless_view(320, 200)), (0.08, B.orbit_view(2, 8, 417, 233))):
+        s = B.CloudSettings(global_scale=scale, gaussian_mode=gm, aabb=aabb)
+        check_against_oracle(plugin, oracle, cloud, s, view, f16=f16)
 
 
 def test_parity_model_transform_and_draw_selected(plugin, oracle):
