@@ -29,6 +29,8 @@ void launch_onesweep(const uint32_t* keys_in, const uint32_t* vals_in, uint32_t*
                      const uint32_t* n_ptr, uint32_t capacity, uint32_t n_hint, const uint32_t* hist, uint32_t* status,
                      uint32_t* tile_ctr, int shift, int sm_count, cudaStream_t stream);
 // project.cu
+void launch_depth_range(const float4* pos, uint32_t n, const uint32_t* sorted_payload, const uint32_t* slot_ids,
+                        FrameCounters* ctr, const FrameConsts& fc, cudaStream_t stream);
 void launch_project(bool f16, const float4* pos, const void* sh, const void* rot, const void* so,
                     const uint32_t* index_list, int by_slot, const FrameCounters* ctr, const FrameConsts& fc,
                     SplatRec* recs, float4* extra, uint32_t n_hint, cudaStream_t stream);
@@ -396,8 +398,8 @@ bgs_status bgs_render(bgs_context* c, const bgs_cloud* cloud, const bgs_view* vi
         return fail(c, BGS_EINVAL, "render: radix_sort_depth_bits must be 16, 24 or 32");
     if (st->gaussian_mode != BGS_GAUSSIAN_3D && st->gaussian_mode != BGS_GAUSSIAN_2D)
         return fail(c, BGS_EINVAL, "render: gaussian_mode %u not supported (Gaussian4d is out of scope)", st->gaussian_mode);
-    if (st->rasterize_mode != BGS_RASTERIZE_COLOR && st->rasterize_mode != BGS_RASTERIZE_NORMAL)
-        return fail(c, BGS_EINVAL, "render: rasterize_mode %u not supported yet", st->rasterize_mode);
+    if (st->rasterize_mode > BGS_RASTERIZE_NORMAL)
+        return fail(c, BGS_EINVAL, "render: rasterize_mode %u not supported (Color, Depth, Normal are)", st->rasterize_mode);
     if (st->draw_mode > BGS_DRAW_HIGHLIGHT_SELECTED) return fail(c, BGS_EINVAL, "render: bad draw_mode");
     const int W = (int)view->viewport[2], H = (int)view->viewport[3];
     if (W <= 0 || H <= 0 || W > 65535 || H > 65535) return fail(c, BGS_EINVAL, "render: viewport %dx%d out of range", W, H);
@@ -427,6 +429,7 @@ bgs_status bgs_render(bgs_context* c, const bgs_cloud* cloud, const bgs_view* vi
     fc.gaussian_mode = st->gaussian_mode; fc.rasterize_mode = st->rasterize_mode; fc.aabb = st->aabb;
     fc.adaptive = st->opacity_adaptive_radius; fc.draw_mode = st->draw_mode;
     fc.Wi = W; fc.Hi = H; fc.tiles_x = tiles_x; fc.tiles_y = tiles_y;
+    fc.n_cloud = n;
 
     bgs_status s = ensure_cloud_scratch(c, n);
     if (s != BGS_OK) return s;
@@ -488,7 +491,9 @@ bgs_status bgs_render(bgs_context* c, const bgs_cloud* cloud, const bgs_view* vi
         // ---- stage 3 (compact mode): projection + colour in slot order on the second stream, concurrently
         //      with the depth sort (it only needs slot_ids); records land at recs[slot]
         const uint32_t n_hint = c->n_vis_hint ? c->n_vis_hint + c->n_vis_hint / 4 + 1024 : n;
-        if (by_slot) {
+        // Depth colouring needs sorted[1] / sorted[N-1]: the projection then waits for the sort
+        const bool overlap = by_slot && st->rasterize_mode != BGS_RASTERIZE_DEPTH;
+        if (overlap) {
             CU(c, cudaEventRecord(c->ev_fork, q));
             CU(c, cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
             CU(c, cudaEventRecord(c->ev_p0, c->stream2));
@@ -512,12 +517,17 @@ bgs_status bgs_render(bgs_context* c, const bgs_cloud* cloud, const bgs_view* vi
         }
         c->depth_result = cur;
         CU(c, cudaEventRecord(c->ev[2], q));
-        if (by_slot) {
+        if (overlap) {
             CU(c, cudaStreamWaitEvent(q, c->ev_join, 0));
         } else {
-            // ---- stage 3 (SORT_ALL): projection in front-to-back rank order after the sort; recs[rank]
+            // ---- stage 3 after the sort: SORT_ALL (records by front-to-back rank) or Depth colouring (by slot)
+            if (st->rasterize_mode == BGS_RASTERIZE_DEPTH) {
+                launch_depth_range(cloud->pos, n, c->vals[cur], by_slot ? c->slot_ids : nullptr, c->ctr, fc, q);
+                ++launches;
+            }
             CU(c, cudaEventRecord(c->ev_p0, q));
-            launch_project(cloud->f16, cloud->pos, cloud->sh, cloud->rot, cloud->so, c->vals[cur], 0, c->ctr, fc, c->recs,
+            launch_project(cloud->f16, cloud->pos, cloud->sh, cloud->rot, cloud->so, by_slot ? c->slot_ids : c->vals[cur],
+                           by_slot ? 1 : 0, c->ctr, fc, c->recs,
                            raster_mode == 2 ? c->extra : nullptr, n_hint < n ? n_hint : n, q);
             ++launches;
             CU(c, cudaEventRecord(c->ev_p1, q));

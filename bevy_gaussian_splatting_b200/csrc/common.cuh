@@ -26,6 +26,7 @@ struct FrameConsts {
     uint32_t key_shift;         // 32 - radix_sort_depth_bits
     uint32_t gaussian_mode, rasterize_mode, aabb, adaptive, draw_mode;
     int Wi, Hi, tiles_x, tiles_y;
+    uint32_t n_cloud;           // gaussians in the cloud
 };
 
 // Projected splat record, 48 B, stored by front-to-back rank.
@@ -45,8 +46,9 @@ struct FrameCounters {
     uint32_t n_pairs_needed;    // pairs the frame needs (may exceed capacity -> host regrows)
     uint32_t tile_ctr[16];      // dynamic tile tickets: [0] keygen, [1..4] depth passes,
                                 // [5] bin, [6..7] pair passes, [8..] spare
-    uint32_t culled_min, culled_min2, culled_max;   // for RasterizeMode::Depth's sorted[1]/[N-1]
-    uint32_t pad;
+    uint32_t culled_min_inv;    // RasterizeMode::Depth: max over culled of (0xFFFFFFFF - index); 0 = none culled
+    uint32_t culled_max_p1;     //                       max over culled of (index + 1);          0 = none culled
+    float depth_min, depth_max; //                       distances of sorted[N-1] / sorted[1] (gaussian.wgsl:329-349)
     uint32_t barrier[8];        // grid barriers of the cooperative kernels: [0] keygen, [1] bin
     uint32_t big_count, big_head;   // bin: queue of large footprints (grows from the back of the queue arrays)
     uint32_t med_count, med_head;   // bin: queue of medium footprints (grows from the front), drained 32 per warp

@@ -47,6 +47,10 @@ keygen_compact_kernel(const float4* __restrict__ pos, uint32_t n, FrameConsts fc
         const KeyOut k = key_of(fc, p[j].x, p[j].y, p[j].z);
         const bool v = (i < n) && k.visible;
         key[j] = k.key;
+        if (fc.rasterize_mode == BGS_RASTERIZE_DEPTH && i < n && !k.visible) {
+            atomicMax(&ctr->culled_min_inv, 0xFFFFFFFFu - i);
+            atomicMax(&ctr->culled_max_p1, i + 1u);
+        }
         const uint32_t b = __ballot_sync(0xffffffffu, v);
         prefix[j] = __popc(b & lanemask_lt());
         if (v) vis_bits |= 1u << j;
@@ -123,6 +127,7 @@ keygen_coop_kernel(const float4* __restrict__ pos, uint32_t n, FrameConsts fc, u
 
     // ---- phase 1: keys for every gaussian of this CTA's range, visible count
     uint32_t mine = 0u;
+    uint32_t cmin_inv = 0u, cmax_p1 = 0u;   // Depth mode only: extremes of the culled indices
     for (uint32_t tile = t0; tile < t1; ++tile) {
         const uint32_t tile_base = tile * KG_TILE;
         float4 p[KG_ITEMS];
@@ -139,12 +144,21 @@ keygen_coop_kernel(const float4* __restrict__ pos, uint32_t n, FrameConsts fc, u
                 const uint32_t key = k.visible ? k.key : culled;
                 __stcg(keys_tmp + i, key);
                 mine += k.visible ? 1u : 0u;
+                if (!k.visible) { cmin_inv = max(cmin_inv, 0xFFFFFFFFu - i); cmax_p1 = max(cmax_p1, i + 1u); }
             }
         }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
     if (lane == 0) s_red[warp] = mine;
+    if (fc.rasterize_mode == BGS_RASTERIZE_DEPTH) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            cmin_inv = max(cmin_inv, __shfl_xor_sync(0xffffffffu, cmin_inv, o));
+            cmax_p1 = max(cmax_p1, __shfl_xor_sync(0xffffffffu, cmax_p1, o));
+        }
+        if (lane == 0 && cmax_p1) { atomicMax(&ctr->culled_min_inv, cmin_inv); atomicMax(&ctr->culled_max_p1, cmax_p1); }
+    }
     __syncthreads();
     if (t == 0) {
         uint32_t tot = 0u;

@@ -94,6 +94,34 @@ struct Attr<true> {    // f16 planes: src/gaussian/f16.rs:30-56,244-263; planar.
     }
 };
 
+// RasterizeMode::Depth (gaussian.wgsl:329-349): min distance from sorted[N-1], max from sorted[1] of the
+// reference's FULL sorted buffer (culled entries keyed all-ones sit at its end, in index order) -- literal,
+// including the [1] (not [0]) and the fact that the "nearest" entry is a culled gaussian whenever one exists.
+__global__ void depth_range_kernel(const float4* __restrict__ pos, uint32_t n, const uint32_t* __restrict__ sorted_payload,
+                                   const uint32_t* __restrict__ slot_ids /* null: payload is the gaussian index */,
+                                   FrameCounters* __restrict__ ctr, FrameConsts fc) {
+    if (threadIdx.x != 0 || blockIdx.x != 0 || n < 2u) return;
+    const uint32_t n_vis = ctr->n_vis, n_sorted = ctr->n_sort;
+    auto id_at = [&](uint32_t i) { const uint32_t p = sorted_payload[i]; return slot_ids ? slot_ids[p] : p; };
+    uint32_t first, last;
+    if (n_sorted == n) {                       // SORT_ALL: the full buffer is materialised
+        first = id_at(1u); last = id_at(n - 1u);
+    } else {
+        const uint32_t cmin = 0xFFFFFFFFu - ctr->culled_min_inv, cmax = ctr->culled_max_p1 - 1u;
+        first = n_vis >= 2u ? id_at(1u) : cmin;            // n_vis == 0 draws nothing: value irrelevant
+        last = (n - n_vis) >= 1u ? cmax : id_at(n - 1u);
+    }
+    auto dist = [&](uint32_t id) {
+        const float4 p = pos[id];
+        float pw[4];
+        mat4_point(fc.model, p.x, p.y, p.z, pw);
+        const float d[3] = {pw[0] - fc.cam[0], pw[1] - fc.cam[1], pw[2] - fc.cam[2]};
+        return sqrtf(dot3(d, d));
+    };
+    ctr->depth_min = dist(last);
+    ctr->depth_max = dist(first);
+}
+
 template <bool F16>
 __global__ void __launch_bounds__(128)
 project_kernel(const float4* __restrict__ pos, const void* __restrict__ sh_p, const void* __restrict__ rot_p,
@@ -325,6 +353,20 @@ project_kernel(const float4* __restrict__ pos, const void* __restrict__ sh_p, co
 #pragma unroll
                     for (int cc = 0; cc < 3; ++cc) rgb[cc] = srgb_to_linear(rgb[cc]);
                 }
+            } else if (fc.rasterize_mode == BGS_RASTERIZE_DEPTH) {
+                // material/depth.wgsl:3-11
+                const float dlt[3] = {k.pw[0] - fc.cam[0], k.pw[1] - fc.cam[1], k.pw[2] - fc.cam[2]};
+                const float depth = sqrtf(dot3(dlt, dlt));
+                const float dmin = ctr->depth_min, dmax = ctr->depth_max;
+                if (fc.n_cloud >= 2u) {   // the reference reads sorted[1]: undefined for a 1-gaussian cloud (oracle: black)
+                float nd = (depth - dmin) / (dmax - dmin);
+                nd = fminf(fmaxf(nd, 0.0f), 1.0f);   // fmin/fmax ignore a NaN operand, like the oracle's
+                float t1 = (nd - 0.5f) / (1.0f - 0.5f); t1 = fminf(fmaxf(t1, 0.0f), 1.0f);
+                float t2 = (nd - 0.0f) / (0.5f - 0.0f); t2 = fminf(fmaxf(t2, 0.0f), 1.0f);
+                rgb[0] = t1 * t1 * (3.0f - 2.0f * t1);
+                rgb[1] = 1.0f - fabsf(nd - 0.5f) * 2.0f;
+                rgb[2] = 1.0f - t2 * t2 * (3.0f - 2.0f * t2);
+                }
             } else if (fc.rasterize_mode == BGS_RASTERIZE_NORMAL) {
                 // gaussian.wgsl:350-368
                 float SR[3], Ln[3], wn[4];
@@ -348,6 +390,11 @@ project_kernel(const float4* __restrict__ pos, const void* __restrict__ sh_p, co
         out[1] = make_float4(rec.vx, rec.vy, __uint_as_float(rec.bx), __uint_as_float(rec.by));
         out[2] = make_float4(rec.r, rec.g, rec.b, rec.op);
     }
+}
+
+void launch_depth_range(const float4* pos, uint32_t n, const uint32_t* sorted_payload, const uint32_t* slot_ids,
+                        FrameCounters* ctr, const FrameConsts& fc, cudaStream_t stream) {
+    depth_range_kernel<<<1, 32, 0, stream>>>(pos, n, sorted_payload, slot_ids, ctr, fc);
 }
 
 void launch_project(bool f16, const float4* pos, const void* sh, const void* rot, const void* so,
