@@ -32,6 +32,7 @@ METRIC = "rendered Msplats/sec @1080p, 6M-gaussian cloud"
 N_GAUSSIANS = 6_000_000
 WIDTH, HEIGHT = 1920, 1080
 GLOBAL_SCALE = 0.02
+FRAMES_IN_FLIGHT = 2
 WORKLOAD = ("C3: 6M random_gaussians (seed 0), f16 planar 128 B/gaussian, 1920x1080, global_scale=0.02 "
             "(Mip-NeRF-360-scale), headless camera (0,1.5,5) / one orbit view per GPU")
 
@@ -161,47 +162,65 @@ def run_cuda(args):
 
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    plugin = B.GaussianSplattingPlugin(local_rank)
+    # FRAMES_IN_FLIGHT contexts on this GPU share the cloud; consecutive frames alternate between them, so one
+    # frame's latency-bound front (key-gen, sorts, binning) overlaps the previous frame's raster.  Each context
+    # has its own stream + scratch (bgs.h: "distinct contexts may be used concurrently").
+    plugins = [B.GaussianSplattingPlugin(local_rank) for _ in range(FRAMES_IN_FLIGHT)]
+    plugin = plugins[0]
     cloud = make_cloud(N_GAUSSIANS)
     handle = plugin.add_cloud(cloud, f16=True)
     settings = B.CloudSettings(global_scale=GLOBAL_SCALE)
-    sess = MultiViewSession(rank, world, 0, plugin=plugin if world > 1 else None)
+    sessions = [MultiViewSession(rank, world, 0, plugin=p if world > 1 else None) for p in plugins]
+    sess = sessions[0]
     view = sess.view(WIDTH, HEIGHT) if world > 1 else B.headless_view(WIDTH, HEIGHT)
     frame_bytes = WIDTH * HEIGHT * 4
-    stream = torch.cuda.ExternalStream(plugin.stream_ptr, device=torch.device("cuda", local_rank))
-    all_frames = torch.empty(world * frame_bytes, dtype=torch.uint8, device="cuda") if (world > 1 and rank == 0) else None
+    dev = torch.device("cuda", local_rank)
+    streams = [torch.cuda.ExternalStream(p.stream_ptr, device=dev) for p in plugins]
+    all_frames = [torch.empty(world * frame_bytes, dtype=torch.uint8, device="cuda") if (world > 1 and rank == 0) else None
+                  for _ in plugins]
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step_device():
-        # frames are enqueued back to back on the context stream (BGS_FLAG_ASYNC), as the reference submits
-        # command buffers without reading anything back; plugin.sync() closes the timed region
-        plugin.render_view(handle, settings, view, fmt="rgba8_srgb", to_host=False, asynchronous=True)
+    def sync_all():
+        ok = True
+        for p in plugins:
+            ok = p.sync() and ok
+        return ok
+
+    def step(i, out=None):
+        # frames are only ENQUEUED (BGS_FLAG_ASYNC), as the reference submits command buffers without reading
+        # anything back; sync_all() closes the timed region
+        k = i % FRAMES_IN_FLIGHT
+        p = plugins[k]
+        p.render_view(handle, settings, view, fmt="rgba8_srgb", to_host=out is not None, out=out, asynchronous=True)
         if world > 1:
-            sess.gather_device(plugin.frame_device_ptr, all_frames.data_ptr() if all_frames is not None else 0, frame_bytes)
+            sessions[k].gather_device(p.frame_device_ptr, all_frames[k].data_ptr() if all_frames[k] is not None else 0, frame_bytes)
 
     # ---- device-resident throughput ("value"): inputs (768 MB cloud >> 126 MB L2) already in HBM
-    plugin.render_view(handle, settings, view, fmt="rgba8_srgb", to_host=False)   # sizes every buffer
-    for _ in range(args.warmup):
-        step_device()
-    assert plugin.sync()
+    for p in plugins:
+        p.render_view(handle, settings, view, fmt="rgba8_srgb", to_host=False)   # sizes every buffer
+    for i in range(args.warmup):
+        step(i)
+    assert sync_all()
     barrier()
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(args.steps):
-        step_device()
-    e1.record(stream)
-    assert plugin.sync(), "pair buffer overflowed inside the timed region"
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = [torch.cuda.Event(enable_timing=True) for _ in plugins]
+    e0.record(streams[0])
+    for i in range(args.steps):
+        step(i)
+    for ev, st_ in zip(e1, streams):
+        ev.record(st_)
+    assert sync_all(), "pair buffer overflowed inside the timed region"
     barrier()
-    ms_total = e0.elapsed_time(e1)
+    ms_total = max(e0.elapsed_time(ev) for ev in e1)     # device time from the first frame's start to the last frame's end
     clk = clocks.stop() if rank == 0 else None
-    # per-frame / per-stage times (live CUDA events inside the library), measured frame by frame
+    # per-frame / per-stage times (live CUDA events inside the library), one frame at a time on an idle GPU
     frame_us, stage_rows = [], []
     for _ in range(min(args.steps, 100)):
         plugin.render_view(handle, settings, view, fmt="rgba8_srgb", to_host=False)
@@ -217,20 +236,18 @@ def run_cuda(args):
     stage_med = np.median(np.array(stage_rows), axis=0)
 
     # ---- end to end through the C ABI with HOST buffers: per step the view/uniform/settings structs go
-    #      host->device as kernel arguments and the finished RGBA8 frame comes back into pinned host memory
-    # K frames in, K frames out: each frame's D2H copy (copy stream) overlaps the next frame's kernels; two pinned
-    # host buffers alternate, plugin.sync() (all frames delivered) closes the timed region.
-    host_frames = [torch.empty((HEIGHT, WIDTH, 4), dtype=torch.uint8).pin_memory().numpy() for _ in range(2)]
-    for i in range(min(3, args.warmup)):
-        plugin.render_view(handle, settings, view, fmt="rgba8_srgb", out=host_frames[i & 1], asynchronous=True)
-    assert plugin.sync()
+    #      host->device as kernel arguments and the finished RGBA8 frame comes back into pinned host memory.
+    # K frames in, K frames out: each frame's D2H copy (copy stream) overlaps later frames' kernels; pinned host
+    # buffers alternate; sync_all() (every frame delivered to host memory) closes the timed region.
+    host_frames = [torch.empty((HEIGHT, WIDTH, 4), dtype=torch.uint8).pin_memory().numpy() for _ in range(2 * FRAMES_IN_FLIGHT)]
+    for i in range(2 * FRAMES_IN_FLIGHT):
+        step(i, out=host_frames[i])
+    assert sync_all()
     barrier()
     t0 = time.perf_counter()
     for i in range(args.steps):
-        plugin.render_view(handle, settings, view, fmt="rgba8_srgb", out=host_frames[i & 1], asynchronous=True)
-        if world > 1:
-            sess.gather_device(plugin.frame_device_ptr, all_frames.data_ptr() if all_frames is not None else 0, frame_bytes)
-    assert plugin.sync()
+        step(i, out=host_frames[i % (2 * FRAMES_IN_FLIGHT)])
+    assert sync_all()
     barrier()
     e2e_ms = 1000.0 * (time.perf_counter() - t0) / args.steps
     if dist is not None:
@@ -240,7 +257,8 @@ def run_cuda(args):
     h2d = sum(__import__("ctypes").sizeof(c) for c in (abi.bgs_view, abi.bgs_cloud_uniform, abi.bgs_settings))
 
     if rank != 0:
-        sess.destroy()
+        for se in sessions:
+            se.destroy()
         if dist is not None:
             dist.destroy_process_group()
         return 0
@@ -285,6 +303,7 @@ def run_cuda(args):
         "vs_baseline": None, "dtype": "f32 (f16-packed inputs)", "data": "synthetic",
         "config": {"workload": WORKLOAD, "views": views, "parallelism": f"view-parallel x{world}, replicated cloud",
                    "n_visible": nv, "n_pairs": I, "l2": "inputs larger than L2 (768 MB cloud vs 126 MB)",
+                   "frames_in_flight": FRAMES_IN_FLIGHT,
                    "frame_format": "rgba8_srgb"},
         "frame_ms_p50": round(float(np.percentile(frame_us, 50)) / 1000.0, 4),
         "frame_ms_p95": round(float(np.percentile(frame_us, 95)) / 1000.0, 4),
@@ -295,7 +314,8 @@ def run_cuda(args):
         "roofline": roofline, "stages": stages, "cpu_baseline": cpu, "clocks": clk,
     }
     print(json.dumps(line), flush=True)
-    sess.destroy()
+    for se in sessions:
+        se.destroy()
     if dist is not None:
         dist.destroy_process_group()
     return 0

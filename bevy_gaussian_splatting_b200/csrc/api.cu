@@ -266,8 +266,10 @@ bgs_status bgs_context_create(int cuda_device, bgs_context** out) {
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&c->coop, cudaDevAttrCooperativeLaunch, cuda_device);
     if (e == cudaSuccess && c->coop) {
         const int kb = keygen_coop_blocks_per_sm(), bb = bin_coop_blocks_per_sm();
-        c->kg_grid = (uint32_t)(c->sm_count * (kb > 4 ? 4 : kb));
-        c->bin_grid = (uint32_t)(c->sm_count * (bb > 4 ? 4 : bb));
+        int lim = 4;   // CTAs per SM of the cooperative kernels (BGS_COOP_BLOCKS overrides; fewer leaves room for a
+        if (const char* e = getenv("BGS_COOP_BLOCKS")) lim = atoi(e) > 0 ? atoi(e) : 4;   // second context's kernels)
+        c->kg_grid = (uint32_t)(c->sm_count * (kb > lim ? lim : kb));
+        c->bin_grid = (uint32_t)(c->sm_count * (bb > lim ? lim : bb));
         if (c->kg_grid == 0 || c->bin_grid == 0 || c->kg_grid > 4096 || c->bin_grid > 4096) c->coop = 0;
     }
     if (e != cudaSuccess) {
@@ -392,7 +394,8 @@ bgs_status bgs_render(bgs_context* c, const bgs_cloud* cloud, const bgs_view* vi
     if (!c) return BGS_EINVAL;
     // not-ready inputs map to the reference's silent skip-frame (radix.rs:645-658, mod.rs:1533-1539)
     if (!cloud || !view || !uni || !st) return fail(c, BGS_NOT_READY, "render: cloud/view/uniform/settings not ready");
-    if (cloud->ctx != c) return fail(c, BGS_EINVAL, "render: cloud belongs to another context");
+    if (cloud->ctx != c && cloud->ctx->device != c->device)
+        return fail(c, BGS_EINVAL, "render: cloud lives on another device");   // contexts of one GPU may share clouds
     if (out_format > BGS_FORMAT_RGBA32F) return fail(c, BGS_EINVAL, "render: unknown out_format %u", out_format);
     if (st->radix_sort_depth_bits != 16 && st->radix_sort_depth_bits != 24 && st->radix_sort_depth_bits != 32)
         return fail(c, BGS_EINVAL, "render: radix_sort_depth_bits must be 16, 24 or 32");
