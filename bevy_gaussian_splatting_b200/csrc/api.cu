@@ -47,8 +47,9 @@ cudaError_t launch_bin_emit_coop(const SplatRec* recs, const uint32_t* perm, Fra
 void launch_tile_ranges(const uint32_t* sorted_tile_ids, const FrameCounters* ctr, uint2* ranges, uint32_t capacity,
                         int sm_count, cudaStream_t stream);
 // raster.cu
-void launch_raster(int mode, const SplatRec* recs, const float4* extra, const uint32_t* tile_entries, const uint2* ranges,
-                   int W, int H, int tiles_x, int tiles_y, void* out, uint32_t format, cudaStream_t stream);
+void launch_raster(int mode, bool large_footprints, const SplatRec* recs, const float4* extra, const uint32_t* tile_entries,
+                   const uint2* ranges, int W, int H, int tiles_x, int tiles_y, void* out, uint32_t format,
+                   cudaStream_t stream);
 }  // namespace bgs
 
 using namespace bgs;
@@ -564,7 +565,9 @@ bgs_status bgs_render(bgs_context* c, const bgs_cloud* cloud, const bgs_view* vi
         CU(c, cudaEventRecord(c->ev[4], q));
         // ---- stage 5: per-tile front-to-back blend
         if (async_host && c->copy_pending[fslot]) CU(c, cudaStreamWaitEvent(q, c->ev_copied[fslot], 0));   // target free again
-        launch_raster(raster_mode, c->recs, c->extra, c->pvals[pcur], c->ranges, W, H, tiles_x, tiles_y, target, out_format, q);
+        // kernel variant picked from the previous frame's mean footprint (pairs per visible splat); results are identical
+        const bool large_fp = c->n_vis_hint > 0 && (uint64_t)c->n_pairs_hint >= 8ull * c->n_vis_hint;
+        launch_raster(raster_mode, large_fp, c->recs, c->extra, c->pvals[pcur], c->ranges, W, H, tiles_x, tiles_y, target, out_format, q);
         ++launches;
         CU(c, cudaEventRecord(c->ev[5], q));
         CU(c, cudaEventRecord(c->ev_done, q));

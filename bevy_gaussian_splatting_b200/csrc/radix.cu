@@ -105,7 +105,18 @@ onesweep_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict
 #pragma unroll
         for (int j = 0; j < RS_ITEMS; ++j) {
             const uint32_t d = (k[j] >> shift) & 255u;
+#ifdef RS_MATCH_BALLOT
+            // 8 ballots + mask intersections instead of one MATCH.ANY (which issues at a fraction of the ALU rate)
+            uint32_t peers = 0xffffffffu;
+#pragma unroll
+            for (int bit = 0; bit < 8; ++bit) {
+                const bool on = (d >> bit) & 1u;
+                const uint32_t m = __ballot_sync(0xffffffffu, on);
+                peers &= on ? m : ~m;
+            }
+#else
             const uint32_t peers = __match_any_sync(0xffffffffu, d);
+#endif
             const int leader = 31 - __clz(peers);
             uint32_t old = 0u;
             if (lane == leader) {
