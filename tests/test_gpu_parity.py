@@ -61,6 +61,11 @@ def check_against_oracle(plugin, oracle, cloud, settings, view, f16=False, pixel
             assert np.abs(rec[drawn, 8:12] - col[drawn]).max() <= 1e-4
         err = float(np.abs(img - til["image"]).max())
         assert err <= pixel_tol, f"pixel L-inf {err}"
+        # the second frame picks kernel variants from the first frame's counts (sort tile size, raster variant)
+        img2 = plugin.render_view(h, settings, view, fmt="rgba32f")
+        err2 = float(np.abs(img2 - til["image"]).max())
+        assert err2 <= pixel_tol, f"pixel L-inf {err2} on the hinted frame"
+        assert np.array_equal(plugin.tile_ranges(), til["tile_ranges"])
         return img, til
     finally:
         h.destroy()
@@ -271,3 +276,33 @@ def test_async_frames_and_deferred_overflow(plugin):
             p2.destroy()
     finally:
         h.destroy()
+
+
+def test_cpp_host_example_matches_python_host(plugin, tmp_path):
+    """The C++ host mirror (include/bgs.hpp, examples/headless.cpp -- the counterpart of the reference's
+    examples/headless.rs) drives the same C ABI: its frame must be byte-identical to the ctypes host's."""
+    import os
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "examples", "headless")
+    if not os.path.exists(exe):
+        subprocess.run(["make", "-C", os.path.join(root, "examples")], check=True)
+    n, w, h, scale = 50000, 640, 360, 0.2
+    cloud_f, raw_f = str(tmp_path / "cloud.bin"), str(tmp_path / "frame.raw")
+    out = subprocess.run([exe, str(n), str(w), str(h), str(scale), str(tmp_path / "0.ppm"), "--dump-cloud", cloud_f, "--raw", raw_f],
+                         check=True, capture_output=True, text=True).stdout
+    assert "rendered=1" in out
+    buf = np.fromfile(cloud_f, np.uint8)
+    assert int(buf[:8].view(np.uint64)[0]) == n
+    f = buf[8:].view(np.float32)
+    cloud = B.PlanarGaussian3d(f[: n * 4].reshape(n, 4), f[n * 4: n * 52].reshape(n, 48), f[n * 52: n * 56].reshape(n, 4),
+                               f[n * 56: n * 60].reshape(n, 4))
+    hnd = plugin.add_cloud(cloud)
+    try:
+        img = plugin.render_view(hnd, B.CloudSettings(global_scale=scale), B.headless_view(w, h), fmt="rgba8_srgb")
+    finally:
+        hnd.destroy()
+    cpp = np.fromfile(raw_f, np.uint8).reshape(h, w, 4)
+    assert np.array_equal(cpp, img)
+    assert img[..., :3].max() > 16
