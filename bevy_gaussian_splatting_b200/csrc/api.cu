@@ -31,7 +31,9 @@ void launch_onesweep(const uint32_t* keys_in, const uint32_t* vals_in, uint32_t*
 // project.cu
 void launch_depth_range(const float4* pos, uint32_t n, const uint32_t* sorted_payload, const uint32_t* slot_ids,
                         FrameCounters* ctr, const FrameConsts& fc, cudaStream_t stream);
-void launch_project(bool f16, const float4* pos, const void* sh, const void* rot, const void* so,
+void launch_repack(bool f16, const void* pos, const void* sh, const void* rot, const void* so, uint32_t n, void* blocks,
+                   cudaStream_t stream);
+void launch_project(bool f16, bool blocked, const float4* pos, const void* sh, const void* rot, const void* so,
                     const uint32_t* index_list, int by_slot, const FrameCounters* ctr, const FrameConsts& fc,
                     SplatRec* recs, float4* extra, uint32_t n_hint, cudaStream_t stream);
 // bin.cu
@@ -62,6 +64,7 @@ struct bgs_cloud {
     void* sh;         // f32: n * 192 B; f16: n * 96 B
     void* rot;        // f32: n * 16 B (w,x,y,z); f16: n * 16 B packed rotation+scale+opacity
     void* so;         // f32: n * 16 B; f16: unused
+    void* blocks;     // gaussian-major copy (f16: n * 128 B, f32: n * 256 B); when set, sh/rot/so are freed
 };
 
 struct bgs_context {
@@ -313,7 +316,7 @@ static bgs_status upload_common(bgs_context* ctx, uint32_t n, bool f16, const fl
     bgs_cloud* cl = new (std::nothrow) bgs_cloud();
     if (!cl) return BGS_ENOMEM;
     cl->ctx = ctx; cl->n = n; cl->f16 = f16;
-    cl->pos = nullptr; cl->sh = nullptr; cl->rot = nullptr; cl->so = nullptr;
+    cl->pos = nullptr; cl->sh = nullptr; cl->rot = nullptr; cl->so = nullptr; cl->blocks = nullptr;
     const size_t sh_bytes = (size_t)n * (f16 ? 96 : 192);
     cudaError_t e = cudaMalloc(&cl->pos, (size_t)n * 16);
     if (e == cudaSuccess) e = cudaMalloc(&cl->sh, sh_bytes);
@@ -323,6 +326,19 @@ static bgs_status upload_common(bgs_context* ctx, uint32_t n, bool f16, const fl
     if (e == cudaSuccess) e = cudaMemcpyAsync(cl->sh, sh, sh_bytes, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(cl->rot, rot, (size_t)n * 16, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess && !f16) e = cudaMemcpyAsync(cl->so, so, (size_t)n * 16, cudaMemcpyHostToDevice, ctx->stream);
+    // gaussian-major blocks for the projection's gather (BGS_LAYOUT=planar keeps only the reference's planes)
+    const char* lay = getenv("BGS_LAYOUT");
+    if (e == cudaSuccess && !(lay && strcmp(lay, "planar") == 0)) {
+        e = cudaMalloc(&cl->blocks, (size_t)n * (f16 ? 128 : 256));
+        if (e == cudaSuccess) {
+            launch_repack(f16, cl->pos, cl->sh, cl->rot, cl->so, n, cl->blocks, ctx->stream);
+            e = cudaStreamSynchronize(ctx->stream);
+        }
+        if (e == cudaSuccess) {
+            cudaFree(cl->sh); cudaFree(cl->rot); cudaFree(cl->so);
+            cl->sh = cl->rot = cl->so = nullptr;
+        }
+    }
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) {
         bgs_cloud_destroy(cl);
@@ -348,7 +364,7 @@ void bgs_cloud_destroy(bgs_cloud* cl) {
         cudaSetDevice(cl->ctx->device);
         if (cl->ctx->last_cloud == cl) { cl->ctx->last_cloud = nullptr; cl->ctx->have_frame = false; }
     }
-    cudaFree(cl->pos); cudaFree(cl->sh); cudaFree(cl->rot); cudaFree(cl->so);
+    cudaFree(cl->pos); cudaFree(cl->sh); cudaFree(cl->rot); cudaFree(cl->so); cudaFree(cl->blocks);
     delete cl;
 }
 
@@ -501,7 +517,7 @@ bgs_status bgs_render(bgs_context* c, const bgs_cloud* cloud, const bgs_view* vi
             CU(c, cudaEventRecord(c->ev_fork, q));
             CU(c, cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
             CU(c, cudaEventRecord(c->ev_p0, c->stream2));
-            launch_project(cloud->f16, cloud->pos, cloud->sh, cloud->rot, cloud->so, c->slot_ids, 1, c->ctr, fc, c->recs,
+            launch_project(cloud->f16, cloud->blocks != nullptr, cloud->pos, cloud->blocks ? cloud->blocks : cloud->sh, cloud->rot, cloud->so, c->slot_ids, 1, c->ctr, fc, c->recs,
                            raster_mode == 2 ? c->extra : nullptr, n_hint < n ? n_hint : n, c->stream2);
             ++launches;
             CU(c, cudaEventRecord(c->ev_p1, c->stream2));
@@ -530,7 +546,7 @@ bgs_status bgs_render(bgs_context* c, const bgs_cloud* cloud, const bgs_view* vi
                 ++launches;
             }
             CU(c, cudaEventRecord(c->ev_p0, q));
-            launch_project(cloud->f16, cloud->pos, cloud->sh, cloud->rot, cloud->so, by_slot ? c->slot_ids : c->vals[cur],
+            launch_project(cloud->f16, cloud->blocks != nullptr, cloud->pos, cloud->blocks ? cloud->blocks : cloud->sh, cloud->rot, cloud->so, by_slot ? c->slot_ids : c->vals[cur],
                            by_slot ? 1 : 0, c->ctr, fc, c->recs,
                            raster_mode == 2 ? c->extra : nullptr, n_hint < n ? n_hint : n, q);
             ++launches;

@@ -53,12 +53,56 @@ __device__ __forceinline__ void make_bbox(float cx, float cy, float hx, float hy
     bx = pack_bbox(x0, x1); by = pack_bbox(y0, y1);
 }
 
-template <bool F16>
+// Attribute fetch.  PLANAR: the reference's SoA planes as uploaded.  BLOCKED (default): a library-owned
+// gaussian-major copy made once at upload -- f16: 128 B = one cache line per gaussian (pos | rot/scale/opacity |
+// sh x 6), f32: 256 B (pos | rot | scale_opacity | sh x 12 | pad) -- so the random gather of a visible splat
+// touches exactly its own line(s) instead of 3-4 partially used ones (the planes stay planar for key-gen).
+template <bool F16, bool BLOCKED>
 struct Attr;
 template <>
-struct Attr<false> {   // f32 planes: src/gaussian/f32.rs:53-175, planar.wgsl:334-364
-    __device__ static void load(const void* sh_p, const void* rot_p, const void* so_p, uint32_t id, float* sh,
-                                float q[4], float so[4], bool need_sh) {
+struct Attr<false, true> {
+    __device__ static float4 load(const float4*, const void* blocks, const void*, const void*, uint32_t id, float* sh,
+                                  float q[4], float so[4], bool need_sh) {
+        const float4* b = reinterpret_cast<const float4*>(blocks) + (size_t)id * 16;
+        const float4 p = __ldg(b), r = __ldg(b + 1), s = __ldg(b + 2);
+        q[0] = r.x; q[1] = r.y; q[2] = r.z; q[3] = r.w;
+        so[0] = s.x; so[1] = s.y; so[2] = s.z; so[3] = s.w;
+        if (need_sh) {
+#pragma unroll
+            for (int i = 0; i < 12; ++i) {
+                const float4 v = __ldg(b + 3 + i);
+                sh[4 * i] = v.x; sh[4 * i + 1] = v.y; sh[4 * i + 2] = v.z; sh[4 * i + 3] = v.w;
+            }
+        }
+        return p;
+    }
+};
+template <>
+struct Attr<true, true> {
+    __device__ static float lo(uint32_t w) { return __half2float(__ushort_as_half((unsigned short)(w & 0xFFFFu))); }
+    __device__ static float hi(uint32_t w) { return __half2float(__ushort_as_half((unsigned short)(w >> 16))); }
+    __device__ static float4 load(const float4*, const void* blocks, const void*, const void*, uint32_t id, float* sh,
+                                  float q[4], float so[4], bool need_sh) {
+        const uint4* b = reinterpret_cast<const uint4*>(blocks) + (size_t)id * 8;
+        const uint4 pw = __ldg(b), w = __ldg(b + 1);
+        q[0] = hi(w.x); q[1] = lo(w.x); q[2] = hi(w.y); q[3] = lo(w.y);
+        so[0] = hi(w.z); so[1] = lo(w.z); so[2] = hi(w.w); so[3] = lo(w.w);
+        if (need_sh) {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+                const uint4 v = __ldg(b + 2 + i);
+                sh[8 * i] = lo(v.x); sh[8 * i + 1] = hi(v.x); sh[8 * i + 2] = lo(v.y); sh[8 * i + 3] = hi(v.y);
+                sh[8 * i + 4] = lo(v.z); sh[8 * i + 5] = hi(v.z); sh[8 * i + 6] = lo(v.w); sh[8 * i + 7] = hi(v.w);
+            }
+        }
+        return make_float4(__uint_as_float(pw.x), __uint_as_float(pw.y), __uint_as_float(pw.z), __uint_as_float(pw.w));
+    }
+};
+template <>
+struct Attr<false, false> {   // f32 planes: src/gaussian/f32.rs:53-175, planar.wgsl:334-364
+    __device__ static float4 load(const float4* pos, const void* sh_p, const void* rot_p, const void* so_p, uint32_t id,
+                                  float* sh, float q[4], float so[4], bool need_sh) {
+        const float4 p = __ldg(pos + id);
         const float4 r = __ldg(reinterpret_cast<const float4*>(rot_p) + id);
         const float4 s = __ldg(reinterpret_cast<const float4*>(so_p) + id);
         q[0] = r.x; q[1] = r.y; q[2] = r.z; q[3] = r.w;
@@ -71,14 +115,16 @@ struct Attr<false> {   // f32 planes: src/gaussian/f32.rs:53-175, planar.wgsl:33
                 sh[4 * i] = v.x; sh[4 * i + 1] = v.y; sh[4 * i + 2] = v.z; sh[4 * i + 3] = v.w;
             }
         }
+        return p;
     }
 };
 template <>
-struct Attr<true> {    // f16 planes: src/gaussian/f16.rs:30-56,244-263; planar.wgsl:117-176
+struct Attr<true, false> {    // f16 planes: src/gaussian/f16.rs:30-56,244-263; planar.wgsl:117-176
     __device__ static float lo(uint32_t w) { return __half2float(__ushort_as_half((unsigned short)(w & 0xFFFFu))); }
     __device__ static float hi(uint32_t w) { return __half2float(__ushort_as_half((unsigned short)(w >> 16))); }
-    __device__ static void load(const void* sh_p, const void* rso_p, const void*, uint32_t id, float* sh,
-                                float q[4], float so[4], bool need_sh) {
+    __device__ static float4 load(const float4* pos, const void* sh_p, const void* rso_p, const void*, uint32_t id, float* sh,
+                                  float q[4], float so[4], bool need_sh) {
+        const float4 p = __ldg(pos + id);
         const uint4 w = __ldg(reinterpret_cast<const uint4*>(rso_p) + id);
         q[0] = hi(w.x); q[1] = lo(w.x); q[2] = hi(w.y); q[3] = lo(w.y);
         so[0] = hi(w.z); so[1] = lo(w.z); so[2] = hi(w.w); so[3] = lo(w.w);
@@ -91,8 +137,36 @@ struct Attr<true> {    // f16 planes: src/gaussian/f16.rs:30-56,244-263; planar.
                 sh[8 * i + 4] = lo(v.z); sh[8 * i + 5] = hi(v.z); sh[8 * i + 6] = lo(v.w); sh[8 * i + 7] = hi(v.w);
             }
         }
+        return p;
     }
 };
+
+// upload-time repack of the planes into gaussian-major blocks (one thread per 16 B chunk; coalesced both ways)
+template <bool F16>
+__global__ void repack_kernel(const uint4* __restrict__ pos, const uint4* __restrict__ sh, const uint4* __restrict__ rot,
+                              const uint4* __restrict__ so, uint32_t n, uint4* __restrict__ blocks) {
+    constexpr uint32_t CH = F16 ? 8u : 16u;          // 16 B chunks per block
+    constexpr uint32_t SHC = F16 ? 6u : 12u;         // sh chunks per gaussian
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)n * CH) return;
+    const uint32_t id = (uint32_t)(i / CH), c = (uint32_t)(i % CH);
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (c == 0) v = pos[id];
+    else if (c == 1) v = rot[id];                    // f16: packed rotation + scale + opacity
+    else if (!F16 && c == 2) v = so[id];
+    else {
+        const uint32_t k = c - (F16 ? 2u : 3u);
+        if (k < SHC) v = sh[(size_t)id * SHC + k];
+    }
+    blocks[i] = v;
+}
+void launch_repack(bool f16, const void* pos, const void* sh, const void* rot, const void* so, uint32_t n, void* blocks,
+                   cudaStream_t stream) {
+    const size_t total = (size_t)n * (f16 ? 8 : 16);
+    const uint32_t grid = (uint32_t)((total + 255) / 256);
+    if (f16) repack_kernel<true><<<grid, 256, 0, stream>>>((const uint4*)pos, (const uint4*)sh, (const uint4*)rot, (const uint4*)so, n, (uint4*)blocks);
+    else repack_kernel<false><<<grid, 256, 0, stream>>>((const uint4*)pos, (const uint4*)sh, (const uint4*)rot, (const uint4*)so, n, (uint4*)blocks);
+}
 
 // RasterizeMode::Depth (gaussian.wgsl:329-349): min distance from sorted[N-1], max from sorted[1] of the
 // reference's FULL sorted buffer (culled entries keyed all-ones sit at its end, in index order) -- literal,
@@ -122,8 +196,8 @@ __global__ void depth_range_kernel(const float4* __restrict__ pos, uint32_t n, c
     ctr->depth_max = dist(first);
 }
 
-template <bool F16>
-__global__ void __launch_bounds__(128)
+template <bool F16, bool BLOCKED>
+__global__ void __launch_bounds__(128, 6)
 project_kernel(const float4* __restrict__ pos, const void* __restrict__ sh_p, const void* __restrict__ rot_p,
                const void* __restrict__ so_p, const uint32_t* __restrict__ index_list, int by_slot,
                const FrameCounters* __restrict__ ctr, FrameConsts fc, SplatRec* __restrict__ recs,
@@ -133,10 +207,9 @@ project_kernel(const float4* __restrict__ pos, const void* __restrict__ sh_p, co
         // by_slot: r is a compact slot (ascending gaussian index; runs concurrently with the depth sort)
         // else   : r is a front-to-back rank, the list is the far->near sorted index list
         const uint32_t id = by_slot ? __ldg(index_list + r) : __ldg(index_list + (n_vis - 1u - r));
-        const float4 p4 = __ldg(pos + id);
         float sh[48], q[4], so[4];
         const bool need_sh = fc.rasterize_mode == BGS_RASTERIZE_COLOR;
-        Attr<F16>::load(sh_p, rot_p, so_p, id, sh, q, so, need_sh);
+        const float4 p4 = Attr<F16, BLOCKED>::load(pos, sh_p, rot_p, so_p, id, sh, q, so, need_sh);
 
         SplatRec rec;
         rec.ux = 0.f; rec.uy = 0.f; rec.vx = 0.f; rec.vy = 0.f;
@@ -397,7 +470,7 @@ void launch_depth_range(const float4* pos, uint32_t n, const uint32_t* sorted_pa
     depth_range_kernel<<<1, 32, 0, stream>>>(pos, n, sorted_payload, slot_ids, ctr, fc);
 }
 
-void launch_project(bool f16, const float4* pos, const void* sh, const void* rot, const void* so,
+void launch_project(bool f16, bool blocked, const float4* pos, const void* sh, const void* rot, const void* so,
                     const uint32_t* index_list, int by_slot, const FrameCounters* ctr, const FrameConsts& fc,
                     SplatRec* recs, float4* extra, uint32_t n_hint, cudaStream_t stream) {
     // grid sized from a hint (last frame's visible count + head-room); the grid-stride loop keeps any
@@ -405,8 +478,11 @@ void launch_project(bool f16, const float4* pos, const void* sh, const void* rot
     uint32_t blocks = (n_hint + 127) / 128;
     if (blocks > 65535u * 8u) blocks = 65535u * 8u;
     if (blocks < 148u) blocks = 148u;
-    if (f16) project_kernel<true><<<blocks, 128, 0, stream>>>(pos, sh, rot, so, index_list, by_slot, ctr, fc, recs, extra);
-    else project_kernel<false><<<blocks, 128, 0, stream>>>(pos, sh, rot, so, index_list, by_slot, ctr, fc, recs, extra);
+    // blocked layout: `sh` carries the block array
+    if (f16 && blocked) project_kernel<true, true><<<blocks, 128, 0, stream>>>(pos, sh, rot, so, index_list, by_slot, ctr, fc, recs, extra);
+    else if (f16) project_kernel<true, false><<<blocks, 128, 0, stream>>>(pos, sh, rot, so, index_list, by_slot, ctr, fc, recs, extra);
+    else if (blocked) project_kernel<false, true><<<blocks, 128, 0, stream>>>(pos, sh, rot, so, index_list, by_slot, ctr, fc, recs, extra);
+    else project_kernel<false, false><<<blocks, 128, 0, stream>>>(pos, sh, rot, so, index_list, by_slot, ctr, fc, recs, extra);
 }
 
 }  // namespace bgs
