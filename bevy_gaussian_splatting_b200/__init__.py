@@ -8,6 +8,7 @@ from .abi import BgsError  # noqa: F401
 from .camera import GaussianCamera, View, headless_view, orbit_view, perspective_view  # noqa: F401
 from .gaussian import (PlanarGaussian3d, random_gaussians_3d, random_gaussians_3d_seeded,  # noqa: F401
                        SH_COEFF_COUNT)
+from .io import parse_ply_3d  # noqa: F401
 from .plugin import CloudTransform, GaussianSplattingPlugin, PlanarGaussian3dHandle  # noqa: F401
 from .settings import (CloudSettings, DrawMode, GaussianColorSpace, GaussianMode, RadixSortDepthBits,  # noqa: F401
                        RasterizeMode, ShaderDefines, SortMode)

@@ -189,8 +189,9 @@ bgs_status ensure_pair_scratch(bgs_context* c, uint32_t pairs) {
     }
     c->cap_pairs = 0;
     for (int i = 0; i < 2; ++i) {
-        CU(c, cudaMalloc(&c->pkeys[i], (size_t)pairs * 4));
-        CU(c, cudaMalloc(&c->pvals[i], (size_t)pairs * 4));
+        // +64 words: the raster's 16 B-granular bulk copies may read a few entries past the last pair
+        CU(c, cudaMalloc(&c->pkeys[i], ((size_t)pairs + 64) * 4));
+        CU(c, cudaMalloc(&c->pvals[i], ((size_t)pairs + 64) * 4));
     }
     c->cap_pairs = pairs;
     return BGS_OK;

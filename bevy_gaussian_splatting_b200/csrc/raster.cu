@@ -23,6 +23,41 @@ namespace bgs {
 constexpr int RT_THREADS = 256;
 constexpr int RT_CHUNK = 256;
 
+// ---- TMA (cp.async.bulk) staging of a tile's slice of the sorted pair list ------------------------------
+// The slice [range.x, range.y) of tile_entries is contiguous, so each 256-entry chunk is brought into shared
+// memory by ONE bulk async copy (UBLKCP) issued by one thread and tracked by an mbarrier; the next chunk's copy
+// is issued before the current chunk is rasterised (double buffer).  Bulk copies need 16 B alignment: the copy
+// starts at the slice address rounded down to 16 B and `lead` skips the extra leading entries.
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+constexpr uint32_t ENT_WORDS = RT_CHUNK + 8;   // a chunk plus up to 3 leading + rounding words
+
+// issue the bulk copy of entries [base, base + cnt) into buffer `buf`; returns nothing (thread 0 only)
+__device__ __forceinline__ void issue_entries(const uint32_t* tile_entries, uint32_t base, uint32_t cnt, uint32_t a_ent,
+                                              uint32_t a_bar, int buf) {
+    const uint32_t lead = base & 3u;
+    const uint32_t bytes = ((lead + cnt) * 4u + 15u) & ~15u;
+    mbar_expect_tx(a_bar + 8u * buf, bytes);
+    tma_bulk_g2s(a_ent + (uint32_t)buf * ENT_WORDS * 4u, tile_entries + (base - lead), bytes, a_bar + 8u * buf);
+}
+
 __device__ __forceinline__ float linear_to_srgb(float c) {
     c = fminf(fmaxf(c, 0.0f), 1.0f);
     return c <= 0.0031308f ? 12.92f * c : 1.055f * powf(c, 1.0f / 2.4f) - 0.055f;
@@ -45,6 +80,8 @@ __global__ void __launch_bounds__(RT_THREADS)
 raster_kernel(const SplatRec* __restrict__ recs, const float4* __restrict__ extra, const uint32_t* __restrict__ tile_entries,
               const uint2* __restrict__ ranges, int W, int H, int tiles_x, void* __restrict__ out, uint32_t format) {
     __shared__ __align__(16) unsigned char s_mem[MODE == 2 ? SM_BYTES_2D : SM_BYTES];
+    __shared__ __align__(16) uint32_t s_ent[2][ENT_WORDS];    // TMA destination: the tile's pair-list chunks
+    __shared__ __align__(8) unsigned long long s_bar[2];
     float4* s_q0 = reinterpret_cast<float4*>(s_mem + SM_Q0);
     float4* s_uv = reinterpret_cast<float4*>(s_mem + SM_UV);
     float4* s_q2 = reinterpret_cast<float4*>(s_mem + SM_Q2);
@@ -61,12 +98,46 @@ raster_kernel(const SplatRec* __restrict__ recs, const float4* __restrict__ extr
     const float fx = (float)px + 0.5f, fy = (float)py + 0.5f;
     const uint2 range = ranges[tile];
 
+    const uint32_t a_ent = (uint32_t)__cvta_generic_to_shared(&s_ent[0][0]);
+    const uint32_t a_bar = (uint32_t)__cvta_generic_to_shared(&s_bar[0]);
+    if (range.x >= range.y) {            // empty tile: nothing to stage (uniform across the CTA)
+        if (inside) {
+            const size_t pix0 = (size_t)py * W + px;
+            if (format == BGS_FORMAT_RGBA32F) reinterpret_cast<float4*>(out)[pix0] = make_float4(0.f, 0.f, 0.f, 1.0f);
+            else if (format == BGS_FORMAT_RGBA16F) reinterpret_cast<uint2*>(out)[pix0] = make_uint2(0u, 0x3C000000u);
+            else reinterpret_cast<uint32_t*>(out)[pix0] = 0xFF000000u;
+        }
+        return;
+    }
+    // tiles with more than one chunk stream their pair list through the TMA double buffer (the next chunk's
+    // copy overlaps this chunk's blending); single-chunk tiles read it directly (no barrier set-up on their path)
+    const bool use_tma = range.y - range.x > (uint32_t)RT_CHUNK;
+    uint32_t issued = 0u, chunk = 0u;
+    if (use_tma) {
+        if (t == 0) {
+            mbar_init(a_bar, 1u); mbar_init(a_bar + 8u, 1u);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (t == 0) issue_entries(tile_entries, range.x, (uint32_t)RT_CHUNK, a_ent, a_bar, 0);
+        issued = 1u;
+    }
+
     float T = inside ? 1.0f : 0.0f, cr = 0.0f, cg = 0.0f, cb = 0.0f;   // T < T_STOP <=> this pixel is done
-    for (uint32_t base = range.x; base < range.y; base += RT_CHUNK) {
+    for (uint32_t base = range.x; base < range.y; base += RT_CHUNK, ++chunk) {
         if (__syncthreads_count(T < T_STOP ? 0 : 1) == 0) break;   // also fences reuse of the staging buffers
         const uint32_t cnt = min((uint32_t)RT_CHUNK, range.y - base);
+        const int buf = (int)(chunk & 1u);
+        // prefetch the NEXT chunk's entries (its buffer was last read two iterations ago: the vote above fenced it)
+        if (use_tma) {
+            if (base + RT_CHUNK < range.y) {
+                if (t == 0) issue_entries(tile_entries, base + RT_CHUNK, min((uint32_t)RT_CHUNK, range.y - base - RT_CHUNK), a_ent, a_bar, buf ^ 1);
+                ++issued;
+            }
+            mbar_wait(a_bar + 8u * buf, (chunk >> 1) & 1u);
+        }
         if ((uint32_t)t < cnt) {
-            const uint32_t r = __ldg(tile_entries + base + t);
+            const uint32_t r = use_tma ? s_ent[buf][(base & 3u) + t] : __ldg(tile_entries + base + t);
             const float4* rp = reinterpret_cast<const float4*>(recs + r);
             s_q0[t] = __ldg(rp);
             s_uv[t] = __ldg(rp + 1);
@@ -164,6 +235,9 @@ raster_kernel(const SplatRec* __restrict__ recs, const float4* __restrict__ extr
             }
         }
     }
+    // an early exit (all pixels saturated) may leave one prefetch in flight: keep the CTA alive until it lands
+    if (t == 0 && issued > chunk)             // chunks [0, chunk) were waited for inside the loop
+        mbar_wait(a_bar + 8u * (chunk & 1u), (chunk >> 1) & 1u);
     if (!inside) return;
     const size_t pix = (size_t)py * W + px;
     if (format == BGS_FORMAT_RGBA32F) {
