@@ -27,7 +27,7 @@ void launch_radix_hist(const uint32_t* keys, const uint32_t* n_ptr, uint32_t cap
                        int sm_count, cudaStream_t stream);
 void launch_onesweep(const uint32_t* keys_in, const uint32_t* vals_in, uint32_t* keys_out, uint32_t* vals_out,
                      const uint32_t* n_ptr, uint32_t capacity, uint32_t n_hint, const uint32_t* hist, uint32_t* status,
-                     uint32_t* tile_ctr, int shift, int sm_count, cudaStream_t stream);
+                     uint32_t* tile_ctr, int shift, int sm_count, cudaStream_t stream, unsigned long long* tl = nullptr);
 // project.cu
 void launch_depth_range(const float4* pos, uint32_t n, const uint32_t* sorted_payload, const uint32_t* slot_ids,
                         FrameCounters* ctr, const FrameConsts& fc, cudaStream_t stream);
@@ -532,7 +532,7 @@ bgs_status bgs_render(bgs_context* c, const bgs_cloud* cloud, const bgs_view* vi
         for (int p = 0; p < depth_passes; ++p) {
             launch_onesweep(c->keys[cur], c->vals[cur], c->keys[cur ^ 1], c->vals[cur ^ 1], &c->ctr->n_sort, n,
                             sort_all ? n : (c->n_vis_hint ? c->n_vis_hint : n), c->hist + p * 256, c->status_depth + p * depth_status_stride, &c->ctr->tile_ctr[1 + p],
-                            8 * p, c->sm_count, q);
+                            8 * p, c->sm_count, q, (p == 1 && c->timeline && getenv("BGS_TIMELINE_SORT")) ? c->timeline : nullptr);
             ++launches;
             cur ^= 1;
         }

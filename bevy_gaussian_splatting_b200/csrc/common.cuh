@@ -54,13 +54,23 @@ struct FrameCounters {
     uint32_t med_count, med_head;   // bin: queue of medium footprints (grows from the front), drained 32 per warp
 };
 
+// flag/counter words exchanged between CTAs of one kernel: relaxed, GPU scope (L2 is the coherence point;
+// ld/st.volatile would be SYSTEM scope)
 __device__ __forceinline__ uint32_t ld_volatile(const uint32_t* p) {
     uint32_t v;
+#ifdef BGS_SYS_SCOPE
     asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+#else
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+#endif
     return v;
 }
 __device__ __forceinline__ void st_volatile(uint32_t* p, uint32_t v) {
+#ifdef BGS_SYS_SCOPE
     asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+#else
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+#endif
 }
 __device__ __forceinline__ uint32_t lanemask_lt() {
     uint32_t m;
@@ -77,7 +87,11 @@ __device__ __forceinline__ uint32_t lanemask_le() {
 __device__ __forceinline__ void timeline_stamp(unsigned long long* tl, int slot) {
     if (tl != nullptr && threadIdx.x == 0) {
         unsigned long long t;
+#ifdef BGS_TIMELINE_CLOCK64
+        t = (unsigned long long)clock64();              // SM cycles: exact intra-CTA deltas
+#else
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+#endif
         tl[(size_t)blockIdx.x * 8 + slot] = t;
     }
 }
