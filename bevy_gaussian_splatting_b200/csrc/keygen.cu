@@ -111,6 +111,9 @@ keygen_compact_kernel(const float4* __restrict__ pos, uint32_t n, FrameConsts fc
 // uncompacted keys (4 B/gaussian, L2-sized scratch) and publishes the CTA's visible count.  One grid
 // barrier.  Phase 2 sums the counts of all earlier CTAs in parallel (no chained look-back), re-reads
 // its own keys from L2 and writes the visible (key, index) pairs compacted in index order.
+// SMEM_KEYS: the CTA's keys stay in (dynamic) shared memory across the barrier instead of taking a round trip
+// through the global scratch (used whenever the CTA's range fits: <= 48 KB of keys).
+template <bool SMEM_KEYS>
 __global__ void __launch_bounds__(KG_THREADS)
 keygen_coop_kernel(const float4* __restrict__ pos, uint32_t n, FrameConsts fc, uint32_t* __restrict__ keys_tmp,
                    uint32_t* __restrict__ keys_out, uint32_t* __restrict__ ids_out, uint32_t* __restrict__ slots_out,
@@ -119,6 +122,7 @@ keygen_coop_kernel(const float4* __restrict__ pos, uint32_t n, FrameConsts fc, u
     __shared__ uint32_t s_off[KG_ITEMS * (KG_THREADS / 32)];
     __shared__ uint32_t s_red[KG_THREADS / 32];
     __shared__ uint32_t s_total;
+    extern __shared__ uint32_t s_keys_dyn[];
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const uint32_t G = gridDim.x, b = blockIdx.x;
     const uint32_t tiles_total = (n + KG_TILE - 1) / KG_TILE;
@@ -142,7 +146,8 @@ keygen_coop_kernel(const float4* __restrict__ pos, uint32_t n, FrameConsts fc, u
             const KeyOut k = key_of(fc, p[j].x, p[j].y, p[j].z);
             if (i < n) {
                 const uint32_t key = k.visible ? k.key : culled;
-                __stcg(keys_tmp + i, key);
+                if (SMEM_KEYS) s_keys_dyn[(tile - t0) * KG_TILE + j * KG_THREADS + t] = key;
+                else __stcg(keys_tmp + i, key);
                 mine += k.visible ? 1u : 0u;
                 if (!k.visible) { cmin_inv = max(cmin_inv, 0xFFFFFFFFu - i); cmax_p1 = max(cmax_p1, i + 1u); }
             }
@@ -179,7 +184,7 @@ keygen_coop_kernel(const float4* __restrict__ pos, uint32_t n, FrameConsts fc, u
 #pragma unroll
         for (int j = 0; j < KG_ITEMS; ++j) {
             const uint32_t i = tile_base + j * KG_THREADS + t;
-            key[j] = (i < n) ? __ldcg(keys_tmp + i) : culled;
+            key[j] = (i < n) ? (SMEM_KEYS ? s_keys_dyn[(tile - t0) * KG_TILE + j * KG_THREADS + t] : __ldcg(keys_tmp + i)) : culled;
         }
 #pragma unroll
         for (int j = 0; j < KG_ITEMS; ++j) {
@@ -236,9 +241,11 @@ void launch_keygen(const float4* pos, uint32_t n, const FrameConsts& fc, int sor
 }
 uint32_t keygen_num_tiles(uint32_t n) { return (n + KG_TILE - 1) / KG_TILE; }
 
+constexpr size_t KG_SMEM_MAX = 5 * KG_TILE * 4;   // 40 KB of keys per CTA (static + dynamic stays under the 48 KB default limit)
 int keygen_coop_blocks_per_sm() {
+    // sized for the shared-memory variant at its largest footprint, so either variant is co-resident
     int b = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, keygen_coop_kernel, KG_THREADS, 0) != cudaSuccess) return 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, keygen_coop_kernel<true>, KG_THREADS, KG_SMEM_MAX) != cudaSuccess) return 0;
     return b;
 }
 cudaError_t launch_keygen_coop(const float4* pos, uint32_t n, const FrameConsts& fc, uint32_t* keys_tmp, uint32_t* keys_out,
@@ -247,7 +254,11 @@ cudaError_t launch_keygen_coop(const float4* pos, uint32_t n, const FrameConsts&
     FrameConsts fcc = fc;
     void* args[] = {(void*)&pos, (void*)&n, (void*)&fcc, (void*)&keys_tmp, (void*)&keys_out, (void*)&ids_out,
                     (void*)&slots_out, (void*)&block_cnt, (void*)&ctr};
-    return cudaLaunchCooperativeKernel((const void*)keygen_coop_kernel, dim3(grid), dim3(KG_THREADS), args, 0, stream);
+    const uint32_t tiles_total = (n + KG_TILE - 1) / KG_TILE;
+    const size_t need = (size_t)((tiles_total + grid - 1) / grid) * KG_TILE * 4;   // keys of the largest CTA range
+    if (need <= KG_SMEM_MAX)
+        return cudaLaunchCooperativeKernel((const void*)keygen_coop_kernel<true>, dim3(grid), dim3(KG_THREADS), args, need, stream);
+    return cudaLaunchCooperativeKernel((const void*)keygen_coop_kernel<false>, dim3(grid), dim3(KG_THREADS), args, 0, stream);
 }
 
 void launch_culled_flags(const float4* pos, uint32_t n, const FrameConsts& fc, uint32_t* flags, cudaStream_t stream) {
