@@ -27,9 +27,10 @@ __device__ __forceinline__ float dot3(const float a[3], const float b[3]) {
     return (a[0] * b[0] + a[1] * b[1]) + a[2] * b[2];
 }
 // spherical_harmonics.wgsl:22-32; no clamp on either side
+// (colour is compared under tolerance, not bit-exactly: fast pow = ex2(2.4 * lg2 x), ~1e-6 relative)
 __device__ __forceinline__ float srgb_to_linear(float v) {
     if (v <= 0.04045f) return v / 12.92f;
-    return powf((v + 0.055f) / 1.055f, 2.4f);
+    return __powf((v + 0.055f) / 1.055f, 2.4f);
 }
 __device__ __forceinline__ uint32_t pack_bbox(float lo, float hi) {
     return (uint32_t)(int)lo | ((uint32_t)(int)hi << 16);
@@ -419,7 +420,7 @@ project_kernel(const float4* __restrict__ pos, const void* __restrict__ sh_p, co
                 for (int cc = 0; cc < 3; ++cc) {
                     float acc = 0.5f;
 #pragma unroll
-                    for (int kk = 0; kk < 16; ++kk) acc += (c_shc[kk] * sh[3 * kk + cc]) * basis[kk];
+                    for (int kk = 0; kk < 16; ++kk) acc = fmaf(c_shc[kk] * sh[3 * kk + cc], basis[kk], acc);   // colour: FMA is fine
                     rgb[cc] = acc;
                 }
                 if (fc.color_space == 0u) {
