@@ -179,6 +179,24 @@ def test_output_formats_agree(plugin):
         h.destroy()
 
 
+def test_f16_target_within_2_ulp_of_oracle(plugin, oracle):
+    """north_star: per-pixel RGBA within 2 ULP (f16) on the Rgba16Float target (render/mod.rs:917-921)."""
+    cloud = B.random_gaussians_3d_seeded(20000, 21)
+    view = B.headless_view(256, 144)
+    s = B.CloudSettings(global_scale=0.3)
+    h = plugin.add_cloud(cloud)
+    try:
+        got = plugin.render_view(h, s, view, fmt="rgba16f")
+    finally:
+        h.destroy()
+    want = oracle.render_tiles(cloud, view.to_abi(), plugin.cloud_uniform(s), s.to_abi())["image"].astype(np.float16)
+    # distance in f16 ULPs: reinterpret as sign-magnitude integers
+    def ordinal(a):
+        b = a.view(np.int16).astype(np.int32)
+        return np.where(b < 0, -(b & 0x7FFF), b)
+    assert np.abs(ordinal(got) - ordinal(want)).max() <= 2
+
+
 def test_not_ready_and_bad_arguments(plugin):
     import ctypes as C
 
