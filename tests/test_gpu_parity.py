@@ -324,3 +324,34 @@ def test_cpp_host_example_matches_python_host(plugin, tmp_path):
     cpp = np.fromfile(raw_f, np.uint8).reshape(h, w, 4)
     assert np.array_equal(cpp, img)
     assert img[..., :3].max() > 16
+
+
+def test_visibility_render_scene_on_gpu(plugin, oracle):
+    """tests/visibility_render.rs:113-141,199-274 through the CUDA path: 9 red gaussians, 128x128, camera (0,0,5),
+    global_opacity 2, adaptive radius off => >= 64 pixels with max(rgb) > 8 and a max channel > 32; a cloud whose
+    gaussians are all deselected under DrawMode::Selected (the test's "hidden" phase) leaves <= 8 such pixels."""
+    sh = np.zeros(48, np.float32); sh[0] = 6.0
+    pos = [[x, y, z, 1.0] for x in (-0.35, 0.35) for y in (-0.35, 0.35) for z in (-0.35, 0.35)]
+    pos.append(pos[0])
+    n = len(pos)
+    cloud = B.PlanarGaussian3d(np.array(pos, np.float32), np.tile(sh, (n, 1)), np.tile(np.array([1, 0, 0, 0], np.float32), (n, 1)),
+                               np.tile(np.array([0.22, 0.22, 0.22, 0.85], np.float32), (n, 1)))
+    view = B.perspective_view((0, 0, 5), (0, 0, 0), 128, 128)
+    s = B.CloudSettings(global_opacity=2.0, global_scale=1.0, opacity_adaptive_radius=False)
+    img32, _ = check_against_oracle(plugin, oracle, cloud, s, view)
+    h = plugin.add_cloud(cloud)
+    try:
+        img8 = plugin.render_view(h, s, view, fmt="rgba8_srgb")
+        assert int((img8[..., :3].max(axis=2) > 8).sum()) >= 64 and int(img8[..., :3].max()) > 32
+        assert img8[..., 0].max() >= img8[..., 1].max()
+    finally:
+        h.destroy()
+    hidden = B.PlanarGaussian3d(np.concatenate([cloud.position_visibility[:, :3], np.zeros((n, 1), np.float32)], 1),
+                                cloud.spherical_harmonic, cloud.rotation, cloud.scale_opacity)
+    h = plugin.add_cloud(hidden)
+    try:
+        img8 = plugin.render_view(h, B.CloudSettings(global_opacity=2.0, opacity_adaptive_radius=False, draw_mode=B.DrawMode.Selected),
+                                  view, fmt="rgba8_srgb")
+        assert int((img8[..., :3].max(axis=2) > 8).sum()) <= 8
+    finally:
+        h.destroy()
