@@ -19,7 +19,7 @@ uint32_t keygen_num_tiles(uint32_t n);
 int keygen_coop_blocks_per_sm();
 cudaError_t launch_keygen_coop(const float4* pos, uint32_t n, const FrameConsts& fc, uint32_t* keys_tmp, uint32_t* keys_out,
                                uint32_t* ids_out, uint32_t* slots_out, uint32_t* block_cnt, FrameCounters* ctr,
-                               uint32_t grid, cudaStream_t stream);
+                               uint32_t* hist, int hist_passes, uint32_t grid, cudaStream_t stream);
 void launch_culled_flags(const float4* pos, uint32_t n, const FrameConsts& fc, uint32_t* flags, cudaStream_t stream);
 // radix.cu
 uint32_t radix_num_tiles(uint32_t capacity);
@@ -499,10 +499,12 @@ bgs_status bgs_render(bgs_context* c, const bgs_cloud* cloud, const bgs_view* vi
         // compact mode: keys[0][slot], slot_ids[slot] = gaussian index, vals[0][slot] = slot (sort payload)
         // SORT_ALL    : keys[0][i], vals[0][i] = i (payload is the gaussian index itself)
         const bool by_slot = !sort_all;
+        bool hist_fused = false;   // the cooperative key-gen also produces the depth sort's digit histograms
         if (!sort_all && c->coop) {
             // cooperative: uncompacted keys go through keys[1] (scratch until the first sort pass overwrites it)
             CU(c, launch_keygen_coop(cloud->pos, n, fc, c->keys[1], c->keys[0], c->slot_ids, c->vals[0], c->status_keygen,
-                                     c->ctr, c->kg_grid, q));
+                                     c->ctr, c->hist, depth_passes, c->kg_grid, q));
+            hist_fused = true;
         } else {
             launch_keygen(cloud->pos, n, fc, sort_all ? 1 : 0, c->keys[0], sort_all ? c->vals[0] : c->slot_ids,
                           sort_all ? c->slot_ids : c->vals[0], c->status_keygen, c->ctr, q);
@@ -525,8 +527,10 @@ bgs_status bgs_render(bgs_context* c, const bgs_cloud* cloud, const bgs_view* vi
             CU(c, cudaEventRecord(c->ev_join, c->stream2));
         }
         // ---- stage 2: depth radix sort (P = depth_bits / 8 onesweep passes)
-        launch_radix_hist(c->keys[0], &c->ctr->n_sort, n, depth_passes, c->hist, c->sm_count, q);
-        ++launches;
+        if (!hist_fused) {
+            launch_radix_hist(c->keys[0], &c->ctr->n_sort, n, depth_passes, c->hist, c->sm_count, q);
+            ++launches;
+        }
         int cur = 0;
         const size_t depth_status_stride = (size_t)radix_num_tiles(c->arena_n) * 256;
         for (int p = 0; p < depth_passes; ++p) {

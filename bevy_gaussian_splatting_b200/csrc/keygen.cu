@@ -117,8 +117,10 @@ template <bool SMEM_KEYS>
 __global__ void __launch_bounds__(KG_THREADS)
 keygen_coop_kernel(const float4* __restrict__ pos, uint32_t n, FrameConsts fc, uint32_t* __restrict__ keys_tmp,
                    uint32_t* __restrict__ keys_out, uint32_t* __restrict__ ids_out, uint32_t* __restrict__ slots_out,
-                   uint32_t* __restrict__ block_cnt, FrameCounters* __restrict__ ctr) {
+                   uint32_t* __restrict__ block_cnt, FrameCounters* __restrict__ ctr, uint32_t* __restrict__ hist,
+                   int hist_passes) {
     __shared__ uint32_t s_cnt[KG_ITEMS * (KG_THREADS / 32)];
+    __shared__ uint32_t s_hist[4 * 256];   // digit histograms of the visible keys (the depth sort's pre-pass, fused)
     __shared__ uint32_t s_off[KG_ITEMS * (KG_THREADS / 32)];
     __shared__ uint32_t s_red[KG_THREADS / 32];
     __shared__ uint32_t s_total;
@@ -175,6 +177,7 @@ keygen_coop_kernel(const float4* __restrict__ pos, uint32_t n, FrameConsts fc, u
     grid_barrier(&ctr->barrier[0], G);
 
     // ---- phase 2: exclusive prefix over CTAs, then ordered compaction of this CTA's range
+    for (int i = t; i < hist_passes * 256; i += KG_THREADS) s_hist[i] = 0u;
     uint32_t run = block_sum_prefix<KG_THREADS>(block_cnt, b, s_red);
     if (b == G - 1 && t == 0) { ctr->n_vis = run + s_total; ctr->n_sort = run + s_total; }
     for (uint32_t tile = t0; tile < t1; ++tile) {
@@ -216,10 +219,15 @@ keygen_coop_kernel(const float4* __restrict__ pos, uint32_t n, FrameConsts fc, u
                 keys_out[dst] = key[j];
                 ids_out[dst] = tile_base + j * KG_THREADS + t;   // compact slot -> gaussian index
                 slots_out[dst] = dst;                            // the sort's payload: the compact slot
+                for (int p = 0; p < hist_passes; ++p) atomicAdd(&s_hist[p * 256 + ((key[j] >> (8 * p)) & 255u)], 1u);
             }
         }
         run += s_total;
         __syncthreads();
+    }
+    for (int i = t; i < hist_passes * 256; i += KG_THREADS) {
+        const uint32_t c = s_hist[i];
+        if (c) atomicAdd(&hist[i], c);
     }
 }
 
@@ -250,10 +258,10 @@ int keygen_coop_blocks_per_sm() {
 }
 cudaError_t launch_keygen_coop(const float4* pos, uint32_t n, const FrameConsts& fc, uint32_t* keys_tmp, uint32_t* keys_out,
                                uint32_t* ids_out, uint32_t* slots_out, uint32_t* block_cnt, FrameCounters* ctr,
-                               uint32_t grid, cudaStream_t stream) {
+                               uint32_t* hist, int hist_passes, uint32_t grid, cudaStream_t stream) {
     FrameConsts fcc = fc;
     void* args[] = {(void*)&pos, (void*)&n, (void*)&fcc, (void*)&keys_tmp, (void*)&keys_out, (void*)&ids_out,
-                    (void*)&slots_out, (void*)&block_cnt, (void*)&ctr};
+                    (void*)&slots_out, (void*)&block_cnt, (void*)&ctr, (void*)&hist, (void*)&hist_passes};
     const uint32_t tiles_total = (n + KG_TILE - 1) / KG_TILE;
     const size_t need = (size_t)((tiles_total + grid - 1) / grid) * KG_TILE * 4;   // keys of the largest CTA range
     if (need <= KG_SMEM_MAX)
