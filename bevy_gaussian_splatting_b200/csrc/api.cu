@@ -474,9 +474,12 @@ bgs_status bgs_render(bgs_context* c, const bgs_cloud* cloud, const bgs_view* vi
         if (s != BGS_OK) return s;
         target = c->frame;
     }
-    const bool async_host = (st->flags & BGS_FLAG_ASYNC) && out_rgba && !out_is_device_ptr;
+    // async frames rendered into the library's own buffers alternate two device frames, so whatever consumes
+    // frame k off the render stream (the D2H copy, the NCCL gather: both on the copy/comm stream) overlaps frame k+1
+    const bool async_own = (st->flags & BGS_FLAG_ASYNC) && !(out_rgba && out_is_device_ptr);
+    const bool async_host = async_own && out_rgba;
     int fslot = 0;
-    if (async_host) {   // alternate device frames; the D2H copy runs on the copy stream
+    if (async_own) {
         fslot = c->frame_toggle; c->frame_toggle ^= 1;
         target = fslot ? c->frame_alt : c->frame;
     }
@@ -585,7 +588,7 @@ bgs_status bgs_render(bgs_context* c, const bgs_cloud* cloud, const bgs_view* vi
         ++launches;
         CU(c, cudaEventRecord(c->ev[4], q));
         // ---- stage 5: per-tile front-to-back blend
-        if (async_host && c->copy_pending[fslot]) CU(c, cudaStreamWaitEvent(q, c->ev_copied[fslot], 0));   // target free again
+        if (async_own && c->copy_pending[fslot]) CU(c, cudaStreamWaitEvent(q, c->ev_copied[fslot], 0));   // target free again
         // kernel variant picked from the previous frame's mean footprint (pairs per visible splat); results are identical
         const bool large_fp = c->n_vis_hint > 0 && (uint64_t)c->n_pairs_hint >= 8ull * c->n_vis_hint;
         launch_raster(raster_mode, large_fp, c->recs, c->extra, c->pvals[pcur], c->ranges, W, H, tiles_x, tiles_y, target, out_format, q);
@@ -593,8 +596,8 @@ bgs_status bgs_render(bgs_context* c, const bgs_cloud* cloud, const bgs_view* vi
         CU(c, cudaEventRecord(c->ev[5], q));
         CU(c, cudaEventRecord(c->ev_done, q));
         CU(c, cudaMemcpyAsync(c->h_ctr, c->ctr, sizeof(FrameCounters), cudaMemcpyDeviceToHost, q));
+        if (async_own) CU(c, cudaEventRecord(c->ev_raster[fslot], q));
         if (async_host) {
-            CU(c, cudaEventRecord(c->ev_raster[fslot], q));
             CU(c, cudaStreamWaitEvent(c->stream_copy, c->ev_raster[fslot], 0));
             CU(c, cudaMemcpyAsync(out_rgba, target, frame_bytes, cudaMemcpyDeviceToHost, c->stream_copy));
             CU(c, cudaEventRecord(c->ev_copied[fslot], c->stream_copy));
@@ -738,6 +741,27 @@ bgs_status bgs_stage_times_us(bgs_context* c, float out[6]) {
     }
     for (int i = 0; i < 6; ++i) out[i] = c->stage_us[i];
     return BGS_OK;
+}
+
+// gather.cc: where to run the gather of `local_frame`.  A library-owned frame of an async render is consumed on the
+// copy/comm stream (after its raster), so the next frame on the render stream overlaps the transfer; anything else
+// runs on the render stream.  `*slot` >= 0 -> call bgs_internal_gather_end_ afterwards.
+cudaStream_t bgs_internal_gather_begin_(bgs_context* c, const void* local_frame, int* slot) {
+    *slot = -1;
+    if (!c) return nullptr;
+    for (int k = 0; k < 2; ++k) {
+        const void* f = k ? c->frame_alt : c->frame;
+        if (f && f == local_frame && c->async_pending) {
+            if (cudaStreamWaitEvent(c->stream_copy, c->ev_raster[k], 0) != cudaSuccess) return c->stream;
+            *slot = k;
+            return c->stream_copy;
+        }
+    }
+    return c->stream;
+}
+void bgs_internal_gather_end_(bgs_context* c, int slot) {
+    if (!c || slot < 0) return;
+    if (cudaEventRecord(c->ev_copied[slot], c->stream_copy) == cudaSuccess) c->copy_pending[slot] = true;
 }
 
 // undocumented debug aid (not in bgs.h): copy the bin_emit_coop per-CTA timeline (grid x 8 u64 ns stamps)

@@ -13,6 +13,9 @@
 
 #include "../../include/bgs.h"
 
+extern "C" cudaStream_t bgs_internal_gather_begin_(bgs_context* ctx, const void* local_frame, int* slot);   // api.cu
+extern "C" void bgs_internal_gather_end_(bgs_context* ctx, int slot);
+
 namespace {
 
 struct NcclApi {
@@ -97,7 +100,8 @@ bgs_status bgs_gather_frames(bgs_context* ctx, void* nccl_comm, int root, const 
     if (a.CommCount(comm, &nranks) != ncclSuccess || a.CommUserRank(comm, &rank) != ncclSuccess) return BGS_ENCCL;
     if (root < 0 || root >= nranks) return BGS_EINVAL;
     if (rank == root && !all_frames) return BGS_EINVAL;
-    cudaStream_t q = (cudaStream_t)bgs_context_stream(ctx);
+    int slot = -1;
+    cudaStream_t q = bgs_internal_gather_begin_(ctx, local_frame, &slot);   // comm stream for async library frames
     ncclResult_t r = a.GroupStart();
     if (r != ncclSuccess) return BGS_ENCCL;
     if (rank == root) {
@@ -113,6 +117,7 @@ bgs_status bgs_gather_frames(bgs_context* ctx, void* nccl_comm, int root, const 
         r = a.Send(local_frame, bytes, ncclUint8, root, comm, q);
     }
     const ncclResult_t e = a.GroupEnd();
+    bgs_internal_gather_end_(ctx, slot);
     if (r != ncclSuccess || e != ncclSuccess) return BGS_ENCCL;
     return BGS_OK;
 }

@@ -140,7 +140,9 @@ const void* bgs_frame_device_ptr(bgs_context* ctx);
 uint32_t bgs_last_launch_count(const bgs_context* ctx);
 
 /* Multi-GPU (one view per GPU, replicated cloud): gather every rank's frame to `root`.
- * nccl_comm is an ncclComm_t.  Runs on the context stream. */
+ * nccl_comm is an ncclComm_t.  Enqueued on the context's streams (a frame produced by an async
+ * bgs_render is gathered on the copy/comm stream so the next frame overlaps the transfer);
+ * bgs_sync() completes it. */
 bgs_status bgs_nccl_unique_id(void* out_id128 /* 128 bytes */);
 bgs_status bgs_nccl_comm_init(bgs_context* ctx, int nranks, int rank, const void* id128, void** out_comm);
 void bgs_nccl_comm_destroy(void* nccl_comm);
