@@ -1,6 +1,7 @@
 // gather.cc -- multi-GPU frame gather: one view per GPU, replicated cloud, and
 // ONE collective per frame: every rank's finished frame is sent to `root` over NCCL (NVLink 5 /
-// NVSwitch), on the render stream.  The reference has no multi-GPU path at all.
+// NVSwitch); frames of async renders are gathered on the copy/comm stream so the next frame overlaps the
+// transfer.  The reference has no multi-GPU path at all.
 //
 // NCCL is resolved lazily with dlopen so single-GPU users of libbgs.so never need it, and so a
 // host process that already loaded an NCCL (e.g. the torch-bundled one) shares that instance.
