@@ -18,6 +18,8 @@ STATUS_NAMES = ["BGS_OK", "BGS_NOT_READY", "BGS_EINVAL", "BGS_ECUDA", "BGS_ENOME
 BGS_FORMAT_RGBA8_SRGB, BGS_FORMAT_RGBA16F, BGS_FORMAT_RGBA32F = 0, 1, 2
 BGS_FLAG_SORT_ALL = 1
 BGS_FLAG_ASYNC = 2
+BGS_FLAG_NO_CHUNKS = 4
+BGS_FLAG_CHUNKS = 8
 
 
 class bgs_view(C.Structure):
@@ -62,6 +64,8 @@ class bgs_frame_stats(C.Structure):
         ("tiles_y", C.c_uint32),
         ("width", C.c_uint32),
         ("height", C.c_uint32),
+        ("rounds", C.c_uint32),
+        ("tiles_saturated", C.c_uint32),
     ]
 
 

@@ -37,21 +37,26 @@ void launch_project(bool f16, bool blocked, const float4* pos, const void* sh, c
                     const uint32_t* index_list, int by_slot, const FrameCounters* ctr, const FrameConsts& fc,
                     SplatRec* recs, float4* extra, uint32_t n_hint, cudaStream_t stream);
 // bin.cu
-void launch_bin_emit(const SplatRec* recs, const uint32_t* perm, FrameCounters* ctr, uint32_t* status, int tiles_x,
+void launch_bin_emit(const SplatRec* recs, const uint32_t* perm, FrameCounters* ctr, ChunkCounters* cc, uint32_t* status, int tiles_x,
                      uint32_t capacity, uint32_t* pair_keys, uint32_t* pair_vals, uint32_t n_upper, int sm_count,
                      cudaStream_t stream);
 uint32_t bin_num_tiles(uint32_t n);
 int bin_coop_blocks_per_sm();
-cudaError_t launch_bin_emit_coop(const SplatRec* recs, const uint32_t* perm, FrameCounters* ctr, uint32_t* block_cnt,
+cudaError_t launch_bin_emit_coop(const SplatRec* recs, const uint32_t* perm, FrameCounters* ctr, ChunkCounters* cc,
+                                 uint32_t frac_a, uint32_t frac_b, uint32_t num_tiles_total, uint32_t* block_cnt,
                                  int tiles_x, uint32_t capacity, uint32_t* pair_keys, uint32_t* pair_vals,
                                  uint32_t* q_rank, uint32_t* q_off, uint32_t q_cap, unsigned long long* timeline,
                                  uint32_t grid, cudaStream_t stream);
-void launch_tile_ranges(const uint32_t* sorted_tile_ids, const FrameCounters* ctr, uint2* ranges, uint32_t capacity,
+void launch_tile_ranges(const uint32_t* sorted_tile_ids, const uint32_t* n_ptr, uint2* ranges, uint32_t capacity,
                         int sm_count, cudaStream_t stream);
 // raster.cu
 void launch_raster(int mode, bool large_footprints, const SplatRec* recs, const float4* extra, const uint32_t* tile_entries,
                    const uint2* ranges, int W, int H, int tiles_x, int tiles_y, void* out, uint32_t format,
                    cudaStream_t stream);
+void launch_raster_round(const SplatRec* recs, const uint32_t* tile_entries, const uint2* ranges, int W, int H, int tiles_x,
+                         int tiles_y, void* out, uint32_t format, float4* state, unsigned char* tile_done,
+                         uint32_t* tiles_done, int first, int last, cudaStream_t stream);
+void launch_status_clear(uint32_t* status, size_t stride, int passes, const uint32_t* n_ptr, int sm_count, cudaStream_t stream);
 }  // namespace bgs
 
 using namespace bgs;
@@ -78,7 +83,18 @@ struct bgs_context {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_p0 = nullptr, ev_p1 = nullptr;
     unsigned long long* timeline = nullptr;   // BGS_TIMELINE=1: per-CTA phase stamps of bin_emit_coop (debug)
     uint32_t n_vis_hint = 0;          // last frame's visible count (sizes the projection grid)
-    uint32_t n_pairs_hint = 0;        // last frame's pair count (picks the pair sort's tile size)
+    uint32_t n_pairs_hint = 0;        // last frame's pair count (picks the pair sort's tile size); on chunked
+                                      // frames an ESTIMATE of what one round would have emitted
+    // chunked frames (saturation-aware binning): the visible set is binned / sorted / blended in front-to-back
+    // rank rounds [frac[r], frac[r+1]) / 65536; once every tile has saturated the remaining rounds emit nothing
+    uint32_t chunk_frac[MAX_CHUNKS + 1] = {0, 1024, 2048, 4096, 8192, 16384, 65536, 65536, 65536};
+    int chunk_count = 6;
+    uint32_t chunk_pairs_hint[MAX_CHUNKS] = {};   // last chunked frame's pairs per round (pair sort tile size)
+    bool chunk_hint_valid = false;
+    float4* state = nullptr;          // per-pixel blend state between rounds (tile-major), tiles * 256 * 16 B
+    uint32_t cap_state_tiles = 0;
+    unsigned char* tile_done = nullptr;   // in the arena (cleared per frame)
+    int pend_chunks = 1, last_chunks = 1;
     char err[512] = {0};
 
     // scratch sized by the cloud (grow-only)
@@ -104,7 +120,7 @@ struct bgs_context {
     int pend_tiles_x = 0, pend_tiles_y = 0, pend_W = 0, pend_H = 0; const void* pend_target = nullptr;
     cudaEvent_t ev_done = nullptr, ev_clean = nullptr;
     FrameCounters* ctr = nullptr;
-    uint32_t* hist = nullptr;          // [8][256]: depth passes 0..3, pair passes 4..7
+    uint32_t* hist = nullptr;          // [8 + 4 * MAX_CHUNKS][256]: depth passes 0..3, pair passes 4..7 (round 0), 8 + 4r.. (round r)
     uint32_t* status_keygen = nullptr;
     uint32_t* status_bin = nullptr;
     uint2* ranges = nullptr;
@@ -156,6 +172,8 @@ bgs_status fail(bgs_context* ctx, bgs_status st, const char* fmt, ...) {
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+constexpr uint32_t CHUNK_MAX_TILES = 65536;
+
 int pair_passes(uint32_t num_tiles) {
     int bits = 1;
     while ((1u << bits) < num_tiles) ++bits;
@@ -205,10 +223,13 @@ bgs_status ensure_arena(bgs_context* c, uint32_t n, uint32_t pairs, uint32_t til
     cudaFree(c->arena); c->arena = nullptr;
     size_t off = 0;
     const size_t o_ctr = off; off = align_up(off + sizeof(FrameCounters), 256);
-    const size_t o_hist = off; off = align_up(off + 8 * 256 * 4, 256);
+    const size_t o_hist = off; off = align_up(off + (8 + 4 * MAX_CHUNKS) * 256 * 4, 256);
     const size_t o_skg = off; off = align_up(off + ((size_t)keygen_num_tiles(n) + 4096) * 4, 256);
     const size_t o_sbin = off; off = align_up(off + ((size_t)bin_num_tiles(n) + 4096) * 4, 256);
-    const size_t o_rng = off; off = align_up(off + (size_t)tiles * 8, 256);
+    // chunked frames (only for <= CHUNK_MAX_TILES tiles) use one ranges array per round + a done byte per tile
+    const size_t range_sets = tiles <= CHUNK_MAX_TILES ? MAX_CHUNKS : 1;
+    const size_t o_rng = off; off = align_up(off + (size_t)tiles * 8 * range_sets, 256);
+    const size_t o_done = off; off = align_up(off + (tiles <= CHUNK_MAX_TILES ? tiles : 0), 256);
     const size_t o_sd = off; off = align_up(off + (size_t)4 * radix_num_tiles(n) * 256 * 4, 256);
     const size_t o_sp = off; off = align_up(off + (size_t)4 * radix_num_tiles(pairs) * 256 * 4, 256);
     CU(c, cudaMalloc(&c->arena, off));
@@ -220,6 +241,7 @@ bgs_status ensure_arena(bgs_context* c, uint32_t n, uint32_t pairs, uint32_t til
     c->status_keygen = reinterpret_cast<uint32_t*>(c->arena + o_skg);
     c->status_bin = reinterpret_cast<uint32_t*>(c->arena + o_sbin);
     c->ranges = reinterpret_cast<uint2*>(c->arena + o_rng);
+    c->tile_done = c->arena + o_done;
     c->status_depth = reinterpret_cast<uint32_t*>(c->arena + o_sd);
     c->status_pairs = reinterpret_cast<uint32_t*>(c->arena + o_sp);
     c->arena_n = n; c->arena_pairs = pairs; c->arena_tiles = tiles;
@@ -277,6 +299,18 @@ bgs_status bgs_context_create(int cuda_device, bgs_context** out) {
         c->bin_grid = (uint32_t)(c->sm_count * (bb > lim ? lim : bb));
         if (c->kg_grid == 0 || c->bin_grid == 0 || c->kg_grid > 4096 || c->bin_grid > 4096) c->coop = 0;
     }
+    if (const char* fr = getenv("BGS_CHUNK_FRACS")) {
+        // tuning knob: cumulative round boundaries out of 65536, e.g. "256,2048,16384" = 4 rounds
+        int k = 0;
+        uint32_t prev = 0;
+        while (*fr && k < MAX_CHUNKS - 1) {
+            const uint32_t v = (uint32_t)strtoul(fr, const_cast<char**>(&fr), 10);
+            if (v > prev && v < 65536u) { c->chunk_frac[++k] = v; prev = v; }
+            while (*fr == ',' || *fr == ' ') ++fr;
+        }
+        for (int j = k + 1; j <= MAX_CHUNKS; ++j) c->chunk_frac[j] = 65536u;
+        c->chunk_count = k + 1;
+    }
     if (e != cudaSuccess) {
         // no CUDA device / driver: the product has no CPU path
         fprintf(stderr, "libbgs: CUDA initialisation failed on device %d: %s\n", cuda_device, cudaGetErrorString(e));
@@ -298,6 +332,7 @@ void bgs_context_destroy(bgs_context* c) {
     for (int i = 0; i < 2; ++i) {
         cudaFree(c->keys[i]); cudaFree(c->vals[i]); cudaFree(c->pkeys[i]); cudaFree(c->pvals[i]);
     }
+    cudaFree(c->state);
     cudaFree(c->recs); cudaFree(c->extra); cudaFree(c->slot_ids); cudaFree(c->arena); cudaFree(c->frame);
     if (c->h_ctr) cudaFreeHost(c->h_ctr);
     for (int i = 0; i < 6; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
@@ -371,11 +406,19 @@ void bgs_cloud_destroy(bgs_cloud* cl) {
 
 // Bookkeeping once a frame's counters are back on the host (sync render, or bgs_sync after async ones).
 static bgs_status finish_frame(bgs_context* c) {
-    if (c->h_ctr->n_pairs_needed > c->cap_pairs) {
-        // the pair list did not fit: grow (x1.25 head-room); the caller redoes the frame
-        uint64_t want = (uint64_t)c->h_ctr->n_pairs_needed + c->h_ctr->n_pairs_needed / 4 + 1024;
+    const int chunks = c->pend_chunks;
+    uint32_t needed = 0;
+    uint64_t emitted = 0;
+    for (int r = 0; r < chunks; ++r) {
+        const ChunkCounters& cc = c->h_ctr->chunk[r];
+        needed = cc.n_pairs_needed > needed ? cc.n_pairs_needed : needed;
+        emitted += cc.n_pairs;
+    }
+    if (needed > c->cap_pairs) {
+        // the pair list (of one round) did not fit: grow (x1.25 head-room); the caller redoes the frame
+        uint64_t want = (uint64_t)needed + needed / 4 + 1024;
         if (want >= (1ull << 30)) want = (1ull << 30) - 1;
-        if (c->h_ctr->n_pairs_needed >= LB_VMASK || want <= c->cap_pairs)
+        if (needed >= LB_VMASK || want <= c->cap_pairs)
             return fail(c, BGS_ENOMEM, "render: frame needs >= 2^30 (splat, tile) pairs");
         bgs_status s = ensure_pair_scratch(c, (uint32_t)want);
         if (s != BGS_OK) return s;
@@ -383,11 +426,23 @@ static bgs_status finish_frame(bgs_context* c) {
     }
     const uint32_t n = c->pend_cloud ? c->pend_cloud->n : 0;
     c->stage_valid = false;
-    c->stats.n = n; c->stats.n_visible = c->h_ctr->n_vis; c->stats.n_pairs = c->h_ctr->n_pairs;
+    c->stats.n = n; c->stats.n_visible = c->h_ctr->n_vis; c->stats.n_pairs = emitted;
+    c->stats.rounds = (uint32_t)chunks; c->stats.tiles_saturated = c->h_ctr->tiles_done;
     c->stats.tiles_x = (uint32_t)c->pend_tiles_x; c->stats.tiles_y = (uint32_t)c->pend_tiles_y;
     c->stats.width = (uint32_t)c->pend_W; c->stats.height = (uint32_t)c->pend_H;
     c->have_frame = true; c->last_cloud = c->pend_cloud; c->last_fc = c->pend_fc; c->last_sort_all = c->pend_sort_all;
-    c->last_by_slot = c->pend_by_slot; c->n_vis_hint = c->h_ctr->n_vis; c->n_pairs_hint = c->h_ctr->n_pairs;
+    c->last_by_slot = c->pend_by_slot; c->n_vis_hint = c->h_ctr->n_vis; c->last_chunks = chunks;
+    if (chunks > 1) {
+        // round 0 is always emitted in full: scale it up to the whole visible set (the nearest splats have the
+        // largest footprints, so this errs towards staying chunked)
+        const uint64_t est = (uint64_t)c->h_ctr->chunk[0].n_pairs_needed * 65536ull / c->chunk_frac[1];
+        c->n_pairs_hint = est > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)est;
+        for (int r = 0; r < chunks; ++r) c->chunk_pairs_hint[r] = c->h_ctr->chunk[r].n_pairs;
+        c->chunk_hint_valid = true;
+    } else {
+        c->n_pairs_hint = c->h_ctr->chunk[0].n_pairs;
+        c->chunk_hint_valid = false;
+    }
     c->last_frame = c->pend_target;
     c->err[0] = 0;
     return BGS_OK;
@@ -484,6 +539,19 @@ bgs_status bgs_render(bgs_context* c, const bgs_cloud* cloud, const bgs_view* vi
         target = fslot ? c->frame_alt : c->frame;
     }
 
+    // saturation-aware chunking: frames whose splats cover many tiles each (last frame: >= 64 pairs per visible splat
+    // and >= 2^24 pairs) run binning / tile sort / blend in front-to-back rank rounds; the rounds after every tile
+    // has saturated emit nothing.  Quad-uv records + cooperative binning only; BGS_FLAG_CHUNKS / _NO_CHUNKS force it.
+    bool chunked = raster_mode == 0 && c->coop && num_tiles <= CHUNK_MAX_TILES && !(st->flags & BGS_FLAG_NO_CHUNKS) && c->chunk_count > 1;
+    if (chunked && !(st->flags & BGS_FLAG_CHUNKS))
+        chunked = c->n_vis_hint > 0 && c->n_pairs_hint >= (1u << 24) && (uint64_t)c->n_pairs_hint >= 64ull * c->n_vis_hint;
+    const int rounds = chunked ? c->chunk_count : 1;
+    if (chunked && c->cap_state_tiles < num_tiles) {
+        cudaFree(c->state); c->state = nullptr; c->cap_state_tiles = 0;
+        CU(c, cudaMalloc(&c->state, (size_t)num_tiles * 256 * sizeof(float4)));
+        c->cap_state_tiles = num_tiles;
+    }
+
     for (int attempt = 0; attempt < 4; ++attempt) {
         s = ensure_arena(c, n, c->cap_pairs, num_tiles);
         if (s != BGS_OK) return s;
@@ -561,38 +629,60 @@ bgs_status bgs_render(bgs_context* c, const bgs_cloud* cloud, const bgs_view* vi
             CU(c, cudaEventRecord(c->ev_p1, q));
         }
         CU(c, cudaEventRecord(c->ev[3], q));
-        // ---- stage 4: tile binning -> stable tile-id sort -> ranges
-        if (c->coop) {
-            // the depth sort's spare ping-pong buffers (N words each) hold the large-footprint queue
-            CU(c, launch_bin_emit_coop(c->recs, by_slot ? c->vals[cur] : nullptr, c->ctr, c->status_bin, tiles_x,
-                                       c->cap_pairs, c->pkeys[0], c->pvals[0], c->keys[cur ^ 1], c->vals[cur ^ 1],
-                                       c->cap_n, c->timeline, c->bin_grid, q));
-        } else {
-            launch_bin_emit(c->recs, by_slot ? c->vals[cur] : nullptr, c->ctr, c->status_bin, tiles_x, c->cap_pairs,
-                            c->pkeys[0], c->pvals[0], n, c->sm_count, q);
-        }
-        ++launches;
-        launch_radix_hist(c->pkeys[0], &c->ctr->n_pairs, c->cap_pairs, tile_passes, c->hist + 4 * 256, c->sm_count, q);
-        ++launches;
-        int pcur = 0;
-        const size_t pair_status_stride = (size_t)radix_num_tiles(c->arena_pairs) * 256;
-        for (int p = 0; p < tile_passes; ++p) {
-            launch_onesweep(c->pkeys[pcur], c->pvals[pcur], c->pkeys[pcur ^ 1], c->pvals[pcur ^ 1], &c->ctr->n_pairs,
-                            c->cap_pairs, c->n_pairs_hint ? c->n_pairs_hint : c->cap_pairs, c->hist + (4 + p) * 256, c->status_pairs + p * pair_status_stride,
-                            &c->ctr->tile_ctr[6 + p], 8 * p, c->sm_count, q);
-            ++launches;
-            pcur ^= 1;
-        }
-        c->pair_result = pcur;
-        launch_tile_ranges(c->pkeys[pcur], c->ctr, c->ranges, c->cap_pairs, c->sm_count, q);
-        ++launches;
-        CU(c, cudaEventRecord(c->ev[4], q));
-        // ---- stage 5: per-tile front-to-back blend
-        if (async_own && c->copy_pending[fslot]) CU(c, cudaStreamWaitEvent(q, c->ev_copied[fslot], 0));   // target free again
+        // ---- stage 4: tile binning -> stable tile-id sort -> ranges; stage 5: per-tile front-to-back blend.
+        //      One round normally; `rounds` front-to-back rank rounds on chunked frames, each resuming the pixels'
+        //      blend state, the last one writing the frame (identical pixels either way).
         // kernel variant picked from the previous frame's mean footprint (pairs per visible splat); results are identical
         const bool large_fp = c->n_vis_hint > 0 && (uint64_t)c->n_pairs_hint >= 8ull * c->n_vis_hint;
-        launch_raster(raster_mode, large_fp, c->recs, c->extra, c->pvals[pcur], c->ranges, W, H, tiles_x, tiles_y, target, out_format, q);
-        ++launches;
+        const size_t pair_status_stride = (size_t)radix_num_tiles(c->arena_pairs) * 256;
+        int pcur = 0;
+        for (int r = 0; r < rounds; ++r) {
+            ChunkCounters* cc = &c->ctr->chunk[r];
+            const uint32_t fa = rounds > 1 ? c->chunk_frac[r] : 0u, fb = rounds > 1 ? c->chunk_frac[r + 1] : 65536u;
+            uint2* rng = c->ranges + (size_t)r * num_tiles;
+            uint32_t* hist_r = c->hist + (size_t)(4 + 4 * r) * 256;
+            if (c->coop) {
+                // the depth sort's spare ping-pong buffers (N words each) hold the large-footprint queue
+                CU(c, launch_bin_emit_coop(c->recs, by_slot ? c->vals[cur] : nullptr, c->ctr, cc, fa, fb, num_tiles,
+                                           c->status_bin, tiles_x, c->cap_pairs, c->pkeys[0], c->pvals[0], c->keys[cur ^ 1],
+                                           c->vals[cur ^ 1], c->cap_n, c->timeline, c->bin_grid, q));
+            } else {
+                launch_bin_emit(c->recs, by_slot ? c->vals[cur] : nullptr, c->ctr, cc, c->status_bin, tiles_x, c->cap_pairs,
+                                c->pkeys[0], c->pvals[0], n, c->sm_count, q);
+            }
+            ++launches;
+            launch_radix_hist(c->pkeys[0], &cc->n_pairs, c->cap_pairs, tile_passes, hist_r, c->sm_count, q);
+            ++launches;
+            uint32_t p_hint = c->n_pairs_hint ? c->n_pairs_hint : c->cap_pairs;
+            if (rounds > 1) p_hint = c->chunk_hint_valid ? c->chunk_pairs_hint[r] : c->cap_pairs;
+            if (p_hint > c->cap_pairs) p_hint = c->cap_pairs;
+            pcur = 0;
+            for (int p = 0; p < tile_passes; ++p) {
+                launch_onesweep(c->pkeys[pcur], c->pvals[pcur], c->pkeys[pcur ^ 1], c->pvals[pcur ^ 1], &cc->n_pairs,
+                                c->cap_pairs, p_hint, hist_r + p * 256, c->status_pairs + p * pair_status_stride,
+                                &cc->tile_ctr_sort[p], 8 * p, c->sm_count, q);
+                ++launches;
+                pcur ^= 1;
+            }
+            if (r + 1 < rounds) {   // the next round's sort reuses the look-back status rows
+                launch_status_clear(c->status_pairs, pair_status_stride, tile_passes, &cc->n_pairs, c->sm_count, q);
+                ++launches;
+            }
+            launch_tile_ranges(c->pkeys[pcur], &cc->n_pairs, rng, c->cap_pairs, c->sm_count, q);
+            ++launches;
+            if (r + 1 == rounds) {
+                // (chunked frames: the earlier rounds' blends are accounted to stage 4)
+                CU(c, cudaEventRecord(c->ev[4], q));
+                if (async_own && c->copy_pending[fslot]) CU(c, cudaStreamWaitEvent(q, c->ev_copied[fslot], 0));   // target free again
+            }
+            if (rounds == 1)
+                launch_raster(raster_mode, large_fp, c->recs, c->extra, c->pvals[pcur], rng, W, H, tiles_x, tiles_y, target, out_format, q);
+            else
+                launch_raster_round(c->recs, c->pvals[pcur], rng, W, H, tiles_x, tiles_y, target, out_format, c->state,
+                                    c->tile_done, &c->ctr->tiles_done, r == 0, r + 1 == rounds, q);
+            ++launches;
+        }
+        c->pair_result = pcur;
         CU(c, cudaEventRecord(c->ev[5], q));
         CU(c, cudaEventRecord(c->ev_done, q));
         CU(c, cudaMemcpyAsync(c->h_ctr, c->ctr, sizeof(FrameCounters), cudaMemcpyDeviceToHost, q));
@@ -606,6 +696,7 @@ bgs_status bgs_render(bgs_context* c, const bgs_cloud* cloud, const bgs_view* vi
             CU(c, cudaMemcpyAsync(out_rgba, target, frame_bytes, cudaMemcpyDeviceToHost, q));
         }
         c->pend_cloud = cloud; c->pend_fc = fc; c->pend_sort_all = sort_all; c->pend_by_slot = by_slot;
+        c->pend_chunks = rounds;
         c->pend_tiles_x = tiles_x; c->pend_tiles_y = tiles_y; c->pend_W = W; c->pend_H = H; c->pend_target = target;
         // pre-clean the status rows for the next frame, off the critical path
         CU(c, cudaStreamWaitEvent(c->stream2, c->ev_done, 0));
@@ -668,6 +759,7 @@ bgs_status bgs_debug_sorted_entries(bgs_context* c, uint32_t* out) {
 bgs_status bgs_debug_tile_ranges(bgs_context* c, uint32_t* start_end) {
     if (!c || !start_end) return BGS_EINVAL;
     if (!c->have_frame) return fail(c, BGS_NOT_READY, "no frame rendered yet");
+    if (c->last_chunks > 1) return fail(c, BGS_NOT_READY, "the last frame was binned in %d rounds: set BGS_FLAG_NO_CHUNKS for the tile hooks", c->last_chunks);
     CU(c, cudaSetDevice(c->device));
     CU(c, cudaMemcpy(start_end, c->ranges, (size_t)c->stats.tiles_x * c->stats.tiles_y * 8, cudaMemcpyDeviceToHost));
     return BGS_OK;
@@ -676,6 +768,7 @@ bgs_status bgs_debug_tile_ranges(bgs_context* c, uint32_t* start_end) {
 bgs_status bgs_debug_tile_entries(bgs_context* c, uint32_t* ranks, uint64_t capacity) {
     if (!c || !ranks) return BGS_EINVAL;
     if (!c->have_frame) return fail(c, BGS_NOT_READY, "no frame rendered yet");
+    if (c->last_chunks > 1) return fail(c, BGS_NOT_READY, "the last frame was binned in %d rounds: set BGS_FLAG_NO_CHUNKS for the tile hooks", c->last_chunks);
     CU(c, cudaSetDevice(c->device));
     const uint64_t cnt = c->stats.n_pairs < capacity ? c->stats.n_pairs : capacity;
     CU(c, cudaMemcpy(ranks, c->pvals[c->pair_result], (size_t)cnt * 4, cudaMemcpyDeviceToHost));

@@ -19,8 +19,8 @@ constexpr uint32_t BIN_BIG = 128u;   // larger than this: global queue, drained 
 
 __global__ void __launch_bounds__(BIN_THREADS)
 bin_emit_kernel(const SplatRec* __restrict__ recs, const uint32_t* __restrict__ perm, FrameCounters* __restrict__ ctr,
-                uint32_t* __restrict__ status, int tiles_x, uint32_t capacity, uint32_t* __restrict__ pair_keys,
-                uint32_t* __restrict__ pair_vals) {
+                ChunkCounters* __restrict__ cc, uint32_t* __restrict__ status, int tiles_x, uint32_t capacity,
+                uint32_t* __restrict__ pair_keys, uint32_t* __restrict__ pair_vals) {
     __shared__ uint32_t s_wtot[BIN_THREADS / 32];
     __shared__ uint32_t s_base;
     __shared__ uint32_t s_tile;
@@ -30,7 +30,7 @@ bin_emit_kernel(const SplatRec* __restrict__ recs, const uint32_t* __restrict__ 
     const uint32_t n_vis = ctr->n_vis;
     const uint32_t num_tiles = (n_vis + BIN_TILE - 1) / BIN_TILE;
     while (true) {
-        if (t == 0) { s_tile = atomicAdd(&ctr->tile_ctr[5], 1u); s_nbig = 0u; }
+        if (t == 0) { s_tile = atomicAdd(&cc->tile_ctr_bin, 1u); s_nbig = 0u; }
         __syncthreads();
         const uint32_t tile = s_tile;
         if (tile >= num_tiles) break;
@@ -71,8 +71,8 @@ bin_emit_kernel(const SplatRec* __restrict__ recs, const uint32_t* __restrict__ 
                 s_base = base;
                 if (tile == num_tiles - 1) {
                     const uint32_t need = base + agg;
-                    ctr->n_pairs_needed = need;
-                    ctr->n_pairs = need < capacity ? need : capacity;
+                    cc->n_pairs_needed = need;
+                    cc->n_pairs = need < capacity ? need : capacity;
                 }
             }
         }
@@ -133,6 +133,7 @@ bin_emit_kernel(const SplatRec* __restrict__ recs, const uint32_t* __restrict__ 
 //            sit in the first CTAs' ranges: without this the frame waits on a handful of CTAs)
 __global__ void __launch_bounds__(BIN_THREADS)
 bin_emit_coop_kernel(const SplatRec* __restrict__ recs, const uint32_t* __restrict__ perm, FrameCounters* __restrict__ ctr,
+                     ChunkCounters* __restrict__ cc, uint32_t frac_a, uint32_t frac_b, uint32_t num_tiles_total,
                      uint32_t* __restrict__ block_cnt, int tiles_x, uint32_t capacity, uint32_t* __restrict__ pair_keys,
                      uint32_t* __restrict__ pair_vals, uint32_t* __restrict__ q_rank, uint32_t* __restrict__ q_off,
                      uint32_t q_cap, unsigned long long* __restrict__ tl) {
@@ -148,10 +149,15 @@ bin_emit_coop_kernel(const SplatRec* __restrict__ recs, const uint32_t* __restri
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const uint32_t G = gridDim.x, b = blockIdx.x;
     const uint32_t n_vis = ctr->n_vis;
+    // this round's front-to-back rank range [ra, rb) = n_vis * [frac_a, frac_b) / 65536 (the whole visible set in a
+    // one-round frame); empty once every tile has saturated in the earlier rounds (nothing left to blend into)
+    uint32_t ra = (uint32_t)((uint64_t)n_vis * frac_a >> 16), rb = (uint32_t)((uint64_t)n_vis * frac_b >> 16);
+    if (frac_a != 0u && ld_volatile(&ctr->tiles_done) >= num_tiles_total) rb = ra;
+    const uint32_t n_rng = rb - ra;
     // this CTA's contiguous rank range, cut into sub-tiles of 256 * ipt ranks (ipt chosen so that the whole
     // range is ONE sub-tile whenever it fits 8 items per thread: every CTA then does the same number of rounds)
-    const uint32_t rlo = (uint32_t)((uint64_t)b * n_vis / G), rhi = (uint32_t)((uint64_t)(b + 1) * n_vis / G);
-    const uint32_t chunk = (n_vis + G - 1) / G;
+    const uint32_t rlo = ra + (uint32_t)((uint64_t)b * n_rng / G), rhi = ra + (uint32_t)((uint64_t)(b + 1) * n_rng / G);
+    const uint32_t chunk = (n_rng + G - 1) / G;
     uint32_t ipt = (chunk + BIN_THREADS - 1) / BIN_THREADS;
     if (ipt > COOP_ITEMS) ipt = COOP_ITEMS;
     if (ipt == 0) ipt = 1;
@@ -188,7 +194,7 @@ bin_emit_coop_kernel(const SplatRec* __restrict__ recs, const uint32_t* __restri
         st_volatile(block_cnt + b, s_total);
     }
     timeline_stamp(tl, 1);
-    grid_barrier(&ctr->barrier[1], G);
+    grid_barrier(&cc->barrier, G);
     timeline_stamp(tl, 2);
 
     // ---- phase 2 (sums saturate at 2^30 - 1: such a frame is rejected by the host)
@@ -206,8 +212,8 @@ bin_emit_coop_kernel(const SplatRec* __restrict__ recs, const uint32_t* __restri
     if (b == G - 1 && t == 0) {
         const uint64_t need64 = run64 + s_total;
         const uint32_t need = need64 > LB_VMASK ? LB_VMASK : (uint32_t)need64;
-        ctr->n_pairs_needed = need;
-        ctr->n_pairs = need < capacity ? need : capacity;
+        cc->n_pairs_needed = need;
+        cc->n_pairs = need < capacity ? need : capacity;
     }
     uint32_t run = run64 > LB_VMASK ? LB_VMASK : (uint32_t)run64;
     for (uint32_t base = rlo; base < rhi; base += sub) {
@@ -242,8 +248,8 @@ bin_emit_coop_kernel(const SplatRec* __restrict__ recs, const uint32_t* __restri
             ttotal += c; btotal += d; mtotal += e;
         }
         if (t == 0) {   // one reservation per round in each global queue
-            if (btotal) s_qbase = atomicAdd(&ctr->big_count, btotal);
-            if (mtotal) s_mbase = atomicAdd(&ctr->med_count, mtotal);
+            if (btotal) s_qbase = atomicAdd(&cc->big_count, btotal);
+            if (mtotal) s_mbase = atomicAdd(&cc->med_count, mtotal);
         }
         __syncthreads();
         // footprint classes:  <= BIN_TINY tiles: written right here by the owning thread;
@@ -278,15 +284,15 @@ bin_emit_coop_kernel(const SplatRec* __restrict__ recs, const uint32_t* __restri
         __syncthreads();
     }
     timeline_stamp(tl, 3);
-    grid_barrier(&ctr->barrier[1], 2u * G);
+    grid_barrier(&cc->barrier, 2u * G);
     timeline_stamp(tl, 4);
 
     // ---- phase 3a: medium footprints, 32 per warp: each lane fetches one splat's (record, offset, bbox)
     //      so the memory latency is paid once per 32 splats; then the warp writes them one after another
-    const uint32_t nm = ld_volatile(&ctr->med_count);
+    const uint32_t nm = ld_volatile(&cc->med_count);
     while (true) {
         uint32_t mb = 0u;
-        if (lane == 0) mb = atomicAdd(&ctr->med_head, 32u);
+        if (lane == 0) mb = atomicAdd(&cc->med_head, 32u);
         mb = __shfl_sync(0xffffffffu, mb, 0);
         if (mb >= nm) break;
         const uint32_t i = mb + lane;
@@ -315,10 +321,10 @@ bin_emit_coop_kernel(const SplatRec* __restrict__ recs, const uint32_t* __restri
         }
     }
     // ---- phase 3b: warps pull large-footprint splats from the back queue, one at a time
-    const uint32_t nq = ld_volatile(&ctr->big_count);
+    const uint32_t nq = ld_volatile(&cc->big_count);
     while (true) {
         uint32_t q = 0u;
-        if (lane == 0) q = atomicAdd(&ctr->big_head, 1u);
+        if (lane == 0) q = atomicAdd(&cc->big_head, 1u);
         q = __shfl_sync(0xffffffffu, q, 0);
         if (q >= nq) break;
         const uint32_t r = __ldcg(q_rank + (q_cap - 1u - q)), off = __ldcg(q_off + (q_cap - 1u - q));
@@ -341,9 +347,9 @@ bin_emit_coop_kernel(const SplatRec* __restrict__ recs, const uint32_t* __restri
     timeline_stamp(tl, 5);
 }
 
-__global__ void tile_ranges_kernel(const uint32_t* __restrict__ sorted_tile_ids, const FrameCounters* __restrict__ ctr,
+__global__ void tile_ranges_kernel(const uint32_t* __restrict__ sorted_tile_ids, const uint32_t* __restrict__ n_ptr,
                                    uint2* __restrict__ ranges) {
-    const uint32_t n = ctr->n_pairs;
+    const uint32_t n = *n_ptr;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const uint32_t t = sorted_tile_ids[i];
         if (i == 0 || sorted_tile_ids[i - 1] != t) ranges[t].x = i;
@@ -351,14 +357,14 @@ __global__ void tile_ranges_kernel(const uint32_t* __restrict__ sorted_tile_ids,
     }
 }
 
-void launch_bin_emit(const SplatRec* recs, const uint32_t* perm, FrameCounters* ctr, uint32_t* status, int tiles_x,
-                     uint32_t capacity, uint32_t* pair_keys, uint32_t* pair_vals, uint32_t n_upper, int sm_count,
-                     cudaStream_t stream) {
+void launch_bin_emit(const SplatRec* recs, const uint32_t* perm, FrameCounters* ctr, ChunkCounters* cc, uint32_t* status,
+                     int tiles_x, uint32_t capacity, uint32_t* pair_keys, uint32_t* pair_vals, uint32_t n_upper,
+                     int sm_count, cudaStream_t stream) {
     uint32_t blocks = (n_upper + BIN_TILE - 1) / BIN_TILE;
     const uint32_t cap_blocks = (uint32_t)sm_count * 4u;
     if (blocks > cap_blocks) blocks = cap_blocks;
     if (blocks == 0) blocks = 1;
-    bin_emit_kernel<<<blocks, BIN_THREADS, 0, stream>>>(recs, perm, ctr, status, tiles_x, capacity, pair_keys, pair_vals);
+    bin_emit_kernel<<<blocks, BIN_THREADS, 0, stream>>>(recs, perm, ctr, cc, status, tiles_x, capacity, pair_keys, pair_vals);
 }
 uint32_t bin_num_tiles(uint32_t n) { return (n + BIN_TILE - 1) / BIN_TILE; }
 
@@ -367,22 +373,24 @@ int bin_coop_blocks_per_sm() {
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, bin_emit_coop_kernel, BIN_THREADS, 0) != cudaSuccess) return 0;
     return b;
 }
-cudaError_t launch_bin_emit_coop(const SplatRec* recs, const uint32_t* perm, FrameCounters* ctr, uint32_t* block_cnt,
+cudaError_t launch_bin_emit_coop(const SplatRec* recs, const uint32_t* perm, FrameCounters* ctr, ChunkCounters* cc,
+                                 uint32_t frac_a, uint32_t frac_b, uint32_t num_tiles_total, uint32_t* block_cnt,
                                  int tiles_x, uint32_t capacity, uint32_t* pair_keys, uint32_t* pair_vals,
                                  uint32_t* q_rank, uint32_t* q_off, uint32_t q_cap, unsigned long long* timeline,
                                  uint32_t grid, cudaStream_t stream) {
-    void* args[] = {(void*)&recs, (void*)&perm, (void*)&ctr, (void*)&block_cnt, (void*)&tiles_x, (void*)&capacity, (void*)&pair_keys,
+    void* args[] = {(void*)&recs, (void*)&perm, (void*)&ctr, (void*)&cc, (void*)&frac_a, (void*)&frac_b, (void*)&num_tiles_total,
+                    (void*)&block_cnt, (void*)&tiles_x, (void*)&capacity, (void*)&pair_keys,
                     (void*)&pair_vals, (void*)&q_rank, (void*)&q_off, (void*)&q_cap, (void*)&timeline};
     return cudaLaunchCooperativeKernel((const void*)bin_emit_coop_kernel, dim3(grid), dim3(BIN_THREADS), args, 0, stream);
 }
 
-void launch_tile_ranges(const uint32_t* sorted_tile_ids, const FrameCounters* ctr, uint2* ranges, uint32_t capacity,
+void launch_tile_ranges(const uint32_t* sorted_tile_ids, const uint32_t* n_ptr, uint2* ranges, uint32_t capacity,
                         int sm_count, cudaStream_t stream) {
     uint32_t blocks = (capacity + 255) / 256;
     const uint32_t cap_blocks = (uint32_t)sm_count * 8u;
     if (blocks > cap_blocks) blocks = cap_blocks;
     if (blocks == 0) blocks = 1;
-    tile_ranges_kernel<<<blocks, 256, 0, stream>>>(sorted_tile_ids, ctr, ranges);
+    tile_ranges_kernel<<<blocks, 256, 0, stream>>>(sorted_tile_ids, n_ptr, ranges);
 }
 
 }  // namespace bgs

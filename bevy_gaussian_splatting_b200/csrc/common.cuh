@@ -38,20 +38,34 @@ struct __align__(16) SplatRec {
 };
 static_assert(sizeof(SplatRec) == 48, "SplatRec must be 48 bytes");
 
-// Device-resident per-frame counters (one cudaMemsetAsync per frame clears them).
+// Counters of one binning round.  A frame normally has ONE round (chunk 0 = all visible splats); frames whose
+// splats cover many tiles each are binned / sorted / rasterised in several front-to-back rank chunks so that the
+// rounds after every tile has saturated emit nothing (saturation-aware binning, see api.cu).
+struct ChunkCounters {
+    uint32_t n_pairs;           // (splat, tile) pairs emitted (clamped to capacity)
+    uint32_t n_pairs_needed;    // pairs the round needs (may exceed capacity -> host regrows and redoes the frame)
+    uint32_t barrier;           // grid barrier of bin_emit_coop (two uses per launch)
+    uint32_t big_count, big_head;   // queue of large footprints (grows from the back of the queue arrays)
+    uint32_t med_count, med_head;   // queue of medium footprints (grows from the front), drained 32 per warp
+    uint32_t tile_ctr_bin;      // tile tickets of the fallback (chained look-back) bin kernel
+    uint32_t tile_ctr_sort[4];  // tile tickets of the pair sort's passes
+    uint32_t pad[4];
+};
+static_assert(sizeof(ChunkCounters) == 64, "ChunkCounters is 64 bytes");
+constexpr int MAX_CHUNKS = 8;
+
+// Device-resident per-frame counters (cleared at frame start).
 struct FrameCounters {
     uint32_t n_sort;            // entries the depth sort runs over (n_vis, or N with SORT_ALL)
     uint32_t n_vis;             // in-frustum gaussians
-    uint32_t n_pairs;           // (splat, tile) pairs emitted (clamped to capacity)
-    uint32_t n_pairs_needed;    // pairs the frame needs (may exceed capacity -> host regrows)
-    uint32_t tile_ctr[16];      // dynamic tile tickets: [0] keygen, [1..4] depth passes,
-                                // [5] bin, [6..7] pair passes, [8..] spare
+    uint32_t tiles_done;        // tiles whose pixels have all saturated (chunked frames)
+    uint32_t pad0;
+    uint32_t tile_ctr[8];       // dynamic tile tickets: [0] keygen (fallback kernel), [1..4] depth sort passes
     uint32_t culled_min_inv;    // RasterizeMode::Depth: max over culled of (0xFFFFFFFF - index); 0 = none culled
     uint32_t culled_max_p1;     //                       max over culled of (index + 1);          0 = none culled
     float depth_min, depth_max; //                       distances of sorted[N-1] / sorted[1] (gaussian.wgsl:329-349)
-    uint32_t barrier[8];        // grid barriers of the cooperative kernels: [0] keygen, [1] bin
-    uint32_t big_count, big_head;   // bin: queue of large footprints (grows from the back of the queue arrays)
-    uint32_t med_count, med_head;   // bin: queue of medium footprints (grows from the front), drained 32 per warp
+    uint32_t barrier[4];        // grid barrier of keygen_coop: [0]
+    ChunkCounters chunk[MAX_CHUNKS];
 };
 
 // flag/counter words exchanged between CTAs of one kernel: relaxed, GPU scope (L2 is the coherence point;

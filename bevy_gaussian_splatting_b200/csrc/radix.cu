@@ -258,6 +258,19 @@ onesweep_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict
     }
 }
 
+// Clears the look-back status rows a sort over *n_ptr entries has used (passes rows of `stride` words), so the same
+// rows can serve the next sort of the frame (chunked frames run one pair sort per round).
+__global__ void status_clear_kernel(uint32_t* __restrict__ status, size_t stride, int passes, const uint32_t* __restrict__ n_ptr) {
+    const uint32_t n = *n_ptr;
+    const uint32_t t = RS_THREADS * RS_ITEMS_MIN;
+    const size_t words = (size_t)((n + t - 1) / t) * 256u / 4u;   // uint4 stores
+    for (int p = 0; p < passes; ++p) {
+        uint4* row = reinterpret_cast<uint4*>(status + (size_t)p * stride);
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < words; i += (size_t)gridDim.x * blockDim.x)
+            row[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+}
+
 // ---- host-side launch helpers ------------------------------------------------------------------
 // status rows are sized for the smallest tile so either variant fits
 uint32_t radix_num_tiles(uint32_t capacity) {
@@ -291,6 +304,10 @@ void launch_onesweep(const uint32_t* keys_in, const uint32_t* vals_in, uint32_t*
     else
         onesweep_kernel<16><<<blocks, RS_THREADS, 0, stream>>>(keys_in, vals_in, keys_out, vals_out, n_ptr, hist, status,
                                                                 tile_ctr, shift, tl);
+}
+
+void launch_status_clear(uint32_t* status, size_t stride, int passes, const uint32_t* n_ptr, int sm_count, cudaStream_t stream) {
+    status_clear_kernel<<<sm_count * 2, 256, 0, stream>>>(status, stride, passes, n_ptr);
 }
 
 }  // namespace bgs

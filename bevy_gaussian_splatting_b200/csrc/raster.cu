@@ -287,9 +287,11 @@ __device__ __forceinline__ void store_pixel2(void* out, uint32_t format, size_t 
     }
 }
 
+template <bool CHUNKED>
 __global__ void __launch_bounds__(R2_THREADS)
 raster2_kernel(const SplatRec* __restrict__ recs, const uint32_t* __restrict__ tile_entries, const uint2* __restrict__ ranges,
-               int W, int H, int tiles_x, void* __restrict__ out, uint32_t format) {
+               int W, int H, int tiles_x, void* __restrict__ out, uint32_t format, float4* __restrict__ state,
+               unsigned char* __restrict__ tile_done, uint32_t* __restrict__ tiles_done, int first, int last) {
     __shared__ __align__(16) unsigned char s_mem[R2_BYTES];
     float4* s_q0 = reinterpret_cast<float4*>(s_mem + SM_Q0);
     float4* s_uv = reinterpret_cast<float4*>(s_mem + SM_UV);
@@ -304,12 +306,29 @@ raster2_kernel(const SplatRec* __restrict__ recs, const uint32_t* __restrict__ t
     const int px0 = tile_x * TILE_PX + 2 * (lane & 7), py = wy0 + (lane >> 3);
     const bool in0 = px0 < W && py < H, in1 = px0 + 1 < W && py < H;
     const float fx0 = (float)px0 + 0.5f, fx1 = (float)px0 + 1.5f, fy = (float)py + 0.5f;
-    const uint2 range = ranges[tile];
+    uint2 range = ranges[tile];
 
     // T < T_STOP <=> pixel done; lim = 1 while alive, -1 once done (folds the "alive" test into |u| <= lim)
     float T0 = in0 ? 1.0f : 0.0f, T1 = in1 ? 1.0f : 0.0f;
     float lim0 = in0 ? 1.0f : -1.0f, lim1 = in1 ? 1.0f : -1.0f;
     float r0 = 0.f, g0 = 0.f, b0 = 0.f, r1 = 0.f, g1 = 0.f, b1 = 0.f;
+    float4* st = nullptr;
+    if (CHUNKED) {
+        // one of several front-to-back rounds of a frame: the blend state (premultiplied rgb, transmittance) of
+        // every pixel lives in `state` (tile-major, so a warp's accesses are contiguous) between rounds; since a
+        // round resumes each pixel exactly where the previous one stopped, the frame is bit-identical to one round
+        st = state + ((size_t)tile * R2_THREADS + t) * 2;
+        if (!first) {
+            const bool done = tile_done[tile] != 0;             // every pixel saturated in an earlier round
+            if (!last && (done || range.x == range.y)) return;  // nothing to blend, state unchanged
+            const float4 s0 = st[0], s1 = st[1];
+            r0 = s0.x; g0 = s0.y; b0 = s0.z; T0 = s0.w;
+            r1 = s1.x; g1 = s1.y; b1 = s1.z; T1 = s1.w;
+            lim0 = (in0 && !(T0 < T_STOP)) ? 1.0f : -1.0f;
+            lim1 = (in1 && !(T1 < T_STOP)) ? 1.0f : -1.0f;
+            if (done) range.y = range.x;
+        }
+    }
     for (uint32_t base = range.x; base < range.y; base += RT_CHUNK) {
         if (__syncthreads_count((lim0 > 0.f || lim1 > 0.f) ? 1 : 0) == 0) break;   // also fences smem reuse
         const uint32_t cnt = min((uint32_t)RT_CHUNK, range.y - base);
@@ -381,6 +400,15 @@ raster2_kernel(const SplatRec* __restrict__ recs, const uint32_t* __restrict__ t
             }
         }
     }
+    if (CHUNKED && !last) {
+        st[0] = make_float4(r0, g0, b0, T0);
+        st[1] = make_float4(r1, g1, b1, T1);
+        if (__syncthreads_count((lim0 > 0.f || lim1 > 0.f) ? 1 : 0) == 0 && t == 0) {
+            tile_done[tile] = 1;
+            atomicAdd(tiles_done, 1u);
+        }
+        return;
+    }
     if (!(in0 || in1)) return;
     store_pixel2(out, format, (size_t)py * W + px0, in0, in1, r0, g0, b0, r1, g1, b1);
 }
@@ -391,7 +419,8 @@ void launch_raster(int mode, bool large_footprints, const SplatRec* recs, const 
     // measured on B200: the 2-pixels-per-thread variant wins when splats cover many tiles (C2 raw, scale 1:
     // 131 -> 117 us) and loses when most splats are a few pixels (C3, scale 0.02: 178 -> 217 us)
     if (mode == 0 && large_footprints)
-        raster2_kernel<<<tiles_x * tiles_y, R2_THREADS, 0, stream>>>(recs, tile_entries, ranges, W, H, tiles_x, out, format);
+        raster2_kernel<false><<<tiles_x * tiles_y, R2_THREADS, 0, stream>>>(recs, tile_entries, ranges, W, H, tiles_x, out, format,
+                                                                            nullptr, nullptr, nullptr, 1, 1);
     else if (mode == 0) {
         // experiment knob: pad the CTA's shared memory so fewer raster CTAs fit per SM and kernels of another
         // in-flight frame can co-run (BGS_RASTER_PAD = bytes of dynamic shared memory, default 0)
@@ -403,6 +432,14 @@ void launch_raster(int mode, bool large_footprints, const SplatRec* recs, const 
         raster_kernel<1><<<tiles_x * tiles_y, RT_THREADS, 0, stream>>>(recs, extra, tile_entries, ranges, W, H, tiles_x, out, format);
     else
         raster_kernel<2><<<tiles_x * tiles_y, RT_THREADS, 0, stream>>>(recs, extra, tile_entries, ranges, W, H, tiles_x, out, format);
+}
+
+// One front-to-back round of a chunked frame (quad-uv records only); see raster2_kernel.
+void launch_raster_round(const SplatRec* recs, const uint32_t* tile_entries, const uint2* ranges, int W, int H, int tiles_x,
+                         int tiles_y, void* out, uint32_t format, float4* state, unsigned char* tile_done,
+                         uint32_t* tiles_done, int first, int last, cudaStream_t stream) {
+    raster2_kernel<true><<<tiles_x * tiles_y, R2_THREADS, 0, stream>>>(recs, tile_entries, ranges, W, H, tiles_x, out, format,
+                                                                       state, tile_done, tiles_done, first, last);
 }
 
 }  // namespace bgs

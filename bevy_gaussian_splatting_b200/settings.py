@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import dataclasses
 import enum
+from typing import Optional
 
 from . import abi
 
@@ -89,6 +90,9 @@ class CloudSettings:
     time: float = 0.0
     # this repo's extension: sort all N entries like the reference instead of compacting first
     sort_all: bool = False
+    # this repo's extension: front-to-back binning rounds (BGS_FLAG_CHUNKS): None = library's choice from the last
+    # frame's footprint statistics, True = always, False = never (the tile debug hooks need a one-round frame)
+    binning_rounds: Optional[bool] = None
 
     def to_abi(self) -> abi.bgs_settings:
         return abi.bgs_settings(
@@ -98,6 +102,7 @@ class CloudSettings:
             opacity_adaptive_radius=int(bool(self.opacity_adaptive_radius)),
             draw_mode=int(self.draw_mode),
             radix_sort_depth_bits=int(self.radix_sort_depth_bits),
-            flags=abi.BGS_FLAG_SORT_ALL if self.sort_all else 0,
+            flags=(abi.BGS_FLAG_SORT_ALL if self.sort_all else 0)
+            | (0 if self.binning_rounds is None else (abi.BGS_FLAG_CHUNKS if self.binning_rounds else abi.BGS_FLAG_NO_CHUNKS)),
             reserved=0,
         )

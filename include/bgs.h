@@ -61,9 +61,15 @@ enum { BGS_DRAW_ALL = 0, BGS_DRAW_SELECTED = 1, BGS_DRAW_HIGHLIGHT_SELECTED = 2 
 enum {
     BGS_FLAG_SORT_ALL = 1u, /* sort all N entries like the reference (culled keyed 0xFFFFFFFF)
                                instead of stream-compacting the visible ones first; same output */
-    BGS_FLAG_ASYNC = 2u     /* bgs_render only enqueues the frame on the context stream and returns;
+    BGS_FLAG_ASYNC = 2u,    /* bgs_render only enqueues the frame on the context stream and returns;
                                bgs_sync() completes it (frames may be queued back to back, like the
                                reference's command-buffer submission: radix.rs / mod.rs never read back) */
+    BGS_FLAG_NO_CHUNKS = 4u,/* never split the frame into front-to-back binning rounds (see BGS_FLAG_CHUNKS);
+                               the tile debug hooks need a one-round frame */
+    BGS_FLAG_CHUNKS = 8u    /* always bin / tile-sort / blend in front-to-back rank rounds that stop emitting
+                               (splat, tile) pairs once every tile has saturated.  Same pixels, bit for bit.
+                               Without either flag the library picks rounds when the previous frame had
+                               >= 64 pairs per visible splat (USE_OBB records only). */
 };
 typedef struct {
     uint32_t gaussian_mode;           /* BGS_GAUSSIAN_* */
@@ -87,6 +93,8 @@ typedef struct {
     uint64_t n_pairs;    /* (splat, tile) intersections this frame */
     uint32_t tiles_x, tiles_y;
     uint32_t width, height;
+    uint32_t rounds;          /* binning rounds of the frame: 1, or > 1 on chunked frames (BGS_FLAG_CHUNKS) */
+    uint32_t tiles_saturated; /* chunked frames: tiles whose every pixel saturated before the last round */
 } bgs_frame_stats;
 
 bgs_status bgs_context_create(int cuda_device, bgs_context** out);

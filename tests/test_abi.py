@@ -32,7 +32,7 @@ def test_struct_layouts_match_header():
     assert C.sizeof(abi.bgs_view) == (48 + 3 + 4) * 4
     assert C.sizeof(abi.bgs_cloud_uniform) == 20 * 4
     assert C.sizeof(abi.bgs_settings) == 32
-    assert C.sizeof(abi.bgs_frame_stats) == 32
+    assert C.sizeof(abi.bgs_frame_stats) == 40 and abi.bgs_frame_stats.rounds.offset == 32
     assert abi.bgs_frame_stats.n_pairs.offset == 8
 
 
