@@ -87,8 +87,10 @@ struct bgs_context {
                                       // frames an ESTIMATE of what one round would have emitted
     // chunked frames (saturation-aware binning): the visible set is binned / sorted / blended in front-to-back
     // rank rounds [frac[r], frac[r+1]) / 65536; once every tile has saturated the remaining rounds emit nothing
-    uint32_t chunk_frac[MAX_CHUNKS + 1] = {0, 1024, 2048, 4096, 8192, 16384, 65536, 65536, 65536};
-    int chunk_count = 6;
+    // (x8 schedule: the front of a heavy scene saturates the frame within a few hundred splats; measured on C2/C3
+    // at global_scale 1, profiles/r1_rounds.md)
+    uint32_t chunk_frac[MAX_CHUNKS + 1] = {0, 16, 128, 1024, 8192, 65536, 65536, 65536, 65536};
+    int chunk_count = 5;
     uint32_t chunk_pairs_hint[MAX_CHUNKS] = {};   // last chunked frame's pairs per round (pair sort tile size)
     bool chunk_hint_valid = false;
     float4* state = nullptr;          // per-pixel blend state between rounds (tile-major), tiles * 256 * 16 B
@@ -433,9 +435,12 @@ static bgs_status finish_frame(bgs_context* c) {
     c->have_frame = true; c->last_cloud = c->pend_cloud; c->last_fc = c->pend_fc; c->last_sort_all = c->pend_sort_all;
     c->last_by_slot = c->pend_by_slot; c->n_vis_hint = c->h_ctr->n_vis; c->last_chunks = chunks;
     if (chunks > 1) {
-        // round 0 is always emitted in full: scale it up to the whole visible set (the nearest splats have the
-        // largest footprints, so this errs towards staying chunked)
-        const uint64_t est = (uint64_t)c->h_ctr->chunk[0].n_pairs_needed * 65536ull / c->chunk_frac[1];
+        // the rounds emitted in full, scaled up to the whole visible set (the nearest splats have the largest
+        // footprints, so this errs towards staying chunked)
+        uint64_t got = 0;
+        int full = 0;
+        while (full < chunks && !c->h_ctr->chunk[full].skipped) got += c->h_ctr->chunk[full++].n_pairs_needed;
+        const uint64_t est = got * 65536ull / c->chunk_frac[full];
         c->n_pairs_hint = est > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)est;
         for (int r = 0; r < chunks; ++r) c->chunk_pairs_hint[r] = c->h_ctr->chunk[r].n_pairs;
         c->chunk_hint_valid = true;
@@ -539,12 +544,14 @@ bgs_status bgs_render(bgs_context* c, const bgs_cloud* cloud, const bgs_view* vi
         target = fslot ? c->frame_alt : c->frame;
     }
 
-    // saturation-aware chunking: frames whose splats cover many tiles each (last frame: >= 64 pairs per visible splat
-    // and >= 2^24 pairs) run binning / tile sort / blend in front-to-back rank rounds; the rounds after every tile
-    // has saturated emit nothing.  Quad-uv records + cooperative binning only; BGS_FLAG_CHUNKS / _NO_CHUNKS force it.
+    // saturation-aware chunking: frames whose splats cover many tiles each (last frame: >= 32 pairs per visible splat
+    // and >= 2^24 pairs; measured crossover on B200: ~15-30 M pairs, profiles/r1_rounds.md) run binning / tile sort /
+    // blend in front-to-back rank rounds; the rounds after every tile has saturated emit nothing.
+    // Quad-uv records + cooperative binning only; BGS_FLAG_CHUNKS / _NO_CHUNKS force it.
     bool chunked = raster_mode == 0 && c->coop && num_tiles <= CHUNK_MAX_TILES && !(st->flags & BGS_FLAG_NO_CHUNKS) && c->chunk_count > 1;
     if (chunked && !(st->flags & BGS_FLAG_CHUNKS))
-        chunked = c->n_vis_hint > 0 && c->n_pairs_hint >= (1u << 24) && (uint64_t)c->n_pairs_hint >= 64ull * c->n_vis_hint;
+        chunked = c->n_vis_hint > 0 && c->n_pairs_hint >= (c->last_chunks > 1 ? 3u << 22 : 1u << 24) &&
+                  (uint64_t)c->n_pairs_hint >= (c->last_chunks > 1 ? 24ull : 32ull) * c->n_vis_hint;   // (hysteresis)
     const int rounds = chunked ? c->chunk_count : 1;
     if (chunked && c->cap_state_tiles < num_tiles) {
         cudaFree(c->state); c->state = nullptr; c->cap_state_tiles = 0;

@@ -152,8 +152,12 @@ bin_emit_coop_kernel(const SplatRec* __restrict__ recs, const uint32_t* __restri
     // this round's front-to-back rank range [ra, rb) = n_vis * [frac_a, frac_b) / 65536 (the whole visible set in a
     // one-round frame); empty once every tile has saturated in the earlier rounds (nothing left to blend into)
     uint32_t ra = (uint32_t)((uint64_t)n_vis * frac_a >> 16), rb = (uint32_t)((uint64_t)n_vis * frac_b >> 16);
-    if (frac_a != 0u && ld_volatile(&ctr->tiles_done) >= num_tiles_total) rb = ra;
+    if (frac_a != 0u && ld_volatile(&ctr->tiles_done) >= num_tiles_total) {
+        if (b == 0 && t == 0) cc->skipped = 1u;
+        rb = ra;
+    }
     const uint32_t n_rng = rb - ra;
+    if (n_rng == 0u) return;   // (grid-uniform) nothing to emit: the round's counters stay zero
     // this CTA's contiguous rank range, cut into sub-tiles of 256 * ipt ranks (ipt chosen so that the whole
     // range is ONE sub-tile whenever it fits 8 items per thread: every CTA then does the same number of rounds)
     const uint32_t rlo = ra + (uint32_t)((uint64_t)b * n_rng / G), rhi = ra + (uint32_t)((uint64_t)(b + 1) * n_rng / G);
@@ -321,20 +325,32 @@ bin_emit_coop_kernel(const SplatRec* __restrict__ recs, const uint32_t* __restri
         }
     }
     // ---- phase 3b: warps pull large-footprint splats from the back queue, one at a time
+    //      (a few splats that each cover thousands of tiles -- the front of a heavy scene -- are cut into up to
+    //      16 parts so the whole grid shares them)
     const uint32_t nq = ld_volatile(&cc->big_count);
+    uint32_t part_shift = 0u;
+    while (part_shift < 4u && ((uint64_t)nq << (part_shift + 2u)) <= (uint64_t)G * (BIN_THREADS / 32)) ++part_shift;
+    const uint32_t n_tickets = nq << part_shift;
     while (true) {
         uint32_t q = 0u;
         if (lane == 0) q = atomicAdd(&cc->big_head, 1u);
         q = __shfl_sync(0xffffffffu, q, 0);
-        if (q >= nq) break;
+        if (q >= n_tickets) break;
+        const uint32_t part = q & ((1u << part_shift) - 1u);
+        q >>= part_shift;
         const uint32_t r = __ldcg(q_rank + (q_cap - 1u - q)), off = __ldcg(q_off + (q_cap - 1u - q));
         const uint2 bb = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const char*>(recs + r) + 24));
         const uint32_t txlo = (bb.x & 0xFFFFu) >> 4, txhi = (bb.x >> 16) >> 4;
         const uint32_t tylo = (bb.y & 0xFFFFu) >> 4, tyhi = (bb.y >> 16) >> 4;
-        const uint32_t w = txhi - txlo + 1u, total = w * (tyhi - tylo + 1u);
-        uint32_t ty = tylo + (uint32_t)lane / w, tx = txlo + (uint32_t)lane % w;
+        const uint32_t w = txhi - txlo + 1u, total_all = w * (tyhi - tylo + 1u);
+        // this part's slice [i0, total) of the footprint, in multiples of 32 pairs
+        const uint32_t per = (((total_all + (1u << part_shift) - 1u) >> part_shift) + 31u) & ~31u;
+        const uint32_t i0 = part * per;
+        if (i0 >= total_all) continue;
+        const uint32_t total = min(total_all, i0 + per);
+        uint32_t ty = tylo + (i0 + (uint32_t)lane) / w, tx = txlo + (i0 + (uint32_t)lane) % w;
         const uint32_t dy = 32u / w, dxr = 32u % w;
-        for (uint32_t i = lane; i < total; i += 32) {
+        for (uint32_t i = i0 + lane; i < total; i += 32) {
             const uint32_t o = off + i;
             if (o < capacity) {
                 pair_keys[o] = ty * (uint32_t)tiles_x + tx;

@@ -49,7 +49,8 @@ struct ChunkCounters {
     uint32_t med_count, med_head;   // queue of medium footprints (grows from the front), drained 32 per warp
     uint32_t tile_ctr_bin;      // tile tickets of the fallback (chained look-back) bin kernel
     uint32_t tile_ctr_sort[4];  // tile tickets of the pair sort's passes
-    uint32_t pad[4];
+    uint32_t skipped;           // 1 = the round emitted nothing because every tile had already saturated
+    uint32_t pad[3];
 };
 static_assert(sizeof(ChunkCounters) == 64, "ChunkCounters is 64 bytes");
 constexpr int MAX_CHUNKS = 8;

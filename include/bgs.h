@@ -69,7 +69,7 @@ enum {
     BGS_FLAG_CHUNKS = 8u    /* always bin / tile-sort / blend in front-to-back rank rounds that stop emitting
                                (splat, tile) pairs once every tile has saturated.  Same pixels, bit for bit.
                                Without either flag the library picks rounds when the previous frame had
-                               >= 64 pairs per visible splat (USE_OBB records only). */
+                               >= 32 (splat, tile) pairs per visible splat and >= 2^24 pairs (USE_OBB records only). */
 };
 typedef struct {
     uint32_t gaussian_mode;           /* BGS_GAUSSIAN_* */

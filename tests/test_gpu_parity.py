@@ -191,7 +191,7 @@ def test_binning_rounds_bit_identical(plugin, oracle, n, w, h, scale, f16, kw):
             pairs1, rounds1 = fs1.n_pairs, fs1.rounds
             many = plugin.render_view(hnd, many_s, view, fmt=fmt)
             fs2 = plugin.frame_stats()
-            assert rounds1 == 1 and fs2.rounds == 6
+            assert rounds1 == 1 and fs2.rounds > 1
             assert fs2.n_visible == fs1.n_visible and fs2.n_pairs <= pairs1
             assert np.array_equal(one.view(np.uint8), many.view(np.uint8)), fmt
             if fs2.tiles_saturated < fs2.tiles_x * fs2.tiles_y:
@@ -227,7 +227,7 @@ def test_binning_rounds_saturation_and_async(plugin):
                 assert p2.sync()
         fs = p2.frame_stats()
         pairs_rounds, sat = fs.n_pairs, fs.tiles_saturated
-        assert fs.rounds == 6 and sat == fs.tiles_x * fs.tiles_y
+        assert fs.rounds > 1 and sat == fs.tiles_x * fs.tiles_y
         ref = p2.render_view(hnd, one_s, view, fmt="rgba32f")
         assert np.array_equal(out, ref)
         assert pairs_rounds < p2.frame_stats().n_pairs // 2
