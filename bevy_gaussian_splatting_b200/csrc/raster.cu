@@ -60,7 +60,9 @@ __device__ __forceinline__ void issue_entries(const uint32_t* tile_entries, uint
 
 __device__ __forceinline__ float linear_to_srgb(float c) {
     c = fminf(fmaxf(c, 0.0f), 1.0f);
-    return c <= 0.0031308f ? 12.92f * c : 1.055f * powf(c, 1.0f / 2.4f) - 0.055f;
+    // __powf = ex2.approx(lg2.approx(c) / 2.4): ~1e-6 relative, far below the 8-bit quantisation step (the full
+    // powf was 7 % of the kernel's instructions)
+    return c <= 0.0031308f ? 12.92f * c : 1.055f * __powf(c, 1.0f / 2.4f) - 0.055f;
 }
 
 // shared-memory layout (byte offsets from one base so the hot loop needs a single address register)
@@ -96,6 +98,7 @@ raster_kernel(const SplatRec* __restrict__ recs, const float4* __restrict__ extr
     const int px = wx0 + (lane & 7), py = wy0 + (lane >> 3);
     const bool inside = px < W && py < H;
     const float fx = (float)px + 0.5f, fy = (float)py + 0.5f;
+    const float rcx = (float)wx0 + 4.0f, rcy = (float)wy0 + 2.0f;   // centre of the warp's pixel centres
     const uint2 range = ranges[tile];
 
     const uint32_t a_ent = (uint32_t)__cvta_generic_to_shared(&s_ent[0][0]);
@@ -161,19 +164,82 @@ raster_kernel(const SplatRec* __restrict__ recs, const float4* __restrict__ extr
                     const uint32_t bx = __float_as_uint(q.z), by = __float_as_uint(q.w);
                     hit = !((int)(bx >> 16) < wx0 || (int)(bx & 0xFFFFu) > wx0 + 7 || (int)(by >> 16) < wy0 ||
                             (int)(by & 0xFFFFu) > wy0 + 3);
+                    if (MODE == 0 && hit) {
+                        // separating-axis test of the splat's quad (|u| <= 1, |v| <= 1) against the warp's pixel
+                        // centres [wx0 + .5, wx0 + 7.5] x [wy0 + .5, wy0 + 3.5]: the bbox of a slanted quad passes
+                        // many warps none of whose pixels it covers.  Conservative: the slack (1e-5 of the terms'
+                        // magnitudes) is ~100x the rounding error of the per-pixel u, v; NaN/inf never cull.
+                        const float4 p = s_q0[j];
+                        const float dxc = rcx - p.x, dyc = rcy - p.y;
+                        const float aux = fabsf(p.z), auy = fabsf(p.w), avx = fabsf(q.x), avy = fabsf(q.y);
+                        const float uc = fabsf(p.z * dxc + p.w * dyc), vc = fabsf(q.x * dxc + q.y * dyc);
+                        const float ur = aux * 3.5f + auy * 1.5f, vr = avx * 3.5f + avy * 1.5f;
+                        const float um = aux * fabsf(dxc) + auy * fabsf(dyc) + ur, vm = avx * fabsf(dxc) + avy * fabsf(dyc) + vr;
+                        if (uc - ur > 1.0f + 1e-5f * um || vc - vr > 1.0f + 1e-5f * vm) hit = false;
+                    }
                 }
                 const uint32_t m = __ballot_sync(0xffffffffu, hit);
-                if (hit) s_list[nl + __popc(m & lanemask_lt())] = (unsigned short)(j * 16u);
+                if (hit) s_list[nl + __popc(m & lanemask_lt())] = (unsigned short)(a_base + j * 16u);   // shared address of q0[j]
                 nl += __popc(m);
             }
             __syncwarp();
         }
-        if (!(T < T_STOP)) {
+        if (MODE == 0) {
+            // two candidates per iteration: one 32-bit load brings both list entries, the four record loads and both
+            // coverage tests are independent (ILP), loop control is paid once; blending stays strictly in list order
+            if (!(T < T_STOP)) {
+                const uint32_t a_end = a_list + nl * 2u;
+                uint32_t a_it = a_list;
+                auto blend = [&](uint32_t a_rec, float u, float v) {
+                    float4 q2; float e;
+                    const float qd = __fmaf_rn(v, v, __fmul_rn(u, u));
+                    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4+8192];" : "=f"(q2.x), "=f"(q2.y), "=f"(q2.z), "=f"(q2.w) : "r"(a_rec));
+                    // exp(-4.5 qd) = 2^(qd * -4.5 log2 e); qd <= 2 so the argument stays >= -13 (no range fix-up)
+                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(qd * -6.492127684f));
+                    const float a = fminf(e * q2.w, 0.999f);
+                    const float w = a * T;
+                    cr = fmaf(w, q2.x, cr); cg = fmaf(w, q2.y, cg); cb = fmaf(w, q2.z, cb);
+                    T = fmaf(-a, T, T);
+                };
+                bool alive = true;
+                for (; a_it + 2u < a_end; a_it += 4u) {
+                    uint32_t two;
+                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(two) : "r"(a_it));
+                    const uint32_t ra = two & 0xFFFFu, rb = two >> 16;
+                    float4 pa, pb; float2 sa, sb;
+                    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(pa.x), "=f"(pa.y), "=f"(pa.z), "=f"(pa.w) : "r"(ra));
+                    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(pb.x), "=f"(pb.y), "=f"(pb.z), "=f"(pb.w) : "r"(rb));
+                    asm volatile("ld.shared.v2.f32 {%0,%1}, [%2+4096];" : "=f"(sa.x), "=f"(sa.y) : "r"(ra));
+                    asm volatile("ld.shared.v2.f32 {%0,%1}, [%2+4096];" : "=f"(sb.x), "=f"(sb.y) : "r"(rb));
+                    const float dxa = __fsub_rn(fx, pa.x), dya = __fsub_rn(fy, pa.y);
+                    const float dxb = __fsub_rn(fx, pb.x), dyb = __fsub_rn(fy, pb.y);
+                    const float ua = __fmaf_rn(pa.w, dya, __fmul_rn(pa.z, dxa)), va = __fmaf_rn(sa.y, dya, __fmul_rn(sa.x, dxa));
+                    const float ub = __fmaf_rn(pb.w, dyb, __fmul_rn(pb.z, dxb)), vb = __fmaf_rn(sb.y, dyb, __fmul_rn(sb.x, dxb));
+                    if (fabsf(ua) <= 1.0f && fabsf(va) <= 1.0f) {
+                        blend(ra, ua, va);
+                        if (T < T_STOP) { alive = false; break; }
+                    }
+                    if (fabsf(ub) <= 1.0f && fabsf(vb) <= 1.0f) {
+                        blend(rb, ub, vb);
+                        if (T < T_STOP) { alive = false; break; }
+                    }
+                }
+                if (alive && a_it != a_end) {   // odd tail
+                    uint32_t ra;
+                    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(ra) : "r"(a_it));
+                    float4 pa; float2 sa;
+                    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(pa.x), "=f"(pa.y), "=f"(pa.z), "=f"(pa.w) : "r"(ra));
+                    asm volatile("ld.shared.v2.f32 {%0,%1}, [%2+4096];" : "=f"(sa.x), "=f"(sa.y) : "r"(ra));
+                    const float dxa = __fsub_rn(fx, pa.x), dya = __fsub_rn(fy, pa.y);
+                    const float ua = __fmaf_rn(pa.w, dya, __fmul_rn(pa.z, dxa)), va = __fmaf_rn(sa.y, dya, __fmul_rn(sa.x, dxa));
+                    if (fabsf(ua) <= 1.0f && fabsf(va) <= 1.0f) blend(ra, ua, va);
+                }
+            }
+        } else if (!(T < T_STOP)) {
             const uint32_t a_end = a_list + nl * 2u;
             for (uint32_t a_it = a_list; a_it != a_end; a_it += 2u) {
-                uint32_t off;
-                asm volatile("ld.shared.u16 %0, [%1];" : "=r"(off) : "r"(a_it));
-                const uint32_t a_rec = a_base + off;
+                uint32_t a_rec;
+                asm volatile("ld.shared.u16 %0, [%1];" : "=r"(a_rec) : "r"(a_it));
                 float4 q0; float2 q1;
                 asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(q0.x), "=f"(q0.y), "=f"(q0.z), "=f"(q0.w) : "r"(a_rec));
                 asm volatile("ld.shared.v2.f32 {%0,%1}, [%2+4096];" : "=f"(q1.x), "=f"(q1.y) : "r"(a_rec));
