@@ -32,7 +32,7 @@ METRIC = "rendered Msplats/sec @1080p, 6M-gaussian cloud"
 N_GAUSSIANS = 6_000_000
 WIDTH, HEIGHT = 1920, 1080
 GLOBAL_SCALE = 0.02
-FRAMES_IN_FLIGHT = 2
+FRAMES_IN_FLIGHT = int(os.environ.get("BGS_FRAMES_IN_FLIGHT", "3"))   # contexts sharing the cloud (tuning knob)
 WORKLOAD = ("C3: 6M random_gaussians (seed 0), f16 planar 128 B/gaussian, 1920x1080, global_scale=0.02 "
             "(Mip-NeRF-360-scale), headless camera (0,1.5,5) / one orbit view per GPU")
 

@@ -511,6 +511,8 @@ bgs_status bgs_render(bgs_context* c, const bgs_cloud* cloud, const bgs_view* vi
     fc.adaptive = st->opacity_adaptive_radius; fc.draw_mode = st->draw_mode;
     fc.Wi = W; fc.Hi = H; fc.tiles_x = tiles_x; fc.tiles_y = tiles_y;
     fc.n_cloud = n;
+    static const float kIdentity[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    fc.model_identity = memcmp(uni->transform, kIdentity, 64) == 0 ? 1u : 0u;   // (-0.0 entries take the general path)
 
     bgs_status s = ensure_cloud_scratch(c, n);
     if (s != BGS_OK) return s;

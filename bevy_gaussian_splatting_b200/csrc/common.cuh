@@ -27,6 +27,7 @@ struct FrameConsts {
     uint32_t gaussian_mode, rasterize_mode, aabb, adaptive, draw_mode;
     int Wi, Hi, tiles_x, tiles_y;
     uint32_t n_cloud;           // gaussians in the cloud
+    uint32_t model_identity;    // CloudUniform.transform is exactly the identity (key-gen skips the multiply)
 };
 
 // Projected splat record, 48 B, stored by front-to-back rank.

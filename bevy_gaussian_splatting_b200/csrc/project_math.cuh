@@ -49,6 +49,44 @@ __device__ __forceinline__ KeyOut key_of(const FrameConsts& c, float px, float p
     return k;
 }
 
+// Key-gen's version of key_of: the SAME key and the SAME visibility decision, cheaper.
+//  * identity model matrix (the common case): M*(p,1) == p bit for bit when p is finite (x*1 + y*0 + z*0 + 0), so
+//    the multiply is skipped for finite positions;
+//  * the three IEEE divisions of world_to_clip only feed the frustum test here: one approximate reciprocal
+//    (|error| < 4e-7 relative) decides every gaussian whose ndc is not within 1e-4 of a frustum bound; the few that
+//    are fall back to the exact divisions.  Denominators outside [1e-30, 1e30] (rcp.approx flushes) also fall back.
+__device__ __forceinline__ uint32_t key_of_fast(const FrameConsts& c, float px, float py, float pz, bool& visible) {
+    float pw[4];
+    if (c.model_identity && (fabsf(px) + fabsf(py)) + fabsf(pz) < __uint_as_float(0x7F800000u)) {
+        pw[0] = px; pw[1] = py; pw[2] = pz;
+    } else {
+        mat4_point(c.model, px, py, pz, pw);
+    }
+    float cl[4];
+    mat4_point(c.clip_from_world, pw[0], pw[1], pw[2], cl);
+    const float den = cl[3] + 0.000000001f;
+    float rc;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(den));
+    const float ax = fabsf(cl[0] * rc), ay = fabsf(cl[1] * rc), z = cl[2] * rc;
+    const float ad = fabsf(den);
+    const bool sure_in = ax < 1.0999f && ay < 1.0999f && z > 1e-6f && z < 0.9999f;
+    const bool sure_out = ax > 1.1001f || ay > 1.1001f || z < -1e-6f || z > 1.0001f;
+    const bool den_ok = ad > 1e-30f && ad < 1e30f;
+    bool vis;
+    if (den_ok && (sure_in || sure_out)) {
+        vis = sure_in;
+    } else {
+        const float nx = cl[0] / den, ny = cl[1] / den, nz = cl[2] / den;
+        vis = fabsf(nx) < 1.1f && fabsf(ny) < 1.1f && fabsf(nz - 0.5f) < 0.5f;
+    }
+    visible = vis;
+    const float dx = pw[0] - c.cam[0], dy = pw[1] - c.cam[1], dz = pw[2] - c.cam[2];
+    const float d2 = (dx * dx + dy * dy) + dz * dz;
+    uint32_t key = 0xFFFFFFFFu;
+    if (vis) key = 0xFFFFFFFFu - __float_as_uint(d2);
+    return key >> c.key_shift;
+}
+
 // Fixed-series natural log in f64 (the policy replacement for WGSL log(), gaussian.wgsl:229):
 // x = m 2^e, m in [sqrt(1/2), sqrt 2); s = (m-1)/(m+1); ln x = e ln2 + 2 s P(s^2), rounded to f32.
 __device__ __forceinline__ float det_ln(float xf) {

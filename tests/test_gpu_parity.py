@@ -236,6 +236,52 @@ def test_binning_rounds_saturation_and_async(plugin):
         p2.destroy()
 
 
+@pytest.mark.parametrize("with_model", [False, True])
+def test_frustum_boundary_visibility_bit_exact(plugin, oracle, with_model):
+    """Key-gen decides visibility with one approximate reciprocal and falls back to the exact IEEE divisions near the
+    frustum bounds (|ndc.x|, |ndc.y| = 1.1, ndc.z = 0 / 1): gaussians placed within a few ulp of every bound, on both
+    sides, must be classified exactly like the oracle's divisions do (transform.wgsl:5-14)."""
+    view = B.orbit_view(1, 8, 320, 200)
+    VP = view.clip_from_world.astype(np.float64)          # row-major (row, col)
+    rng = np.random.default_rng(3)
+    m = np.eye(4, dtype=np.float32)
+    if with_model:
+        m[:3, :3] = np.array([[0.8, 0.1, 0.0], [-0.1, 0.9, 0.2], [0.05, -0.2, 1.1]], np.float32)
+        m[:3, 3] = [0.3, -0.2, 0.5]
+    Minv = np.linalg.inv(m.astype(np.float64))
+    pts = []
+    VPinv = np.linalg.inv(VP)
+    for _ in range(6000):
+        # an interior point of the frustum in NDC with ONE coordinate put on its bound +- a few ulp, unprojected
+        # (f64) and rounded to f32: the rounding alone scatters the points over both sides of the bound
+        nd = np.array([rng.uniform(-0.9, 0.9), rng.uniform(-0.9, 0.9), 0.1 / rng.uniform(0.5, 30.0), 1.0])
+        row = int(rng.integers(0, 3))
+        t = [1.1, -1.1][int(rng.integers(0, 2))] if row < 2 else 1.0
+        nd[row] = t * (1.0 + float(rng.integers(-6, 7)) * 2.0 ** -23)
+        w = VPinv @ nd
+        pts.append((Minv @ (w / w[3]))[:3])
+    pts = np.asarray(pts, np.float32)
+    pts = pts[np.isfinite(pts).all(1) & (np.abs(pts).max(1) < 1e4)]
+    n = len(pts)
+    cloud = B.random_gaussians_3d_seeded(n, 1)
+    cloud.position_visibility[:, :3] = pts
+    s = B.CloudSettings(global_scale=0.05)
+    tr = B.CloudTransform(m) if with_model else None
+    h = plugin.add_cloud(cloud)
+    try:
+        plugin.render_view(h, s, view, transform=tr, to_host=False)
+        u = plugin.cloud_uniform(s, tr)
+        keys = oracle.keygen(cloud.position_visibility, view.to_abi(), u, 32)
+        vis = keys != 0xFFFFFFFF
+        assert 0.15 * n < vis.sum() < 0.85 * n, "the construction must straddle the bounds"
+        sk, si = oracle.radix_sort(keys, 32)
+        got = plugin.sorted_entries()
+        assert plugin.frame_stats().n_visible == int(vis.sum())
+        assert np.array_equal(got[:, 0], sk) and np.array_equal(got[:, 1], si)
+    finally:
+        h.destroy()
+
+
 def test_output_formats_agree(plugin):
     cloud = B.random_gaussians_3d_seeded(30000, 9)
     view = B.headless_view(320, 192)
