@@ -39,6 +39,8 @@ class bgs_cloud_uniform(C.Structure):
         ("global_scale", C.c_float),
         ("color_space", C.c_uint32),
         ("time", C.c_float),
+        ("aabb_min", C.c_float * 4),
+        ("aabb_max", C.c_float * 4),
     ]
 
 

@@ -479,8 +479,8 @@ bgs_status bgs_render(bgs_context* c, const bgs_cloud* cloud, const bgs_view* vi
         return fail(c, BGS_EINVAL, "render: radix_sort_depth_bits must be 16, 24 or 32");
     if (st->gaussian_mode != BGS_GAUSSIAN_3D && st->gaussian_mode != BGS_GAUSSIAN_2D)
         return fail(c, BGS_EINVAL, "render: gaussian_mode %u not supported (Gaussian4d is out of scope)", st->gaussian_mode);
-    if (st->rasterize_mode > BGS_RASTERIZE_NORMAL)
-        return fail(c, BGS_EINVAL, "render: rasterize_mode %u not supported (Color, Depth, Normal are)", st->rasterize_mode);
+    if (st->rasterize_mode > BGS_RASTERIZE_POSITION)
+        return fail(c, BGS_EINVAL, "render: rasterize_mode %u not supported (Color, Depth, Normal, Position are)", st->rasterize_mode);
     if (st->draw_mode > BGS_DRAW_HIGHLIGHT_SELECTED) return fail(c, BGS_EINVAL, "render: bad draw_mode");
     const int W = (int)view->viewport[2], H = (int)view->viewport[3];
     if (W <= 0 || H <= 0 || W > 65535 || H > 65535) return fail(c, BGS_EINVAL, "render: viewport %dx%d out of range", W, H);
@@ -511,6 +511,7 @@ bgs_status bgs_render(bgs_context* c, const bgs_cloud* cloud, const bgs_view* vi
     fc.adaptive = st->opacity_adaptive_radius; fc.draw_mode = st->draw_mode;
     fc.Wi = W; fc.Hi = H; fc.tiles_x = tiles_x; fc.tiles_y = tiles_y;
     fc.n_cloud = n;
+    memcpy(fc.aabb_min, uni->aabb_min, 12); memcpy(fc.aabb_max, uni->aabb_max, 12);
     static const float kIdentity[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
     fc.model_identity = memcmp(uni->transform, kIdentity, 64) == 0 ? 1u : 0u;   // (-0.0 entries take the general path)
 

@@ -28,6 +28,7 @@ struct FrameConsts {
     int Wi, Hi, tiles_x, tiles_y;
     uint32_t n_cloud;           // gaussians in the cloud
     uint32_t model_identity;    // CloudUniform.transform is exactly the identity (key-gen skips the multiply)
+    float aabb_min[3], aabb_max[3];   // CloudUniform.min / .max (RasterizeMode::Position)
 };
 
 // Projected splat record, 48 B, stored by front-to-back rank.

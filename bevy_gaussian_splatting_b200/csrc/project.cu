@@ -441,6 +441,10 @@ project_kernel(const float4* __restrict__ pos, const void* __restrict__ sh_p, co
                 rgb[1] = 1.0f - fabsf(nd - 0.5f) * 2.0f;
                 rgb[2] = 1.0f - t2 * t2 * (3.0f - 2.0f * t2);
                 }
+            } else if (fc.rasterize_mode == BGS_RASTERIZE_POSITION) {
+                // gaussian.wgsl:375-376: (transformed_position - min) / (max - min)
+#pragma unroll
+                for (int cc = 0; cc < 3; ++cc) rgb[cc] = (k.pw[cc] - fc.aabb_min[cc]) / (fc.aabb_max[cc] - fc.aabb_min[cc]);
             } else if (fc.rasterize_mode == BGS_RASTERIZE_NORMAL) {
                 // gaussian.wgsl:350-368
                 float SR[3], Ln[3], wn[4];

@@ -45,6 +45,20 @@ class PlanarGaussian3d:
                                 self.scale_opacity[:n])
 
     # ---- f16 planar layout (src/gaussian/f16.rs:30-56,244-263; planar.wgsl:117-176) -----------------
+    def compute_aabb(self) -> tuple[np.ndarray, np.ndarray]:
+        """The entity `Aabb` as the render world sees it: `compute_aabb` (src/gaussian/interface.rs:22-66: positions
+        +- 0.1) -> `Aabb {center, half_extents}` (src/gaussian/cloud.rs:45-62) -> `aabb.min()` / `aabb.max()`
+        (center -+ half_extents, src/render/mod.rs:1070-1071), every step in f32 like glam."""
+        p = self.position_visibility[:, :3]
+        off = np.float32(0.1)
+        # (min over (p - 0.1) == min(p) - 0.1: f32 subtraction of a constant is monotone)
+        lo = (p.min(0) - off).astype(np.float32) if len(p) else np.full(3, np.inf, np.float32)
+        hi = (p.max(0) + off).astype(np.float32) if len(p) else np.full(3, -np.inf, np.float32)
+        two = np.float32(2.0)
+        center = ((lo + hi).astype(np.float32) / two).astype(np.float32)
+        half = ((hi - lo).astype(np.float32) / two).astype(np.float32)
+        return (center - half).astype(np.float32), (center + half).astype(np.float32)
+
     def pack_f16(self) -> tuple[np.ndarray, np.ndarray]:
         """-> (sh_packed (n,24) u32, rot_scale_opacity (n,4) u32); pack(upper, lower) = upper<<16 | lower."""
         def bits(a):

@@ -41,6 +41,7 @@ class PlanarGaussian3dHandle:
         self._lib = plugin._lib
         self.n = len(cloud)
         self.f16 = f16
+        self.aabb = cloud.compute_aabb()        # the entity's Aabb (calculate_bounds, src/gaussian/cloud.rs:45-62)
         self._h = C.c_void_p()
         if f16:
             sh_p, rso = cloud.pack_f16()
@@ -87,8 +88,12 @@ class GaussianSplattingPlugin:
             raise abi.BgsError(st, (self._lib.bgs_last_error(self._ctx) or b"").decode())
 
     @staticmethod
-    def cloud_uniform(settings: CloudSettings, transform: CloudTransform | None = None) -> abi.bgs_cloud_uniform:
+    def cloud_uniform(settings: CloudSettings, transform: CloudTransform | None = None, aabb=None) -> abi.bgs_cloud_uniform:
+        """extract_gaussians (src/render/mod.rs:1056-1072); `aabb` = (min, max) of the entity's Aabb."""
         u = abi.bgs_cloud_uniform()
+        lo, hi = aabb if aabb is not None else (np.zeros(3, np.float32), np.ones(3, np.float32))
+        u.aabb_min[:] = [float(lo[0]), float(lo[1]), float(lo[2]), 1.0]
+        u.aabb_max[:] = [float(hi[0]), float(hi[1]), float(hi[2]), 1.0]
         m = (transform.matrix if transform is not None else np.eye(4, dtype=np.float32)).astype(np.float32)
         u.transform[:] = m.T.reshape(-1).tolist()
         u.global_opacity = settings.global_opacity
@@ -108,12 +113,12 @@ class GaussianSplattingPlugin:
             return None
         code, dtype, ch = self.FORMATS[fmt]
         v = view.to_abi()
-        key = (dataclasses.astuple(settings), None if transform is None else transform.matrix.tobytes(), asynchronous)
+        key = (dataclasses.astuple(settings), None if transform is None else transform.matrix.tobytes(), asynchronous, id(handle))
         if getattr(self, "_us_cache", (None,))[0] != key:
             s_ = settings.to_abi()
             if asynchronous:
                 s_.flags |= abi.BGS_FLAG_ASYNC
-            self._us_cache = (key, self.cloud_uniform(settings, transform), s_)
+            self._us_cache = (key, self.cloud_uniform(settings, transform, handle.aabb), s_)
         _, u, s = self._us_cache
         if to_host:
             if out is None:

@@ -24,10 +24,11 @@ class GaussianMode(enum.IntEnum):  # settings.rs:17-22 (Gaussian4d is out of sco
     Gaussian3d = 1
 
 
-class RasterizeMode(enum.IntEnum):  # settings.rs:38-48 (Color/Depth/Normal are on the path)
+class RasterizeMode(enum.IntEnum):  # settings.rs:38-48 (Color/Depth/Normal/Position are on the path)
     Color = 0
     Depth = 1
     Normal = 2
+    Position = 3
 
 
 class RadixSortDepthBits(enum.IntEnum):  # settings.rs:50-77

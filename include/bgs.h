@@ -52,11 +52,13 @@ typedef struct {
     float global_scale;
     uint32_t color_space; /* GaussianColorSpace: 0 SrgbRec709Display, 1 LinRec709Display */
     float time;
+    float aabb_min[4];    /* CloudUniform.min / .max = the entity's Aabb.min()/.max() extended with 1.0 */
+    float aabb_max[4];    /* (render/mod.rs:1070-1071); read by RasterizeMode::Position only */
 } bgs_cloud_uniform;
 
 /* CloudSettings / CloudPipelineKey (src/gaussian/settings.rs:90-133, render/mod.rs:898-909). */
 enum { BGS_GAUSSIAN_2D = 0, BGS_GAUSSIAN_3D = 1 };
-enum { BGS_RASTERIZE_COLOR = 0, BGS_RASTERIZE_DEPTH = 1, BGS_RASTERIZE_NORMAL = 2 };
+enum { BGS_RASTERIZE_COLOR = 0, BGS_RASTERIZE_DEPTH = 1, BGS_RASTERIZE_NORMAL = 2, BGS_RASTERIZE_POSITION = 3 };
 enum { BGS_DRAW_ALL = 0, BGS_DRAW_SELECTED = 1, BGS_DRAW_HIGHLIGHT_SELECTED = 2 };
 enum {
     BGS_FLAG_SORT_ALL = 1u, /* sort all N entries like the reference (culled keyed 0xFFFFFFFF)

@@ -24,7 +24,7 @@ namespace bgs {
 
 enum class DrawMode : uint32_t { All = 0, Selected = 1, HighlightSelected = 2 };
 enum class GaussianMode : uint32_t { Gaussian2d = 0, Gaussian3d = 1 };
-enum class RasterizeMode : uint32_t { Color = 0, Depth = 1, Normal = 2 };
+enum class RasterizeMode : uint32_t { Color = 0, Depth = 1, Normal = 2, Position = 3 };
 enum class RadixSortDepthBits : uint32_t { Bits16 = 16, Bits24 = 24, Bits32 = 32 };
 enum class GaussianColorSpace : uint32_t { SrgbRec709Display = 0, LinRec709Display = 1 };
 
@@ -64,6 +64,19 @@ struct PlanarGaussian3d {   // four planes, binding order (planar_3d.rs:45-54)
     std::vector<float> rotation;              // n*4, (w, x, y, z)
     std::vector<float> scale_opacity;         // n*4
     size_t len() const { return position_visibility.size() / 4; }
+    // the entity Aabb's min()/max(): compute_aabb (interface.rs:22-66, positions +- 0.1) -> Aabb {center, half_extents}
+    // (cloud.rs:45-62) -> center -+ half_extents (render/mod.rs:1070-1071), all in f32
+    void compute_aabb(float mn[3], float mx[3]) const {
+        for (int k = 0; k < 3; ++k) {
+            float lo = INFINITY, hi = -INFINITY;
+            for (size_t i = 0; i < len(); ++i) {
+                const float p = position_visibility[4 * i + k];
+                lo = std::fmin(lo, p - 0.1f); hi = std::fmax(hi, p + 0.1f);
+            }
+            const float center = (lo + hi) / 2.0f, half = (hi - lo) / 2.0f;
+            mn[k] = center - half; mx[k] = center + half;
+        }
+    }
 };
 
 // splitmix64-based counter PRNG: this repo's generator for the C++ host (the reference's ChaCha stream is not
@@ -145,7 +158,11 @@ public:
     PlanarGaussian3dHandle() = default;
     PlanarGaussian3dHandle(const PlanarGaussian3dHandle&) = delete;
     PlanarGaussian3dHandle& operator=(const PlanarGaussian3dHandle&) = delete;
-    PlanarGaussian3dHandle(PlanarGaussian3dHandle&& o) noexcept : h_(o.h_), n_(o.n_) { o.h_ = nullptr; }
+    PlanarGaussian3dHandle(PlanarGaussian3dHandle&& o) noexcept : h_(o.h_), n_(o.n_) {
+        std::memcpy(aabb_min_, o.aabb_min_, 12); std::memcpy(aabb_max_, o.aabb_max_, 12); o.h_ = nullptr;
+    }
+    const float* aabb_min() const { return aabb_min_; }
+    const float* aabb_max() const { return aabb_max_; }
     ~PlanarGaussian3dHandle() { if (h_) bgs_cloud_destroy(h_); }
     bgs_cloud* get() const { return h_; }
     uint32_t len() const { return n_; }
@@ -153,6 +170,7 @@ private:
     friend class GaussianSplattingPlugin;
     bgs_cloud* h_ = nullptr;
     uint32_t n_ = 0;
+    float aabb_min_[3] = {0, 0, 0}, aabb_max_[3] = {1, 1, 1};
 };
 
 class GaussianSplattingPlugin {
@@ -168,6 +186,7 @@ public:
     PlanarGaussian3dHandle add_cloud(const PlanarGaussian3d& c) {   // asset prepare
         PlanarGaussian3dHandle h;
         h.n_ = (uint32_t)c.len();
+        c.compute_aabb(h.aabb_min_, h.aabb_max_);
         check(bgs_cloud_upload_f32(ctx_, h.n_, c.position_visibility.data(), c.spherical_harmonic.data(), c.rotation.data(),
                                    c.scale_opacity.data(), &h.h_));
         return h;
@@ -177,6 +196,8 @@ public:
         std::memcpy(u.transform, transform.m, 64);
         u.global_opacity = s.global_opacity; u.global_scale = s.global_scale;
         u.color_space = (uint32_t)s.color_space; u.time = s.time;
+        u.aabb_min[3] = u.aabb_max[3] = 1.0f;
+        for (int k = 0; k < 3; ++k) u.aabb_max[k] = 1.0f;
         return u;
     }
     // One view of one cloud.  Returns false when the frame is skipped (warm-up camera / not ready), like the
@@ -184,7 +205,8 @@ public:
     bool render_view(const PlanarGaussian3dHandle& cloud, const CloudSettings& settings, const bgs_view& view, void* out_rgba,
                      uint32_t format = BGS_FORMAT_RGBA8_SRGB, const GaussianCamera& camera = {}, bool out_is_device = false) {
         if (camera.warmup) return false;
-        const bgs_cloud_uniform u = cloud_uniform(settings);
+        bgs_cloud_uniform u = cloud_uniform(settings);
+        std::memcpy(u.aabb_min, cloud.aabb_min(), 12); std::memcpy(u.aabb_max, cloud.aabb_max(), 12);
         const bgs_settings s = settings.to_abi();
         const bgs_status st = bgs_render(ctx_, cloud.get(), &view, &u, &s, out_rgba, format, out_is_device ? 1 : 0);
         if (st == BGS_NOT_READY) return false;

@@ -397,6 +397,11 @@ void project_one(const Ctx& C, const float* p4, const float* sh, const float* q,
         const float l = std::sqrt(((wn[0] * wn[0] + wn[1] * wn[1]) + wn[2] * wn[2]) + wn[3] * wn[3]);
         for (int c = 0; c < 3; ++c) rgb[c] = 0.5f * (wn[c] / l + 1.0f);
     }
+    else if (s.rasterize_mode == 3u) {
+        // gaussian.wgsl:375-376 RASTERIZE_POSITION: (transformed_position - min) / (max - min); min/max are the
+        // entity Aabb's (cloud-space) corners while the position is the world-space one -- kept literal
+        for (int c = 0; c < 3; ++c) rgb[c] = (k.pw[c] - u.aabb_min[c]) / (u.aabb_max[c] - u.aabb_min[c]);
+    }
     // rasterize_mode == 1 (Depth) is filled by the caller: it needs the sorted order.
     o.r = rgb[0]; o.g = rgb[1]; o.b = rgb[2];
     if (s.draw_mode == 2u && p4[3] > 0.5f) {   // gaussian.wgsl:423-427 HIGHLIGHT_SELECTED

@@ -35,10 +35,11 @@ typedef struct {
     float global_opacity, global_scale;
     uint32_t color_space; /* 0 = SrgbRec709Display (decode sRGB->linear), 1 = LinRec709Display */
     float time;
+    float aabb_min[4], aabb_max[4]; /* CloudUniform.min / .max (render/mod.rs:1070-1071) */
 } orc_uniform;
 typedef struct {
     uint32_t gaussian_mode;           /* 0 = Gaussian2d, 1 = Gaussian3d */
-    uint32_t rasterize_mode;          /* 0 = Color, 1 = Depth, 2 = Normal */
+    uint32_t rasterize_mode;          /* 0 = Color, 1 = Depth, 2 = Normal, 3 = Position */
     uint32_t aabb;                    /* 0 = USE_OBB, 1 = USE_AABB */
     uint32_t opacity_adaptive_radius; /* bool */
     uint32_t draw_mode;               /* 0 = All, 1 = Selected, 2 = HighlightSelected */

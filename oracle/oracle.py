@@ -22,7 +22,7 @@ class orc_view(C.Structure):
 
 class orc_uniform(C.Structure):
     _fields_ = [("transform", C.c_float * 16), ("global_opacity", C.c_float), ("global_scale", C.c_float),
-                ("color_space", C.c_uint32), ("time", C.c_float)]
+                ("color_space", C.c_uint32), ("time", C.c_float), ("aabb_min", C.c_float * 4), ("aabb_max", C.c_float * 4)]
 
 
 class orc_settings(C.Structure):

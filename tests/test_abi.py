@@ -28,9 +28,9 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_struct_layouts_match_header():
-    # bgs_view: 3*16 + 3 + 4 floats; bgs_cloud_uniform: 16 floats + 2 floats + u32 + float; bgs_settings: 8 u32
+    # bgs_view: 3*16 + 3 + 4 floats; bgs_cloud_uniform: 16 floats + 2 floats + u32 + float + 2 x vec4; bgs_settings: 8 u32
     assert C.sizeof(abi.bgs_view) == (48 + 3 + 4) * 4
-    assert C.sizeof(abi.bgs_cloud_uniform) == 20 * 4
+    assert C.sizeof(abi.bgs_cloud_uniform) == 28 * 4 and abi.bgs_cloud_uniform.aabb_min.offset == 80
     assert C.sizeof(abi.bgs_settings) == 32
     assert C.sizeof(abi.bgs_frame_stats) == 40 and abi.bgs_frame_stats.rounds.offset == 32
     assert abi.bgs_frame_stats.n_pairs.offset == 8

@@ -29,7 +29,7 @@ def check_against_oracle(plugin, oracle, cloud, settings, view, f16=False, pixel
     try:
         img = plugin.render_view(h, settings, view, fmt="rgba32f")
         oc = cloud.rounded_to_f16() if f16 else cloud
-        u = _uniform(settings)
+        u = plugin.cloud_uniform(settings, None, h.aabb)
         bits = int(settings.radix_sort_depth_bits)
         keys = oracle.keygen(oc.position_visibility, view.to_abi(), u, bits)
         sk, si = oracle.radix_sort(keys, bits)
@@ -101,7 +101,8 @@ def test_parity_settings_variants(plugin, oracle):
                dict(rasterize_mode=B.RasterizeMode.Normal), dict(draw_mode=B.DrawMode.HighlightSelected),
                dict(rasterize_mode=B.RasterizeMode.Depth), dict(rasterize_mode=B.RasterizeMode.Depth, sort_all=True),
                dict(rasterize_mode=B.RasterizeMode.Depth, gaussian_mode=B.GaussianMode.Gaussian2d, aabb=True),
-               dict(rasterize_mode=B.RasterizeMode.Normal, gaussian_mode=B.GaussianMode.Gaussian2d)):
+               dict(rasterize_mode=B.RasterizeMode.Normal, gaussian_mode=B.GaussianMode.Gaussian2d),
+               dict(rasterize_mode=B.RasterizeMode.Position), dict(rasterize_mode=B.RasterizeMode.Position, sort_all=True)):
         s = B.CloudSettings(global_scale=0.2, **kw)
         check_against_oracle(plugin, oracle, cloud, s, view)
 

@@ -125,6 +125,26 @@ def test_modes_aabb_2dgs_normal_depth_consistent(oracle):
         assert ref[..., :3].max() > 0.01, (gm, aabb, rm)
 
 
+def test_position_mode_and_entity_aabb(oracle):
+    """RasterizeMode::Position (gaussian.wgsl:375-376): colour = (world position - Aabb.min) / (Aabb.max - Aabb.min),
+    with the entity Aabb of compute_aabb (interface.rs:22-66: positions +- 0.1, via center/half_extents)."""
+    cloud = B.random_gaussians_3d_seeded(800, 3)
+    lo, hi = cloud.compute_aabb()
+    p = cloud.position_visibility[:, :3]
+    assert np.all(np.abs(lo - (p.min(0) - 0.1)) <= 4e-6) and np.all(np.abs(hi - (p.max(0) + 0.1)) <= 4e-6)
+    view = B.headless_view(160, 96)
+    s = B.CloudSettings(global_scale=0.3, rasterize_mode=B.RasterizeMode.Position)
+    u = B.GaussianSplattingPlugin.cloud_uniform(s, None, (lo, hi))
+    til = oracle.render_tiles(cloud, view.to_abi(), u, s.to_abi())
+    rec = oracle.project(cloud, view.to_abi(), u, s.to_abi(), til["rank_to_id"])
+    want = (p[til["rank_to_id"]] - lo) / (hi - lo)            # identity model: world position == cloud position
+    got = np.stack([rec["r"], rec["g"], rec["b"]], 1)
+    assert np.abs(got - want).max() <= 1e-6
+    assert got.min() >= 0.0 and got.max() <= 1.0
+    ref = oracle.render_ref(cloud, view.to_abi(), u, s.to_abi())
+    assert np.abs(ref - til["image"]).max() <= 1e-3
+
+
 def test_golden_fixtures(oracle):
     """Frozen oracle outputs (tests/golden/make_golden.py): keys, order, records, tile ranges, image."""
     g = np.load(os.path.join(GOLD, "c1_small.npz"))
