@@ -15,7 +15,7 @@ while time.time() - t0 < budget:
     w, h = int(rng.integers(8, 700)), int(rng.integers(8, 400))
     scale = float(10 ** rng.uniform(-2, 0.5))
     gm = B.GaussianMode(int(rng.integers(0, 2))); aabb = bool(rng.integers(0, 2))
-    rm = B.RasterizeMode(int(rng.integers(0, 3))); dm = B.DrawMode(int(rng.integers(0, 3)))
+    rm = B.RasterizeMode(int(rng.integers(0, 4))); dm = B.DrawMode(int(rng.integers(0, 3)))
     bits = B.RadixSortDepthBits(int(rng.choice([16, 24, 32])))
     f16 = bool(rng.integers(0, 2)); sort_all = bool(rng.integers(0, 4) == 0)
     s = B.CloudSettings(global_scale=scale, gaussian_mode=gm, aabb=aabb, rasterize_mode=rm, draw_mode=dm, radix_sort_depth_bits=bits,
@@ -36,7 +36,7 @@ while time.time() - t0 < budget:
     try:
         img = pl.render_view(hd, s, view, transform=tr)
         oc = cloud.rounded_to_f16() if f16 else cloud
-        u = pl.cloud_uniform(s, tr)
+        u = pl.cloud_uniform(s, tr, hd.aabb)
         keys = O.keygen(oc.position_visibility, view.to_abi(), u, int(bits))
         sk, si = O.radix_sort(keys, int(bits))
         got = pl.sorted_entries()
@@ -51,6 +51,11 @@ while time.time() - t0 < budget:
         assert err <= 1e-3, f"pixels {err} " + desc
         img2 = pl.render_view(hd, s, view, transform=tr)     # hinted second frame
         assert np.array_equal(np.isfinite(img2), fin) and float(np.abs(img2 - til["image"])[fin].max() if fin.any() else 0) <= 1e-3, "hinted " + desc
+        if not aabb:   # front-to-back binning rounds (quad-uv records): the one-round frame, bit for bit
+            import dataclasses
+            img3 = pl.render_view(hd, dataclasses.replace(s, binning_rounds=True), view, transform=tr)
+            assert pl.frame_stats().rounds > 1, "rounds " + desc
+            assert np.array_equal(img3.view(np.uint32), img.view(np.uint32)), "rounds differ " + desc
     finally:
         hd.destroy()
 print(f"fuzz ok: {it} random configurations, worst pixel L-inf {worst:.2e}")
