@@ -58,6 +58,14 @@ __device__ __forceinline__ void issue_entries(const uint32_t* tile_entries, uint
     tma_bulk_g2s(a_ent + (uint32_t)buf * ENT_WORDS * 4u, tile_entries + (base - lead), bytes, a_bar + 8u * buf);
 }
 
+// CTA -> tile: rows are visited from the middle row outwards (mid, mid-1, mid+1, ...), so the tiles launched last --
+// the ones that form the kernel's tail -- are the top / bottom rows, usually the lightest.
+__device__ __forceinline__ void centre_out_tile(int b, int tiles_x, int tiles_y, int& tile_x, int& tile_y) {
+    const int k = b / tiles_x, mid = tiles_y / 2;
+    tile_x = b - k * tiles_x;
+    tile_y = (k & 1) ? mid - (k + 1) / 2 : mid + k / 2;
+}
+
 __device__ __forceinline__ float linear_to_srgb(float c) {
     c = fminf(fmaxf(c, 0.0f), 1.0f);
     // __powf = ex2.approx(lg2.approx(c) / 2.4): ~1e-6 relative, far below the 8-bit quantisation step (the full
@@ -78,12 +86,13 @@ constexpr uint32_t SM_BYTES_2D = SM_EXTRA + 4 * RT_CHUNK * 16;
 // MODE 1: 3DGS USE_AABB conic falloff                              gaussian.wgsl:459-471
 // MODE 2: 2DGS USE_AABB ray-splat intersection                     gaussian.wgsl:441-458, gaussian_2d.wgsl:134-156
 template <int MODE>
-__global__ void __launch_bounds__(RT_THREADS)
+__global__ void __launch_bounds__(RT_THREADS, MODE == 0 ? 6 : 5)
 raster_kernel(const SplatRec* __restrict__ recs, const float4* __restrict__ extra, const uint32_t* __restrict__ tile_entries,
               const uint2* __restrict__ ranges, int W, int H, int tiles_x, void* __restrict__ out, uint32_t format) {
     __shared__ __align__(16) unsigned char s_mem[MODE == 2 ? SM_BYTES_2D : SM_BYTES];
     __shared__ __align__(16) uint32_t s_ent[2][ENT_WORDS];    // TMA destination: the tile's pair-list chunks
     __shared__ __align__(8) unsigned long long s_bar[2];
+    __shared__ __align__(8) float2 s_thr[MODE == 0 ? RT_CHUNK : 1];   // MODE 0: per staged splat cull thresholds (u, v)
     float4* s_q0 = reinterpret_cast<float4*>(s_mem + SM_Q0);
     float4* s_uv = reinterpret_cast<float4*>(s_mem + SM_UV);
     float4* s_q2 = reinterpret_cast<float4*>(s_mem + SM_Q2);
@@ -91,14 +100,16 @@ raster_kernel(const SplatRec* __restrict__ recs, const float4* __restrict__ extr
     unsigned short* s_list = reinterpret_cast<unsigned short*>(s_mem + SM_LIST) + warp * RT_CHUNK;
     const uint32_t a_base = (uint32_t)__cvta_generic_to_shared(s_mem);
     const uint32_t a_list = a_base + SM_LIST + (uint32_t)warp * RT_CHUNK * 2u;
-    const int tile = blockIdx.x;
-    const int tile_x = tile % tiles_x, tile_y = tile / tiles_x;
+    int tile_x, tile_y;
+    centre_out_tile((int)blockIdx.x, tiles_x, (int)gridDim.x / tiles_x, tile_x, tile_y);
+    const int tile = tile_y * tiles_x + tile_x;
     // warp w covers the 8x4 rectangle at ((w & 1) * 8, (w >> 1) * 4) of the tile
     const int wx0 = tile_x * TILE_PX + (warp & 1) * 8, wy0 = tile_y * TILE_PX + (warp >> 1) * 4;
     const int px = wx0 + (lane & 7), py = wy0 + (lane >> 3);
     const bool inside = px < W && py < H;
     const float fx = (float)px + 0.5f, fy = (float)py + 0.5f;
     const float rcx = (float)wx0 + 4.0f, rcy = (float)wy0 + 2.0f;   // centre of the warp's pixel centres
+    const float tcx = (float)(tile_x * TILE_PX) + 8.0f, tcy = (float)(tile_y * TILE_PX) + 8.0f;   // tile centre
     const uint2 range = ranges[tile];
 
     const uint32_t a_ent = (uint32_t)__cvta_generic_to_shared(&s_ent[0][0]);
@@ -142,9 +153,20 @@ raster_kernel(const SplatRec* __restrict__ recs, const float4* __restrict__ extr
         if ((uint32_t)t < cnt) {
             const uint32_t r = use_tma ? s_ent[buf][(base & 3u) + t] : __ldg(tile_entries + base + t);
             const float4* rp = reinterpret_cast<const float4*>(recs + r);
-            s_q0[t] = __ldg(rp);
-            s_uv[t] = __ldg(rp + 1);
+            const float4 p0 = __ldg(rp), p1 = __ldg(rp + 1);
+            s_q0[t] = p0;
+            s_uv[t] = p1;
             s_q2[t] = __ldg(rp + 2);
+            if (MODE == 0) {
+                // thresholds of the per-warp separating-axis cull below, once per splat: the quad |u| <= 1, |v| <= 1
+                // misses a warp rectangle (pixel centres within +-3.5 x +-1.5 of its centre) when |u(centre)| exceeds
+                // 1 + |ux| 3.5 + |uy| 1.5 (same for v).  Slack: 1e-5 of the largest magnitude the terms of u can take
+                // anywhere in the tile, ~100x the rounding error of the per-pixel u, v.  NaN/inf never cull.
+                const float ax = fabsf(p0.x - tcx) + 4.0f, ay = fabsf(p0.y - tcy) + 6.0f;
+                const float ur = fabsf(p0.z) * 3.5f + fabsf(p0.w) * 1.5f, vr = fabsf(p1.x) * 3.5f + fabsf(p1.y) * 1.5f;
+                const float um = fabsf(p0.z) * ax + fabsf(p0.w) * ay + ur, vm = fabsf(p1.x) * ax + fabsf(p1.y) * ay + vr;
+                s_thr[t] = make_float2(ur + 1.0f + 1e-5f * um, vr + 1.0f + 1e-5f * vm);
+            }
             if (MODE == 2) {
                 float4* s_ex = reinterpret_cast<float4*>(s_mem + SM_EXTRA);
                 const float4* ep = extra + (size_t)r * 4;
@@ -165,17 +187,13 @@ raster_kernel(const SplatRec* __restrict__ recs, const float4* __restrict__ extr
                     hit = !((int)(bx >> 16) < wx0 || (int)(bx & 0xFFFFu) > wx0 + 7 || (int)(by >> 16) < wy0 ||
                             (int)(by & 0xFFFFu) > wy0 + 3);
                     if (MODE == 0 && hit) {
-                        // separating-axis test of the splat's quad (|u| <= 1, |v| <= 1) against the warp's pixel
-                        // centres [wx0 + .5, wx0 + 7.5] x [wy0 + .5, wy0 + 3.5]: the bbox of a slanted quad passes
-                        // many warps none of whose pixels it covers.  Conservative: the slack (1e-5 of the terms'
-                        // magnitudes) is ~100x the rounding error of the per-pixel u, v; NaN/inf never cull.
+                        // separating-axis test of the splat's quad against this warp's pixel centres
+                        // [wx0 + .5, wx0 + 7.5] x [wy0 + .5, wy0 + 3.5] (thresholds staged per splat above): the bbox
+                        // of a slanted quad passes many warps none of whose pixels it covers
                         const float4 p = s_q0[j];
+                        const float2 th = s_thr[j];
                         const float dxc = rcx - p.x, dyc = rcy - p.y;
-                        const float aux = fabsf(p.z), auy = fabsf(p.w), avx = fabsf(q.x), avy = fabsf(q.y);
-                        const float uc = fabsf(p.z * dxc + p.w * dyc), vc = fabsf(q.x * dxc + q.y * dyc);
-                        const float ur = aux * 3.5f + auy * 1.5f, vr = avx * 3.5f + avy * 1.5f;
-                        const float um = aux * fabsf(dxc) + auy * fabsf(dyc) + ur, vm = avx * fabsf(dxc) + avy * fabsf(dyc) + vr;
-                        if (uc - ur > 1.0f + 1e-5f * um || vc - vr > 1.0f + 1e-5f * vm) hit = false;
+                        if (fabsf(p.z * dxc + p.w * dyc) > th.x || fabsf(q.x * dxc + q.y * dyc) > th.y) hit = false;
                     }
                 }
                 const uint32_t m = __ballot_sync(0xffffffffu, hit);
@@ -366,8 +384,9 @@ raster2_kernel(const SplatRec* __restrict__ recs, const uint32_t* __restrict__ t
     unsigned short* s_list = reinterpret_cast<unsigned short*>(s_mem + R2_LIST) + warp * RT_CHUNK;
     const uint32_t a_base = (uint32_t)__cvta_generic_to_shared(s_mem);
     const uint32_t a_list = a_base + R2_LIST + (uint32_t)warp * RT_CHUNK * 2u;
-    const int tile = blockIdx.x;
-    const int tile_x = tile % tiles_x, tile_y = tile / tiles_x;
+    int tile_x, tile_y;
+    centre_out_tile((int)blockIdx.x, tiles_x, (int)gridDim.x / tiles_x, tile_x, tile_y);
+    const int tile = tile_y * tiles_x + tile_x;
     const int wy0 = tile_y * TILE_PX + warp * 4;                    // this warp's 4 rows
     const int px0 = tile_x * TILE_PX + 2 * (lane & 7), py = wy0 + (lane >> 3);
     const bool in0 = px0 < W && py < H, in1 = px0 + 1 < W && py < H;
