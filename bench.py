@@ -287,7 +287,19 @@ def run_cuda(args):
         traffic = json.load(open(traffic_path)).get(dom["stage"])
     roofline = {"kernel": dom["stage"], "bound": "hbm", "achieved": dom["gbs"], "peak": peak, "unit": "GB/s",
                 "frac": dom["frac"], "traffic": traffic, "peak_source": peak_src,
-                "note": "dominant kernel by time; raster is ALU/SFU/shared-memory bound, not HBM bound -- see stages[]"}
+                "note": "dominant kernel by time; raster is bound by instruction issue, not by HBM -- see roofline.issue and stages[]"}
+    # the dominant kernel's OWN roofline: warp-instructions it executes per launch (ncu, profiles/traffic.json) against
+    # the SMs' issue rate (4 warp-instructions per SM cycle) at the SM clock sampled during the timed region
+    if traffic_path and os.path.exists(traffic_path):
+        wi = json.load(open(traffic_path)).get("warp_inst", {}).get(dom["stage"])
+        if wi:
+            sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
+            mhz = float((clk or {}).get("sm_mhz") or 1965.0)
+            peak_gi = sms * 4 * mhz * 1e6 / 1e9
+            ach_gi = wi / (dom["us"] * 1e-6) / 1e9
+            roofline["issue"] = {"warp_inst_per_launch": int(wi), "achieved": round(ach_gi, 1), "peak": round(peak_gi, 1),
+                                 "unit": "G warp-inst/s", "frac": round(ach_gi / peak_gi, 4),
+                                 "source": "ncu smsp__inst_executed.sum of the committed capture (profiles/), live CUDA-event time"}
 
     # ---- CPU baseline beside it (rank 0, N=1 only): bounded sample, ~10-30 s of CPU work
     cpu = None
