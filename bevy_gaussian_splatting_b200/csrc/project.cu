@@ -19,9 +19,10 @@ __constant__ float c_shc[16] = {   // src/material/spherical_harmonics.wgsl:3-20
     0.5462742152960396f, -0.5900435899266435f, 2.890611442640554f, -0.4570457994644658f,
     0.3731763325901154f, -0.4570457994644658f, 1.445305721320277f, -0.5900435899266435f};
 
+// colour path only (compared under tolerance): one rsqrt.approx (2 ulp) instead of an IEEE sqrt + three divisions
 __device__ __forceinline__ void normalize3(const float a[3], float out[3]) {
-    const float l = sqrtf((a[0] * a[0] + a[1] * a[1]) + a[2] * a[2]);
-    out[0] = a[0] / l; out[1] = a[1] / l; out[2] = a[2] / l;
+    const float inv = rsqrtf((a[0] * a[0] + a[1] * a[1]) + a[2] * a[2]);
+    out[0] = a[0] * inv; out[1] = a[1] * inv; out[2] = a[2] * inv;
 }
 __device__ __forceinline__ float dot3(const float a[3], const float b[3]) {
     return (a[0] * b[0] + a[1] * b[1]) + a[2] * b[2];
@@ -29,8 +30,8 @@ __device__ __forceinline__ float dot3(const float a[3], const float b[3]) {
 // spherical_harmonics.wgsl:22-32; no clamp on either side
 // (colour is compared under tolerance, not bit-exactly: fast pow = ex2(2.4 * lg2 x), ~1e-6 relative)
 __device__ __forceinline__ float srgb_to_linear(float v) {
-    if (v <= 0.04045f) return v / 12.92f;
-    return __powf((v + 0.055f) / 1.055f, 2.4f);
+    if (v <= 0.04045f) return v * (1.0f / 12.92f);
+    return __powf((v + 0.055f) * (1.0f / 1.055f), 2.4f);
 }
 __device__ __forceinline__ uint32_t pack_bbox(float lo, float hi) {
     return (uint32_t)(int)lo | ((uint32_t)(int)hi << 16);
@@ -265,6 +266,20 @@ project_kernel(const float4* __restrict__ pos, const void* __restrict__ sh_p, co
             for (int i = 0; i < 3; ++i)
 #pragma unroll
                 for (int j = 0; j < 3; ++j) Sg[i][j] = (M[0][i] * M[0][j] + M[1][i] * M[1][j]) + M[2][i] * M[2][j];
+            // identity model: T Sigma T^t == Sigma bit for bit as long as every entry of Sigma is finite and NON-ZERO
+            // (x*1 + y*0 + z*0 then only ever adds +-0 to a non-zero value); zero entries (axis-aligned splats) keep
+            // the multiply so that even the sign of a zero matches the oracle
+            const float mn = fminf(fminf(fminf(fabsf(Sg[0][0]), fabsf(Sg[0][1])), fminf(fabsf(Sg[0][2]), fabsf(Sg[1][1]))),
+                                   fminf(fabsf(Sg[1][2]), fabsf(Sg[2][2])));
+            const float mx = fmaxf(fmaxf(fmaxf(fabsf(Sg[0][0]), fabsf(Sg[0][1])), fmaxf(fabsf(Sg[0][2]), fabsf(Sg[1][1]))),
+                                   fmaxf(fabsf(Sg[1][2]), fabsf(Sg[2][2])));
+            if (fc.model_identity && mn > 0.0f && mx < __uint_as_float(0x7F800000u) && Sg[0][0] == Sg[0][0] &&
+                Sg[0][1] == Sg[0][1] && Sg[0][2] == Sg[0][2] && Sg[1][1] == Sg[1][1] && Sg[1][2] == Sg[1][2] && Sg[2][2] == Sg[2][2]) {
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) TS[i][j] = Sg[i][j];
+            } else {
 #pragma unroll
             for (int i = 0; i < 3; ++i)
 #pragma unroll
@@ -273,6 +288,7 @@ project_kernel(const float4* __restrict__ pos, const void* __restrict__ sh_p, co
             for (int i = 0; i < 3; ++i)
 #pragma unroll
                 for (int j = 0; j < 3; ++j) TS[i][j] = (X[i][0] * A[j][0] + X[i][1] * A[j][1]) + X[i][2] * A[j][2];
+            }
             const float c3[6] = {TS[0][0], TS[1][0], TS[2][0], TS[1][1], TS[2][1], TS[2][2]};
             const float Vrk[3][3] = {{c3[0], c3[1], c3[2]}, {c3[1], c3[3], c3[4]}, {c3[2], c3[4], c3[5]}};
             // helpers.wgsl:8-47
@@ -393,18 +409,22 @@ project_kernel(const float4* __restrict__ pos, const void* __restrict__ sh_p, co
                 const float dlt[3] = {k.pw[0] - fc.cam[0], k.pw[1] - fc.cam[1], k.pw[2] - fc.cam[2]};
                 float dw[3], loc[3], dl[3];
                 normalize3(dlt, dw);
+                if (fc.model_identity) {     // the normalised model columns are the unit axes
+                    loc[0] = dw[0]; loc[1] = dw[1]; loc[2] = dw[2];
+                } else {
 #pragma unroll
-                for (int cc = 0; cc < 3; ++cc) {
-                    const float col[3] = {A[0][cc], A[1][cc], A[2][cc]};
-                    float bn[3];
-                    normalize3(col, bn);
-                    loc[cc] = dot3(bn, dw);
+                    for (int cc = 0; cc < 3; ++cc) {
+                        const float col[3] = {A[0][cc], A[1][cc], A[2][cc]};
+                        float bn[3];
+                        normalize3(col, bn);
+                        loc[cc] = dot3(bn, dw);
+                    }
                 }
                 normalize3(loc, dl);
                 // spherical_harmonics.wgsl:34-68
                 const float x = dl[0], y = dl[1], z = dl[2];
                 const float xx = x * x, yy = y * y, zz = z * z;
-                float basis[16];
+                float basis[16];   // (the SH constants are folded in below: 16 multiplies instead of 48)
                 basis[0] = 1.0f;
                 basis[1] = y; basis[2] = z; basis[3] = x;
                 basis[4] = x * y; basis[5] = y * z; basis[6] = (2.0f * zz - xx) - yy;
@@ -417,10 +437,12 @@ project_kernel(const float4* __restrict__ pos, const void* __restrict__ sh_p, co
                 basis[14] = z * (xx - yy);
                 basis[15] = x * (xx - 3.0f * yy);
 #pragma unroll
+                for (int kk = 0; kk < 16; ++kk) basis[kk] *= c_shc[kk];
+#pragma unroll
                 for (int cc = 0; cc < 3; ++cc) {
                     float acc = 0.5f;
 #pragma unroll
-                    for (int kk = 0; kk < 16; ++kk) acc = fmaf(c_shc[kk] * sh[3 * kk + cc], basis[kk], acc);   // colour: FMA is fine
+                    for (int kk = 0; kk < 16; ++kk) acc = fmaf(sh[3 * kk + cc], basis[kk], acc);   // colour: FMA is fine
                     rgb[cc] = acc;
                 }
                 if (fc.color_space == 0u) {
