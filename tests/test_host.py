@@ -1,5 +1,6 @@
 """Host-side mirror of the reference interface: settings, pass plan, cameras, generator."""
 import math
+import os
 
 import numpy as np
 
@@ -60,3 +61,49 @@ def test_planar_layout_sizes():
     shp, rso = c.pack_f16()
     f16_bytes = (c.position_visibility.nbytes + shp.nbytes + rso.nbytes) // 10
     assert (f32_bytes, f16_bytes) == (240, 128)
+
+
+def test_entity_aabb_follows_the_reference_sequence():
+    """compute_aabb (interface.rs:22-66) -> Aabb {center, half_extents} (cloud.rs:45-62) -> min()/max() in f32."""
+    cloud = B.random_gaussians_3d_seeded(513, 9)
+    lo, hi = cloud.compute_aabb()
+    p = cloud.position_visibility[:, :3]
+    f = np.float32
+    mn = np.full(3, np.inf, f); mx = np.full(3, -np.inf, f)
+    for row in p:                                  # the non-rayon loop of interface.rs:52-57, literally
+        mn = np.minimum(mn, (row - f(0.1)).astype(f)); mx = np.maximum(mx, (row + f(0.1)).astype(f))
+    center = ((mn + mx).astype(f) / f(2)).astype(f); half = ((mx - mn).astype(f) / f(2)).astype(f)
+    assert np.array_equal(lo, (center - half).astype(f)) and np.array_equal(hi, (center + half).astype(f))
+    u = B.GaussianSplattingPlugin.cloud_uniform(B.CloudSettings(), None, (lo, hi))
+    assert list(u.aabb_min) == [float(lo[0]), float(lo[1]), float(lo[2]), 1.0] and u.aabb_max[3] == 1.0
+
+
+def test_settings_flags_and_modes_map_to_the_abi():
+    from bevy_gaussian_splatting_b200 import abi
+    assert B.CloudSettings().to_abi().flags == 0
+    assert B.CloudSettings(sort_all=True).to_abi().flags == abi.BGS_FLAG_SORT_ALL
+    assert B.CloudSettings(binning_rounds=True).to_abi().flags == abi.BGS_FLAG_CHUNKS
+    assert B.CloudSettings(binning_rounds=False, sort_all=True).to_abi().flags == abi.BGS_FLAG_NO_CHUNKS | abi.BGS_FLAG_SORT_ALL
+    s = B.CloudSettings(rasterize_mode=B.RasterizeMode.Position, gaussian_mode=B.GaussianMode.Gaussian2d, aabb=True).to_abi()
+    assert (s.rasterize_mode, s.gaussian_mode, s.aabb) == (3, 0, 1)
+    hdr = open(os.path.join(os.path.dirname(__file__), "..", "include", "bgs.h")).read()
+    for name, val in (("BGS_FLAG_SORT_ALL", 1), ("BGS_FLAG_ASYNC", 2), ("BGS_FLAG_NO_CHUNKS", 4), ("BGS_FLAG_CHUNKS", 8)):
+        assert f"{name} = {val}u" in hdr and getattr(abi, name) == val
+    assert "BGS_RASTERIZE_POSITION = 3" in hdr
+
+
+def test_bench_arms_on_a_box_without_a_gpu():
+    """The reference arm runs the CPU oracle port and prints the contract's JSON line; the CUDA arm refuses to run
+    without a GPU (no CPU fallback)."""
+    import json, subprocess, sys, torch
+    root = os.path.join(os.path.dirname(__file__), "..")
+    r = subprocess.run([sys.executable, "bench.py", "--impl", "reference", "--steps", "1", "--warmup", "3"], cwd=root,
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "Msplats/s" and line["value"] > 0 and line["higher_is_better"] is True
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and line["n_gpus"] == 1
+    if not torch.cuda.is_available():
+        r = subprocess.run([sys.executable, "bench.py", "--steps", "1"], cwd=root, capture_output=True, text=True, timeout=600)
+        assert r.returncode != 0 and "no CUDA device" in (r.stderr + r.stdout)
