@@ -92,7 +92,8 @@ enum { BGS_FORMAT_RGBA8_SRGB = 0, BGS_FORMAT_RGBA16F = 1, BGS_FORMAT_RGBA32F = 2
 typedef struct {
     uint32_t n;          /* gaussians in the cloud */
     uint32_t n_visible;  /* in-frustum gaussians this frame */
-    uint64_t n_pairs;    /* (splat, tile) intersections this frame */
+    uint64_t n_pairs;    /* (splat, tile) pairs emitted this frame (multi-round frames: summed over the rounds;
+                            fewer than a one-round frame's when the frame saturated early) */
     uint32_t tiles_x, tiles_y;
     uint32_t width, height;
     uint32_t rounds;          /* binning rounds of the frame: 1, or > 1 on chunked frames (BGS_FLAG_CHUNKS) */
@@ -128,7 +129,8 @@ bgs_status bgs_sync(bgs_context* ctx);
 /* Parity / debug hooks (valid after a completed bgs_render on this context). */
 /* n*2 words (key, index): the reference's sorted_entry_buffer (sort/mod.rs:323-329). */
 bgs_status bgs_debug_sorted_entries(bgs_context* ctx, uint32_t* key_index_pairs);
-/* tiles*2 words (start, end) into the per-tile entry list. */
+/* tiles*2 words (start, end) into the per-tile entry list.  The two tile hooks need a one-round frame
+ * (BGS_NOT_READY after a multi-round one: render with BGS_FLAG_NO_CHUNKS). */
 bgs_status bgs_debug_tile_ranges(bgs_context* ctx, uint32_t* start_end);
 /* n_pairs words: front-to-back rank of each (tile, splat) pair, tile-major. */
 bgs_status bgs_debug_tile_entries(bgs_context* ctx, uint32_t* ranks, uint64_t capacity);
@@ -139,7 +141,8 @@ bgs_status bgs_frame_stats_get(bgs_context* ctx, bgs_frame_stats* out);
 
 /* Last frame's stage times (CUDA events on the context stream), microseconds:
  * [0] key-gen, [1] depth sort, [2] projection, [3] binning + tile sort + ranges,
- * [4] raster, [5] whole frame. */
+ * [4] raster, [5] whole frame.  (Multi-round frames: [3] also holds the earlier rounds' blends,
+ * [4] the last round's.) */
 bgs_status bgs_stage_times_us(bgs_context* ctx, float out[6]);
 const char* bgs_last_error(const bgs_context* ctx);
 /* The CUDA stream (cudaStream_t) all of this context's work is launched on. */
