@@ -39,8 +39,12 @@ struct CloudSettings {   // src/gaussian/settings.rs:110-133 (defaults)
     RasterizeMode rasterize_mode = RasterizeMode::Color;
     GaussianColorSpace color_space = GaussianColorSpace::SrgbRec709Display;
     float time = 0.0f;
+    // this repo's extension: front-to-back binning rounds (BGS_FLAG_CHUNKS): -1 = the library's choice from the last
+    // frame's footprint statistics, 1 = always, 0 = never (the tile debug hooks need a one-round frame)
+    int binning_rounds = -1;
 
     bgs_settings to_abi(uint32_t flags = 0) const {
+        if (binning_rounds >= 0) flags |= binning_rounds ? BGS_FLAG_CHUNKS : BGS_FLAG_NO_CHUNKS;
         bgs_settings s{};
         s.gaussian_mode = (uint32_t)gaussian_mode; s.rasterize_mode = (uint32_t)rasterize_mode;
         s.aabb = aabb; s.opacity_adaptive_radius = opacity_adaptive_radius; s.draw_mode = (uint32_t)draw_mode;
