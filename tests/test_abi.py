@@ -75,3 +75,33 @@ def test_product_never_imports_the_oracle():
                     assert "liboracle" not in code and "bgs_oracle" not in code, (f, line)
                     if f.endswith(".py"):
                         assert not re.search(r"^\s*(from|import)\s+oracle\b", code), (f, line)
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """include/bgs.h is the drop-in boundary: it must compile as C99 (no C++isms) and a C program must link against
+    libbgs.so and get a status code (BGS_ECUDA without a GPU) rather than a crash."""
+    import subprocess, textwrap, torch
+
+    root = os.path.join(os.path.dirname(__file__), "..")
+    src = tmp_path / "abi_c.c"
+    src.write_text(textwrap.dedent("""
+        #include <stdio.h>
+        #include "bgs.h"
+        int main(void) {
+            bgs_context* ctx = NULL;
+            bgs_settings s = {BGS_GAUSSIAN_3D, BGS_RASTERIZE_COLOR, 0, 1, BGS_DRAW_ALL, 32, BGS_FLAG_ASYNC | BGS_FLAG_NO_CHUNKS, 0};
+            bgs_cloud_uniform u = {{1,0,0,0, 0,1,0,0, 0,0,1,0, 0,0,0,1}, 1.0f, 1.0f, 0u, 0.0f, {0,0,0,1}, {1,1,1,1}};
+            bgs_frame_stats fs;
+            bgs_status st = bgs_context_create(0, &ctx);
+            printf("%d %u %u %u\\n", (int)st, (unsigned)sizeof(s), (unsigned)sizeof(u), (unsigned)sizeof(fs));
+            if (st == BGS_OK) bgs_context_destroy(ctx);
+            return 0;
+        }
+    """))
+    exe = tmp_path / "abi_c"
+    libdir = os.path.join(root, "bevy_gaussian_splatting_b200")
+    subprocess.run(["/usr/bin/gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(root, "include"), str(src), "-o", str(exe),
+                    "-L", libdir, "-lbgs", f"-Wl,-rpath,{libdir}"], check=True, capture_output=True, text=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    assert out[1:] == ["32", "112", "40"]
+    assert int(out[0]) == (abi.BGS_OK if torch.cuda.is_available() else abi.BGS_ECUDA)
