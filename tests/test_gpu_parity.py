@@ -379,6 +379,47 @@ def test_full_size_properties(plugin, n, f16, scale):
         h.destroy()
 
 
+def test_full_size_surfels_and_auto_binning_rounds(plugin):
+    """Config C4 (2 M surfels, 2DGS + USE_AABB, colour / depth / normal frames) and config C2's raw generator scale
+    (global_scale 1: ~650 tiles per visible splat), at full size, through size-independent properties: idempotence,
+    compaction == sort-all, finite output; and the library switching to binning rounds BY ITSELF on the heavy scene
+    (from the first frame's statistics) without changing a bit of the frame."""
+    view = B.headless_view(1920, 1080)
+    cloud = B.random_gaussians_3d_seeded(2_000_000, 4)
+    h = plugin.add_cloud(cloud)
+    try:
+        for rm in (B.RasterizeMode.Color, B.RasterizeMode.Depth, B.RasterizeMode.Normal):
+            s = B.CloudSettings(global_scale=0.02, gaussian_mode=B.GaussianMode.Gaussian2d, aabb=True, rasterize_mode=rm)
+            img = plugin.render_view(h, s, view, fmt="rgba32f")
+            fs = plugin.frame_stats()
+            assert fs.rounds == 1 and fs.n_visible > 100_000 and fs.n_pairs >= fs.n_visible // 2
+            assert np.isfinite(img).all() and img[..., :3].max() > 0.05 and np.all(img[..., 3] == 1.0)
+            assert np.array_equal(img, plugin.render_view(h, s, view, fmt="rgba32f"))
+            import dataclasses
+            assert np.array_equal(img, plugin.render_view(h, dataclasses.replace(s, sort_all=True), view, fmt="rgba32f"))
+    finally:
+        h.destroy()
+    cloud = B.random_gaussians_3d_seeded(1_000_000, 0)
+    p2 = B.GaussianSplattingPlugin(0)              # fresh context: no footprint statistics yet
+    try:
+        h2 = p2.add_cloud(cloud)
+        s = B.CloudSettings(global_scale=1.0)
+        first = p2.render_view(h2, s, view, fmt="rgba8_srgb")
+        fs1 = p2.frame_stats()
+        pairs1, rounds1 = fs1.n_pairs, fs1.rounds
+        second = p2.render_view(h2, s, view, fmt="rgba8_srgb")
+        fs2 = p2.frame_stats()
+        assert rounds1 == 1 and pairs1 > 50_000_000                      # one round: every (splat, tile) pair
+        assert fs2.rounds > 1 and fs2.n_pairs < pairs1 // 4              # rounds: the frame saturates early
+        assert fs2.tiles_saturated == fs2.tiles_x * fs2.tiles_y
+        assert np.array_equal(first, second)
+        third = p2.render_view(h2, B.CloudSettings(global_scale=1.0, binning_rounds=False), view, fmt="rgba8_srgb")
+        assert p2.frame_stats().rounds == 1 and np.array_equal(first, third)
+        h2.destroy()
+    finally:
+        p2.destroy()
+
+
 def test_async_frames_and_deferred_overflow(plugin):
     """BGS_FLAG_ASYNC: frames queue back to back; bgs_sync completes them; a pair-list overflow is reported at
     sync time (BGS_NOT_READY), the buffer grows, and the re-rendered frame is exact."""
