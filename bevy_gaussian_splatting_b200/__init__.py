@@ -8,7 +8,8 @@ from .abi import BgsError  # noqa: F401
 from .camera import GaussianCamera, View, headless_view, orbit_view, perspective_view  # noqa: F401
 from .gaussian import (PlanarGaussian3d, random_gaussians_3d, random_gaussians_3d_seeded,  # noqa: F401
                        SH_COEFF_COUNT)
-from .io import parse_ply_3d  # noqa: F401
+from .io import load_cloud, parse_ply_3d  # noqa: F401
+from .gcloud import decode_gcloud, encode_gcloud, read_gcloud, write_gcloud  # noqa: F401
 from .plugin import CloudTransform, GaussianSplattingPlugin, PlanarGaussian3dHandle  # noqa: F401
 from .settings import (CloudSettings, DrawMode, GaussianColorSpace, GaussianMode, RadixSortDepthBits,  # noqa: F401
                        RasterizeMode, ShaderDefines, SortMode)

@@ -8,8 +8,8 @@ Restates src/io/ply.rs:23-132 of the reference, including its quirks:
     coefficient * 3 + channel, ignored when >= 48            ply.rs:49-69 (later properties overwrite earlier)
   * the cloud is padded with default gaussians by 32 - (n % 32) entries -- a full 32 when n is already
     a multiple of 32                                          ply.rs:127-129
-`.gcloud` (flexbuffers serde, src/io/gcloud/flexbuffers.rs:9-22) is not read here: no flexbuffers
-implementation or reference-written fixture exists in this image to validate a reader against.
+`.gcloud` (flexbuffers serde, src/io/gcloud/flexbuffers.rs:9-22) lives in `gcloud.py`; `load_cloud` below is the
+extension switch of the reference's asset loader (src/io/loader.rs:38-66).
 """
 from __future__ import annotations
 
@@ -149,3 +149,16 @@ def write_ply_3d(path, cloud: PlanarGaussian3d, n: int | None = None) -> None:
             f.write(f"property float {p}\n".encode())
         f.write(b"end_header\n")
         f.write(arr.tobytes())
+
+
+def load_cloud(path) -> PlanarGaussian3d:
+    """`Gaussian3dLoader::load` (src/io/loader.rs:24-70): `.ply` -> parse_ply_3d, `.gcloud` -> CloudCodec::decode,
+    anything else is an error ("only .ply and .gcloud supported")."""
+    ext = os.path.splitext(str(path))[1].lower()
+    if ext == ".ply":
+        return parse_ply_3d(path)
+    if ext == ".gcloud":
+        from .gcloud import read_gcloud
+
+        return read_gcloud(path)
+    raise ValueError("only .ply and .gcloud supported")

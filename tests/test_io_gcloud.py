@@ -1,0 +1,110 @@
+"""`.gcloud` codec (row f1): the reference pins this format only through a round trip (tests/io.rs:7-17,
+tests/gaussian.rs:7-17: decode(encode(random_gaussians_3d(n))) == original) -- restated here -- plus the generic
+FlexBuffers reader against buffers assembled by hand from the published wire format (every width, typed / fixed /
+untyped vectors, maps, indirect scalars).  Parity with bytes written by the Rust `flexbuffers` crate: unpinned."""
+import struct
+
+import numpy as np
+import pytest
+
+import bevy_gaussian_splatting_b200 as B
+from bevy_gaussian_splatting_b200 import gcloud as G
+
+
+def _same(a, b):
+    return all(np.array_equal(getattr(a, k).view(np.uint32), getattr(b, k).view(np.uint32))
+               for k in ("position_visibility", "spherical_harmonic", "rotation", "scale_opacity"))
+
+
+@pytest.mark.parametrize("n", [100, 10000])          # the counts of tests/gaussian.rs and tests/io.rs
+def test_codec_3d_round_trip(n, tmp_path):
+    cloud = B.random_gaussians_3d_seeded(n, 7)
+    cloud.scale_opacity[0] = [np.float32(1e-38), -0.0, np.inf, np.float32(3e38)]     # bit patterns survive
+    data = G.encode_gcloud(cloud)
+    assert _same(G.decode_gcloud(data), cloud)
+    p = tmp_path / "c.gcloud"
+    G.write_gcloud(p, cloud)
+    assert _same(G.read_gcloud(p), cloud) and p.stat().st_size == len(data)
+    r = G.root(data)
+    assert r.type == G.FBT_MAP and r.keys() == [b"position_visibility", b"rotation", b"scale_opacity", b"spherical_harmonic"]
+    e0 = r.as_dict()[b"position_visibility"][0]
+    assert e0.type == G.FBT_MAP and e0.keys() == [b"position", b"visibility"]
+    assert e0.as_dict()[b"position"].type == G.FBT_VECTOR_INT2 + 3 + 2      # VECTOR_FLOAT3
+
+
+def test_empty_cloud_and_errors():
+    empty = B.PlanarGaussian3d(np.zeros((0, 4), np.float32), np.zeros((0, 48), np.float32), np.zeros((0, 4), np.float32),
+                               np.zeros((0, 4), np.float32))
+    assert len(G.decode_gcloud(G.encode_gcloud(empty))) == 0
+    data = G.encode_gcloud(B.random_gaussians_3d_seeded(3, 1))
+    with pytest.raises(G.FlexBufferError):
+        G.decode_gcloud(data[:2])
+    with pytest.raises(G.FlexBufferError):
+        G.decode_gcloud(b"\x00" * 16 + data[-6:])       # root offset points outside / at garbage
+    with pytest.raises(G.FlexBufferError):
+        G.decode_gcloud(bytes([3, 1, 2, 3, 3, 44, 1]))  # a valid FlexBuffer that is not a cloud
+
+
+def test_reader_on_hand_assembled_buffers():
+    # typed int vector [1, 2, 3], 8-bit: len, elements, root offset, (VECTOR_INT << 2 | 0), root width
+    r = G.root(bytes([3, 1, 2, 3, 3, 44, 1]))
+    assert r.type == G.FBT_VECTOR_INT and len(r) == 3 and [r[i].as_int() for i in range(3)] == [1, 2, 3]
+    assert np.array_equal(r.as_float_array(), np.array([1, 2, 3], np.float32))
+    # map { bar: 14, foo: 13 }: keys, key vector (len, offsets), map header (key-vector offset, key width, len), values, types
+    buf = b"bar\0foo\0" + bytes([2, 9, 6, 2, 1, 2, 14, 13, 4, 4, 4, 36, 1])
+    m = G.root(buf)
+    assert m.type == G.FBT_MAP and m.keys() == [b"bar", b"foo"]
+    assert {k: v.as_int() for k, v in m.as_dict().items()} == {b"bar": 14, b"foo": 13}
+    # untyped vector [f32 1.5 (inline), -> f64 2.25 (indirect), -> VECTOR_FLOAT (16-bit wide? no: 4-byte) of 5 floats], 4-byte slots
+    out = bytearray()
+    out += struct.pack("<d", 2.25)                                   # indirect f64 at 0
+    out += struct.pack("<I", 5); v5 = len(out); out += np.arange(5, dtype="<f4").tobytes()
+    out += struct.pack("<I", 3); vec = len(out)
+    out += struct.pack("<f", 1.5)
+    out += struct.pack("<I", len(out) - 0)
+    out += struct.pack("<I", len(out) - v5)
+    out += bytes([(G.FBT_FLOAT << 2) | 2, (G.FBT_INDIRECT_FLOAT << 2) | 3, (G.FBT_VECTOR_FLOAT << 2) | 2])
+    out += b"\0"                                                     # align the root slot
+    out += struct.pack("<I", len(out) - vec) + bytes([(G.FBT_VECTOR << 2) | 2, 4])
+    r = G.root(bytes(out))
+    assert len(r) == 3 and r[0].as_float() == 1.5 and r[1].as_float() == 2.25
+    assert np.array_equal(r[2].as_float_array(), np.arange(5, dtype=np.float32))
+    # a cloud whose structs are SEQUENCES (serde also accepts a struct as a tuple) and whose floats are f64 / 16-bit offsets
+    b = bytearray()
+
+    def f64vec(vals):
+        b.extend(b"\0" * (-len(b) % 8)); b.extend(struct.pack("<Q", len(vals))); p = len(b)
+        b.extend(np.asarray(vals, "<f8").tobytes()); return p
+
+    def seq(items):   # items: (position, packed) -> untyped vector with 2-byte slots
+        b.extend(b"\0" * (-len(b) % 2)); b.extend(struct.pack("<H", len(items))); p = len(b)
+        for pos, _ in items:
+            b.extend(struct.pack("<H", len(b) - pos))
+        b.extend(bytes(pk for _, pk in items)); return p
+
+    F8 = (G.FBT_VECTOR_FLOAT << 2) | 3
+    V2 = (G.FBT_VECTOR << 2) | 1
+    b.extend(b"\0" * (-len(b) % 8)); vis_pos = len(b); b.extend(struct.pack("<d", 0.75))    # indirect f64 scalar
+    IF8 = (G.FBT_INDIRECT_FLOAT << 2) | 3
+    pv = seq([(seq([(f64vec([1, 2, 3]), F8), (vis_pos, IF8)]), V2)])
+    sh = seq([(seq([(f64vec(np.arange(48)), F8)]), V2)])
+    ro = seq([(seq([(f64vec([1, 0, 0, 0]), F8)]), V2)])
+    so = seq([(seq([(f64vec([.5, .25, .125]), F8)]), V2)])                          # opacity missing -> default 0
+    top = seq([(pv, V2), (sh, V2), (ro, V2), (so, V2)])
+    b.extend(b"\0" * (-len(b) % 2)); b.extend(struct.pack("<H", len(b) - top)); b.extend(bytes([V2, 2]))
+    c = G.decode_gcloud(bytes(b))
+    assert len(c) == 1 and c.position_visibility.tolist() == [[1, 2, 3, 0.75]] and c.rotation.tolist() == [[1, 0, 0, 0]]
+    assert c.scale_opacity.tolist() == [[.5, .25, .125, 0.0]] and np.array_equal(c.spherical_harmonic[0], np.arange(48, dtype=np.float32))
+
+
+def test_loader_switches_on_the_extension(tmp_path):
+    """src/io/loader.rs:38-66: .ply / .gcloud by extension, anything else is an error."""
+    from bevy_gaussian_splatting_b200.io import write_ply_3d
+
+    cloud = B.random_gaussians_3d_seeded(64, 2)
+    G.write_gcloud(tmp_path / "a.gcloud", cloud)
+    assert _same(B.load_cloud(tmp_path / "a.gcloud"), cloud)
+    write_ply_3d(tmp_path / "a.ply", cloud)
+    assert len(B.load_cloud(tmp_path / "a.ply")) == 64 + 32          # ply.rs:127-129 pads by 32 - n % 32
+    with pytest.raises(ValueError):
+        B.load_cloud(tmp_path / "a.splat")
