@@ -46,9 +46,12 @@ def _read_header(f):
             cur = {"name": tok[1], "count": int(tok[2]), "props": []}
             elements.append(cur)
         elif tok[0] == "property":
-            if tok[1] == "list":
-                raise ValueError("list properties are not supported in the vertex element")
-            cur["props"].append((tok[2], _PLY_TYPES[tok[1]]))
+            if tok[1] == "list":     # (count type, item type): fine in other elements (faces), skipped with them
+                if cur["name"] == "vertex":
+                    raise ValueError("list properties are not supported in the vertex element")
+                cur["props"].append((tok[4], ("list", _PLY_TYPES[tok[2]], _PLY_TYPES[tok[3]])))
+            else:
+                cur["props"].append((tok[2], _PLY_TYPES[tok[1]]))
         elif tok[0] == "end_header":
             break
     return fmt, elements
@@ -81,7 +84,16 @@ def parse_ply_3d(source) -> PlanarGaussian3d:
                     f.readline()
             else:
                 end = "<" if fmt == "binary_little_endian" else ">"
-                f.read(np.dtype([(p, end + t) for p, t in el["props"]]).itemsize * el["count"])
+                if any(isinstance(t, tuple) for _, t in el["props"]):
+                    for _ in range(el["count"]):            # rows with list properties have no fixed stride
+                        for _, t in el["props"]:
+                            if isinstance(t, tuple):
+                                cnt = int(np.frombuffer(f.read(np.dtype(t[1]).itemsize), end + t[1], 1)[0])
+                                f.read(cnt * np.dtype(t[2]).itemsize)
+                            else:
+                                f.read(np.dtype(t).itemsize)
+                else:
+                    f.read(np.dtype([(p, end + t) for p, t in el["props"]]).itemsize * el["count"])
     if vertex is None:
         return PlanarGaussian3d(np.zeros((0, 4), np.float32), np.zeros((0, 48), np.float32), np.zeros((0, 4), np.float32),
                                 np.zeros((0, 4), np.float32))

@@ -1,4 +1,6 @@
 """Row f1: the INRIA `.ply` input format, restating src/io/ply.rs:23-132 incl. its quirks."""
+import os
+
 import numpy as np
 
 import bevy_gaussian_splatting_b200 as B
@@ -74,3 +76,46 @@ def test_ply_cloud_renders_through_the_oracle(oracle, tmp_path):
     ref = oracle.render_ref(cloud, view.to_abi(), u, s.to_abi())
     til = oracle.render_tiles(cloud, view.to_abi(), u, s.to_abi())["image"]
     assert np.isfinite(ref).all() and ref[..., :3].max() > 0.01 and np.abs(ref - til).max() <= 1e-3
+
+
+def test_cpp_host_mirror_reads_the_same_planes(tmp_path):
+    """include/bgs_io.hpp (`bgs::io::parse_ply_3d`, the compiled-language host mirror of src/io/ply.rs) against the
+    Python mirror on the same file: identical planes (exp / sigmoid within 2 ulp of each other's libm), same padding,
+    same error on a missing required property.  CPU only (examples/cloud_tool links nothing from libbgs.so)."""
+    import subprocess
+
+    root = os.path.join(os.path.dirname(__file__), "..")
+    subprocess.run(["make", "-C", os.path.join(root, "examples"), "-s", "cloud_tool"], check=True)
+    tool = os.path.join(root, "examples", "cloud_tool")
+    cloud = B.random_gaussians_3d_seeded(333, 6)
+    bio.write_ply_3d(tmp_path / "a.ply", cloud)
+    # an ascii file with an extra non-float property and an extra element, like exporters write
+    rows = np.random.default_rng(0).normal(size=(5, 14)).astype(np.float32)
+    names = ["x", "y", "z", "f_dc_0", "f_dc_1", "f_dc_2", "f_rest_0", "f_rest_31", "opacity", "scale_0", "scale_1", "scale_2", "rot_0", "rot_1"]
+    with open(tmp_path / "b.ply", "w") as f:
+        f.write("ply\nformat ascii 1.0\ncomment made by a test\nelement vertex 5\n")
+        for nm in names:
+            f.write(f"property float {nm}\n")
+        f.write("property float rot_2\nproperty float rot_3\nelement face 1\nproperty list uchar int vertex_indices\nend_header\n")
+        for r in rows:
+            f.write(" ".join(repr(float(v)) for v in r) + " 0.5 -0.25\n")
+        f.write("3 0 1 2\n")
+    for name in ("a.ply", "b.ply"):
+        r = subprocess.run([tool, str(tmp_path / name), str(tmp_path / "out.bin")], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        raw = (tmp_path / "out.bin").read_bytes()
+        n = int(np.frombuffer(raw, "<u8", 1)[0])
+        py = bio.parse_ply_3d(tmp_path / name)
+        assert n == len(py) and n % 32 == 0
+        off = 8
+        for w, want, exact in ((4, py.position_visibility, True), (48, py.spherical_harmonic, True), (4, py.rotation, False),
+                               (4, py.scale_opacity, False)):
+            got = np.frombuffer(raw, "<f4", n * w, off).reshape(n, w); off += n * w * 4
+            if exact:
+                assert np.array_equal(got, want)
+            else:
+                assert np.allclose(got, want, rtol=3e-7, atol=1e-12, equal_nan=True)
+    bad = (tmp_path / "a.ply").read_bytes().replace(b"property float opacity\n", b"property float opacitx\n")
+    (tmp_path / "c.ply").write_bytes(bad)
+    r = subprocess.run([tool, str(tmp_path / "c.ply"), str(tmp_path / "out.bin")], capture_output=True, text=True)
+    assert r.returncode == 2 and "missing required properties" in r.stderr
