@@ -228,10 +228,12 @@ bgs_status ensure_arena(bgs_context* c, uint32_t n, uint32_t pairs, uint32_t til
     const size_t o_hist = off; off = align_up(off + (8 + 4 * MAX_CHUNKS) * 256 * 4, 256);
     const size_t o_skg = off; off = align_up(off + ((size_t)keygen_num_tiles(n) + 4096) * 4, 256);
     const size_t o_sbin = off; off = align_up(off + ((size_t)bin_num_tiles(n) + 4096) * 4, 256);
-    // chunked frames (only for <= CHUNK_MAX_TILES tiles) use one ranges array per round + a done byte per tile
-    const size_t range_sets = tiles <= CHUNK_MAX_TILES ? MAX_CHUNKS : 1;
-    const size_t o_rng = off; off = align_up(off + (size_t)tiles * 8 * range_sets, 256);
-    const size_t o_done = off; off = align_up(off + (tiles <= CHUNK_MAX_TILES ? tiles : 0), 256);
+    // chunked frames (only for <= CHUNK_MAX_TILES tiles) use one ranges array per round + a done byte per tile; an
+    // arena sized by a larger frame must still hold them for a later, smaller (chunkable) frame
+    const size_t chunk_tiles = tiles <= CHUNK_MAX_TILES ? tiles : CHUNK_MAX_TILES;
+    const size_t range_entries = chunk_tiles * MAX_CHUNKS > tiles ? chunk_tiles * MAX_CHUNKS : tiles;
+    const size_t o_rng = off; off = align_up(off + range_entries * 8, 256);
+    const size_t o_done = off; off = align_up(off + chunk_tiles, 256);
     const size_t o_sd = off; off = align_up(off + (size_t)4 * radix_num_tiles(n) * 256 * 4, 256);
     const size_t o_sp = off; off = align_up(off + (size_t)4 * radix_num_tiles(pairs) * 256 * 4, 256);
     CU(c, cudaMalloc(&c->arena, off));
