@@ -278,8 +278,85 @@ _PLANES = (
 )
 
 
-def encode_gcloud(cloud: PlanarGaussian3d) -> bytes:
-    """`PlanarGaussian3d::encode` (src/io/gcloud/flexbuffers.rs:9-16)."""
+def _encode_plane(b: Builder, arr: np.ndarray, fields):
+    """All N element structs of one plane at once (numpy), in the same layout Builder.map / float_vector produce one
+    by one: per element [its float vectors][key-vector offset, key width, length][one slot per field][type bytes, pad].
+    Returns the plane's ("o", position, packed) item."""
+    n = len(arr)
+    ks = tuple(sorted(fk for fk, _, _ in fields))
+    by_key = {fk: (c0, w) for fk, c0, w in fields}
+    # the shared key vector (written once, before the elements)
+    kpos = [b.key(k) for k in ks]
+    b._align()
+    b.out += struct.pack("<I", len(ks))
+    kv = len(b.out)
+    for p in kpos:
+        b.out += struct.pack("<I", len(b.out) - p)
+    b._keyvecs.setdefault(ks, kv)
+    b._align()
+    base = len(b.out)
+    # record layout
+    rec, off, vec_at = [], 0, {}
+    for fk in ks:
+        c0, w = by_key[fk]
+        if w > 1:
+            if not 2 <= w <= 4:
+                rec.append((f"l_{fk.decode()}", "<u4")); off += 4                  # length prefix of a VECTOR_FLOAT
+            vec_at[fk] = off
+            rec.append((f"v_{fk.decode()}", "<f4", (w,))); off += 4 * w
+    hdr_at = off
+    rec += [("koff", "<u4"), ("kw", "<u4"), ("len", "<u4")]; off += 12
+    slot_at = {}
+    for fk in ks:
+        slot_at[fk] = off
+        rec.append((f"s_{fk.decode()}", "<f4" if by_key[fk][1] == 1 else "<u4")); off += 4
+    rec.append(("types", "u1", (len(ks),))); off += len(ks)
+    pad = -off % 4
+    if pad:
+        rec.append(("pad", "u1", (pad,))); off += pad
+    dt = np.dtype(rec)
+    assert dt.itemsize == off
+    r = np.zeros(n, dt)
+    idx = np.arange(n, dtype=np.int64)
+    rec_pos = base + idx * off
+    koff = rec_pos + hdr_at - kv
+    if n and int(koff.max()) >= 1 << 32:
+        raise FlexBufferError("offset does not fit 32 bits")
+    r["koff"], r["kw"], r["len"] = koff, Builder.W, len(ks)
+    types = []
+    for fk in ks:
+        c0, w = by_key[fk]
+        name = fk.decode()
+        if w == 1:
+            r[f"s_{name}"] = arr[:, c0]
+            types.append((FBT_FLOAT << 2) | 2)
+        else:
+            r[f"v_{name}"] = arr[:, c0:c0 + w]
+            if 2 <= w <= 4:
+                ty = FBT_VECTOR_INT2 + (w - 2) * 3 + (FBT_FLOAT - FBT_INT)
+            else:
+                ty = FBT_VECTOR_FLOAT
+                r[f"l_{name}"] = w
+            r[f"s_{name}"] = slot_at[fk] - vec_at[fk]                  # constant backwards distance inside the record
+            types.append((ty << 2) | 2)
+    r["types"] = np.array(types, np.uint8)
+    b.out += r.tobytes()
+    # the plane: an untyped vector of N maps
+    b._align()
+    b.out += struct.pack("<I", n)
+    pos = len(b.out)
+    first_value = rec_pos + hdr_at + 12                                # a map is referenced by its first value slot
+    slots = pos + 4 * idx - first_value
+    if n and int(slots.max()) >= 1 << 32:
+        raise FlexBufferError("offset does not fit 32 bits")
+    b.out += slots.astype("<u4").tobytes()
+    b.out += bytes([(FBT_MAP << 2) | 2]) * n
+    return ("o", pos, (FBT_VECTOR << 2) | 2)
+
+
+def encode_gcloud_elementwise(cloud: PlanarGaussian3d) -> bytes:
+    """The same document written one value at a time through `Builder` (key vectors shared per key set, element structs
+    interleaved with their vectors): a differently laid out but equivalent FlexBuffer, used to exercise the generic reader."""
     b = Builder()
     planes = {}
     for key, attr, fields in _PLANES:
@@ -292,6 +369,76 @@ def encode_gcloud(cloud: PlanarGaussian3d) -> bytes:
             elems.append(("o",) + b.map(m))
         planes[key] = ("o",) + b.vector(elems)
     return b.finish(*b.map(planes))
+
+
+def encode_gcloud(cloud: PlanarGaussian3d) -> bytes:
+    """`PlanarGaussian3d::encode` (src/io/gcloud/flexbuffers.rs:9-16)."""
+    b = Builder()
+    planes = {}
+    for key, attr, fields in _PLANES:
+        planes[key] = _encode_plane(b, np.ascontiguousarray(getattr(cloud, attr), np.float32), fields)
+    return b.finish(*b.map(planes))
+
+
+def _decode_plane_fast(pr: "Ref", fields, width: int):
+    """Vectorised read of a plane whose N elements are maps with one shared key order, 4-byte slots and 4-byte-aligned
+    f32 payloads (what encode_gcloud writes; a regular writer's output in general).  None = not that shape: the caller
+    falls back to the generic per-element reader."""
+    buf = pr.buf
+    if pr.type != FBT_VECTOR or pr.byte_width != 4:
+        return None
+    t, n, _ = pr._vector_info()
+    if n == 0:
+        return np.zeros((0, width), np.float32)
+    if t % 4 or t + 5 * n > len(buf):
+        return None
+    u32 = np.frombuffer(buf, "<u4", len(buf) // 4)
+    f32 = np.frombuffer(buf, "<f4", len(buf) // 4)
+    types = np.frombuffer(buf, np.uint8, n, t + 4 * n)
+    if not np.all(types == ((FBT_MAP << 2) | 2)):
+        return None
+    idx = np.arange(n, dtype=np.int64)
+    vals = t + 4 * idx - u32[t // 4: t // 4 + n].astype(np.int64)      # first value slot of every map
+    if vals.min() < 12 or np.any(vals % 4):
+        return None
+    first = pr[0]
+    keys = first.keys()
+    k = len(keys)
+    if np.any(u32[vals // 4 - 1] != k) or np.any(u32[vals // 4 - 2] != 4) or vals.max() + 5 * k > len(buf):
+        return None
+    kvec = vals - 12 - u32[vals // 4 - 3].astype(np.int64)
+    if np.any(kvec != kvec[0]):                                        # one shared key vector <=> one key order
+        return None
+    arr = np.zeros((n, width), np.float32)
+    tbytes = np.frombuffer(buf, np.uint8)
+    for fk, c0, w in fields:
+        if fk not in keys:
+            continue                                                   # #[serde(default)]
+        j = keys.index(fk)
+        ty = tbytes[vals + 4 * k + j]
+        if np.any(ty != ty[0]):
+            return None
+        slot = vals + 4 * j
+        packed = int(ty[0])
+        if w == 1:
+            if packed != ((FBT_FLOAT << 2) | 2):
+                return None
+            arr[:, c0] = f32[slot // 4]
+            continue
+        vty, bw = packed >> 2, 1 << (packed & 3)
+        fixed = FBT_VECTOR_INT2 <= vty <= FBT_VECTOR_FLOAT4 and (vty - FBT_VECTOR_INT2) % 3 == FBT_FLOAT - FBT_INT
+        if bw != 4 or not (vty == FBT_VECTOR_FLOAT or fixed):
+            return None
+        tgt = slot - u32[slot // 4].astype(np.int64)
+        if tgt.min() < (0 if fixed else 4) or np.any(tgt % 4) or tgt.max() + 4 * w > len(buf):
+            return None
+        if fixed:
+            if (vty - FBT_VECTOR_INT2) // 3 + 2 != w:
+                raise FlexBufferError(f"{fk.decode()} has {(vty - FBT_VECTOR_INT2) // 3 + 2} elements, expected {w}")
+        elif np.any(u32[tgt // 4 - 1] != w):
+            raise FlexBufferError(f"{fk.decode()} does not have {w} elements")
+        arr[:, c0:c0 + w] = f32[(tgt // 4)[:, None] + np.arange(w)]
+    return arr
 
 
 def decode_gcloud(data) -> PlanarGaussian3d:
@@ -316,28 +463,35 @@ def decode_gcloud(data) -> PlanarGaussian3d:
         if n != n_ref:
             raise FlexBufferError("planes differ in length")
         width = sum(w for _, _, w in fields)
-        arr = np.zeros((n, width), np.float32)
-        for i in range(n):
-            e = pr[i]
-            if e.type == FBT_MAP:
-                d = e.as_dict()
-                vals = [d.get(fk) for fk, _, _ in fields]
-            elif e.is_vector():
-                vals = [e[j] if j < len(e) else None for j in range(len(fields))]
-            else:
-                raise FlexBufferError("plane element is not a struct")
-            for (fk, c0, w), v in zip(fields, vals):
-                if v is None:
-                    continue
-                if w == 1:
-                    arr[i, c0] = v.as_float()
-                else:
-                    a = v.as_float_array()
-                    if len(a) != w:
-                        raise FlexBufferError(f"{fk.decode()} has {len(a)} elements, expected {w}")
-                    arr[i, c0:c0 + w] = a
+        arr = _decode_plane_fast(pr, fields, width)
+        if arr is None:
+            arr = _decode_plane_generic(pr, fields, width, n)
         out.append(arr)
     return PlanarGaussian3d(out[0], out[1], out[2], out[3])
+
+
+def _decode_plane_generic(pr: "Ref", fields, width: int, n: int) -> np.ndarray:
+    arr = np.zeros((n, width), np.float32)
+    for i in range(n):
+        e = pr[i]
+        if e.type == FBT_MAP:
+            d = e.as_dict()
+            vals = [d.get(fk) for fk, _, _ in fields]
+        elif e.is_vector():
+            vals = [e[j] if j < len(e) else None for j in range(len(fields))]
+        else:
+            raise FlexBufferError("plane element is not a struct")
+        for (fk, c0, w), v in zip(fields, vals):
+            if v is None:
+                continue
+            if w == 1:
+                arr[i, c0] = v.as_float()
+            else:
+                a = v.as_float_array()
+                if len(a) != w:
+                    raise FlexBufferError(f"{fk.decode()} has {len(a)} elements, expected {w}")
+                arr[i, c0:c0 + w] = a
+    return arr
 
 
 def write_gcloud(path, cloud: PlanarGaussian3d) -> None:

@@ -108,3 +108,28 @@ def test_loader_switches_on_the_extension(tmp_path):
     assert len(B.load_cloud(tmp_path / "a.ply")) == 64 + 32          # ply.rs:127-129 pads by 32 - n % 32
     with pytest.raises(ValueError):
         B.load_cloud(tmp_path / "a.splat")
+
+
+def test_fast_and_generic_paths_agree(monkeypatch):
+    """encode_gcloud writes every plane with numpy and decode_gcloud reads such regular planes with numpy; documents laid
+    out differently (here: written value by value, every struct next to its vectors) go through the generic reader.
+    Both must give the same cloud, and a scene-sized cloud must not take minutes."""
+    import time
+
+    cloud = B.random_gaussians_3d_seeded(3000, 11)
+    fast, slow = G.encode_gcloud(cloud), G.encode_gcloud_elementwise(cloud)
+    assert fast != slow and _same(G.decode_gcloud(slow), cloud)
+    called = {"generic": 0}
+    orig = G._decode_plane_generic
+    monkeypatch.setattr(G, "_decode_plane_generic", lambda *a: (called.__setitem__("generic", called["generic"] + 1), orig(*a))[1])
+    # both layouts are regular (uniform slots, one key order): the vectorised reader takes all planes of both
+    assert _same(G.decode_gcloud(fast), cloud) and _same(G.decode_gcloud(slow), cloud) and called["generic"] == 0
+    # and with the vectorised reader switched off the generic one gives the same cloud from both
+    monkeypatch.setattr(G, "_decode_plane_fast", lambda *a: None)
+    assert _same(G.decode_gcloud(fast), cloud) and _same(G.decode_gcloud(slow), cloud) and called["generic"] == 8
+    monkeypatch.undo()
+    big = B.random_gaussians_3d_seeded(300_000, 12)
+    t0 = time.time()
+    data = G.encode_gcloud(big)
+    back = G.decode_gcloud(data)
+    assert _same(back, big) and time.time() - t0 < 30.0
