@@ -23,3 +23,16 @@ til = O.render_tiles(cloud, view.to_abi(), u, s.to_abi())
 np.savez_compressed(os.path.join(os.path.dirname(__file__), "c1_small.npz"), n=n, seed=seed, w=w, h=h, scale=scale,
                     keys=keys, order=si, tile_ranges=til["tile_ranges"], image=til["image"][::4, ::4].astype(np.float32))
 print("wrote c1_small.npz", til["n_vis"], til["n_pairs"])
+
+
+def make_gcloud_fixture():
+    """tests/golden/c64_seed5.gcloud: `encode_gcloud(random_gaussians_3d_seeded(64, 5))`, frozen so that a change of the
+    writer's layout or of the reader shows up (tests/test_io_gcloud.py::test_committed_fixture)."""
+    from bevy_gaussian_splatting_b200 import gcloud as G
+
+    with open(os.path.join(os.path.dirname(__file__), "c64_seed5.gcloud"), "wb") as f:
+        f.write(G.encode_gcloud(B.random_gaussians_3d_seeded(64, 5)))
+
+
+make_gcloud_fixture()
+print("wrote c64_seed5.gcloud")

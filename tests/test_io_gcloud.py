@@ -133,3 +133,14 @@ def test_fast_and_generic_paths_agree(monkeypatch):
     data = G.encode_gcloud(big)
     back = G.decode_gcloud(data)
     assert _same(back, big) and time.time() - t0 < 30.0
+
+
+def test_committed_fixture():
+    """tests/golden/c64_seed5.gcloud (written by tests/golden/make_golden.py::make_gcloud_fixture) freezes the codec:
+    the reader returns the seeded cloud bit for bit, and the writer still produces the same bytes."""
+    import os
+
+    path = os.path.join(os.path.dirname(__file__), "golden", "c64_seed5.gcloud")
+    cloud = B.random_gaussians_3d_seeded(64, 5)
+    assert _same(G.read_gcloud(path), cloud)
+    assert G.encode_gcloud(cloud) == open(path, "rb").read()
