@@ -6,6 +6,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
+#include <mutex>
 #include <new>
 #include <vector>
 
@@ -39,14 +41,14 @@ void launch_project(bool f16, bool blocked, const float4* pos, const void* sh, c
 // bin.cu
 void launch_bin_emit(const SplatRec* recs, const uint32_t* perm, FrameCounters* ctr, ChunkCounters* cc, uint32_t* status, int tiles_x,
                      uint32_t capacity, uint32_t* pair_keys, uint32_t* pair_vals, uint32_t n_upper, int sm_count,
-                     cudaStream_t stream);
+                     uint32_t* sticky_need, cudaStream_t stream);
 uint32_t bin_num_tiles(uint32_t n);
 int bin_coop_blocks_per_sm();
 cudaError_t launch_bin_emit_coop(const SplatRec* recs, const uint32_t* perm, FrameCounters* ctr, ChunkCounters* cc,
                                  uint32_t frac_a, uint32_t frac_b, uint32_t num_tiles_total, uint32_t* block_cnt,
                                  int tiles_x, uint32_t capacity, uint32_t* pair_keys, uint32_t* pair_vals,
                                  uint32_t* q_rank, uint32_t* q_off, uint32_t q_cap, unsigned long long* timeline,
-                                 uint32_t grid, cudaStream_t stream);
+                                 uint32_t grid, uint32_t* sticky_need, cudaStream_t stream);
 void launch_tile_ranges(const uint32_t* sorted_tile_ids, const uint32_t* n_ptr, uint2* ranges, uint32_t capacity,
                         int sm_count, cudaStream_t stream);
 // raster.cu
@@ -62,7 +64,8 @@ void launch_status_clear(uint32_t* status, size_t stride, int passes, const uint
 using namespace bgs;
 
 struct bgs_cloud {
-    bgs_context* ctx;
+    bgs_context* ctx;       // owning context; nulled when that context is destroyed first
+    int device;             // the CUDA device the planes live on
     uint32_t n;
     bool f16;
     float4* pos;      // n * 16 B
@@ -118,7 +121,7 @@ struct bgs_context {
     size_t arena_small_bytes = 0;      // [0, small): cleared at frame start; [small, end): look-back status rows,
     bool status_clean_pending = false; // cleared right AFTER a frame on stream2 (off the critical path)
     bool async_pending = false;        // a BGS_FLAG_ASYNC frame has been enqueued and not yet completed
-    const bgs_cloud* pend_cloud = nullptr; FrameConsts pend_fc; bool pend_sort_all = false, pend_by_slot = false;
+    const bgs_cloud* pend_cloud = nullptr; uint32_t pend_n = 0; FrameConsts pend_fc; bool pend_sort_all = false, pend_by_slot = false;
     int pend_tiles_x = 0, pend_tiles_y = 0, pend_W = 0, pend_H = 0; const void* pend_target = nullptr;
     cudaEvent_t ev_done = nullptr, ev_clean = nullptr;
     FrameCounters* ctr = nullptr;
@@ -138,6 +141,11 @@ struct bgs_context {
     bool copy_pending[2] = {false, false};
     const void* last_frame = nullptr;
     FrameCounters* h_ctr = nullptr;    // pinned
+    // largest n_pairs_needed of ANY frame since the last bgs_sync / synchronous render (device word outside the
+    // per-frame arena + its pinned copy): a queued async frame that overflowed the pair buffer is never missed
+    uint32_t* d_sticky = nullptr;
+    uint32_t* h_sticky = nullptr;
+    std::vector<bgs_cloud*> clouds;    // clouds uploaded through this context (their ctx is nulled on destroy)
 
     // last-frame facts (for the debug hooks)
     bool have_frame = false;
@@ -153,6 +161,11 @@ struct bgs_context {
 };
 
 namespace {
+
+// live contexts: clouds may be shared by the contexts of one GPU, so destroying a cloud must clear every
+// context's references to it, and destroying a context must not leave its clouds with a dangling owner
+std::mutex g_registry_mu;
+std::vector<bgs_context*> g_contexts;
 
 bgs_status fail(bgs_context* ctx, bgs_status st, const char* fmt, ...) {
     if (ctx) {
@@ -292,6 +305,10 @@ bgs_status bgs_context_create(int cuda_device, bgs_context** out) {
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev_p0);
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev_p1);
     if (e == cudaSuccess) e = cudaMallocHost(&c->h_ctr, sizeof(FrameCounters));
+    if (e == cudaSuccess) e = cudaMallocHost(&c->h_sticky, 16);
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_sticky, 16);
+    if (e == cudaSuccess) e = cudaMemset(c->d_sticky, 0, 16);
+    if (e == cudaSuccess) memset(c->h_sticky, 0, 16);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, cuda_device);
     if (e == cudaSuccess && getenv("BGS_TIMELINE")) e = cudaMalloc(&c->timeline, 4096 * 8 * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&c->coop, cudaDevAttrCooperativeLaunch, cuda_device);
@@ -321,12 +338,22 @@ bgs_status bgs_context_create(int cuda_device, bgs_context** out) {
         bgs_context_destroy(c);
         return BGS_ECUDA;
     }
+    {
+        std::lock_guard<std::mutex> lk(g_registry_mu);
+        g_contexts.push_back(c);
+    }
     *out = c;
     return BGS_OK;
 }
 
 void bgs_context_destroy(bgs_context* c) {
     if (!c) return;
+    {
+        std::lock_guard<std::mutex> lk(g_registry_mu);
+        g_contexts.erase(std::remove(g_contexts.begin(), g_contexts.end(), c), g_contexts.end());
+        for (bgs_cloud* cl : c->clouds) cl->ctx = nullptr;   // the clouds outlive the context (destroyed by their owner later)
+        c->clouds.clear();
+    }
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->stream2) cudaStreamSynchronize(c->stream2);
@@ -339,6 +366,9 @@ void bgs_context_destroy(bgs_context* c) {
     cudaFree(c->state);
     cudaFree(c->recs); cudaFree(c->extra); cudaFree(c->slot_ids); cudaFree(c->arena); cudaFree(c->frame);
     if (c->h_ctr) cudaFreeHost(c->h_ctr);
+    if (c->h_sticky) cudaFreeHost(c->h_sticky);
+    cudaFree(c->d_sticky);
+    cudaFree(c->timeline);
     for (int i = 0; i < 6; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     for (cudaEvent_t e : {c->ev_fork, c->ev_join, c->ev_p0, c->ev_p1, c->ev_done, c->ev_clean}) if (e) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -355,7 +385,7 @@ static bgs_status upload_common(bgs_context* ctx, uint32_t n, bool f16, const fl
     CU(ctx, cudaSetDevice(ctx->device));
     bgs_cloud* cl = new (std::nothrow) bgs_cloud();
     if (!cl) return BGS_ENOMEM;
-    cl->ctx = ctx; cl->n = n; cl->f16 = f16;
+    cl->ctx = ctx; cl->device = ctx->device; cl->n = n; cl->f16 = f16;
     cl->pos = nullptr; cl->sh = nullptr; cl->rot = nullptr; cl->so = nullptr; cl->blocks = nullptr;
     const size_t sh_bytes = (size_t)n * (f16 ? 96 : 192);
     cudaError_t e = cudaMalloc(&cl->pos, (size_t)n * 16);
@@ -384,6 +414,10 @@ static bgs_status upload_common(bgs_context* ctx, uint32_t n, bool f16, const fl
         bgs_cloud_destroy(cl);
         return fail(ctx, e == cudaErrorMemoryAllocation ? BGS_ENOMEM : BGS_ECUDA, "cloud upload: %s", cudaGetErrorString(e));
     }
+    {
+        std::lock_guard<std::mutex> lk(g_registry_mu);
+        ctx->clouds.push_back(cl);
+    }
     *out = cl;
     return BGS_OK;
 }
@@ -400,9 +434,23 @@ bgs_status bgs_cloud_upload_f16(bgs_context* ctx, uint32_t n, const float* pos_v
 
 void bgs_cloud_destroy(bgs_cloud* cl) {
     if (!cl) return;
-    if (cl->ctx) {
-        cudaSetDevice(cl->ctx->device);
-        if (cl->ctx->last_cloud == cl) { cl->ctx->last_cloud = nullptr; cl->ctx->have_frame = false; }
+    cudaSetDevice(cl->device);
+    {
+        // every live context (clouds are shared by the contexts of one GPU) drops its references: queued frames
+        // that still read the planes are drained first, the debug hooks lose their frame
+        std::lock_guard<std::mutex> lk(g_registry_mu);
+        for (bgs_context* c : g_contexts) {
+            if (c->pend_cloud == cl || c->last_cloud == cl) {
+                if (c->async_pending || c->pend_cloud == cl) {
+                    cudaStreamSynchronize(c->stream);
+                    cudaStreamSynchronize(c->stream2);
+                    cudaStreamSynchronize(c->stream_copy);
+                }
+                if (c->pend_cloud == cl) { c->pend_cloud = nullptr; c->pend_n = 0; }
+                if (c->last_cloud == cl) { c->last_cloud = nullptr; c->have_frame = false; }
+            }
+            c->clouds.erase(std::remove(c->clouds.begin(), c->clouds.end(), cl), c->clouds.end());
+        }
     }
     cudaFree(cl->pos); cudaFree(cl->sh); cudaFree(cl->rot); cudaFree(cl->so); cudaFree(cl->blocks);
     delete cl;
@@ -428,7 +476,7 @@ static bgs_status finish_frame(bgs_context* c) {
         if (s != BGS_OK) return s;
         return BGS_NOT_READY;
     }
-    const uint32_t n = c->pend_cloud ? c->pend_cloud->n : 0;
+    const uint32_t n = c->pend_n;   // (snapshot: the cloud may have been destroyed since the frame was queued)
     c->stage_valid = false;
     c->stats.n = n; c->stats.n_visible = c->h_ctr->n_vis; c->stats.n_pairs = emitted;
     c->stats.rounds = (uint32_t)chunks; c->stats.tiles_saturated = c->h_ctr->tiles_done;
@@ -464,8 +512,23 @@ bgs_status bgs_sync(bgs_context* c) {
     c->copy_pending[0] = c->copy_pending[1] = false;
     CU(c, cudaGetLastError());
     c->async_pending = false;
+    // the sticky maximum covers EVERY frame queued since the last sync, not just the last one (whose counters are
+    // in h_ctr): any of them that needed more pairs than the buffer holds was blended from a truncated list
+    const uint32_t worst = c->h_sticky[0];
+    const bool earlier_overflow = worst > c->cap_pairs;
+    c->h_sticky[0] = 0;
+    CU(c, cudaMemsetAsync(c->d_sticky, 0, 4, c->stream));
     const bgs_status s = finish_frame(c);
-    if (s == BGS_NOT_READY) return fail(c, BGS_NOT_READY, "the last async frame outgrew the pair buffer (now grown): render it again");
+    if (s == BGS_NOT_READY) return fail(c, BGS_NOT_READY, "an async frame outgrew the pair buffer (now grown): render the frames queued since the last bgs_sync again");
+    if (s == BGS_OK && earlier_overflow) {
+        uint64_t want = (uint64_t)worst + worst / 4 + 1024;
+        if (want >= (1ull << 30)) want = (1ull << 30) - 1;
+        if (worst >= LB_VMASK || want <= c->cap_pairs) return fail(c, BGS_ENOMEM, "render: frame needs >= 2^30 (splat, tile) pairs");
+        const bgs_status gs = ensure_pair_scratch(c, (uint32_t)want);
+        if (gs != BGS_OK) return gs;
+        c->have_frame = false;
+        return fail(c, BGS_NOT_READY, "an earlier async frame (not the last one) outgrew the pair buffer (now grown): every frame queued since the last bgs_sync may be truncated, render them again");
+    }
     return s;
 }
 
@@ -488,8 +551,10 @@ bgs_status bgs_render(bgs_context* c, const bgs_cloud* cloud, const bgs_view* vi
     if (W <= 0 || H <= 0 || W > 65535 || H > 65535) return fail(c, BGS_EINVAL, "render: viewport %dx%d out of range", W, H);
     CU(c, cudaSetDevice(c->device));
     if (c->async_pending && !(st->flags & BGS_FLAG_ASYNC)) {
+        // a synchronous render after queued frames completes them first; their failure (including an overflowed
+        // pair list = BGS_NOT_READY) is the caller's to see, so this frame is not rendered on top of it
         const bgs_status ps = bgs_sync(c);
-        if (ps != BGS_OK && ps != BGS_NOT_READY) return ps;
+        if (ps != BGS_OK) return ps;
     }
 
     const uint32_t n = cloud->n;
@@ -657,10 +722,10 @@ bgs_status bgs_render(bgs_context* c, const bgs_cloud* cloud, const bgs_view* vi
                 // the depth sort's spare ping-pong buffers (N words each) hold the large-footprint queue
                 CU(c, launch_bin_emit_coop(c->recs, by_slot ? c->vals[cur] : nullptr, c->ctr, cc, fa, fb, num_tiles,
                                            c->status_bin, tiles_x, c->cap_pairs, c->pkeys[0], c->pvals[0], c->keys[cur ^ 1],
-                                           c->vals[cur ^ 1], c->cap_n, c->timeline, c->bin_grid, q));
+                                           c->vals[cur ^ 1], c->cap_n, c->timeline, c->bin_grid, c->d_sticky, q));
             } else {
                 launch_bin_emit(c->recs, by_slot ? c->vals[cur] : nullptr, c->ctr, cc, c->status_bin, tiles_x, c->cap_pairs,
-                                c->pkeys[0], c->pvals[0], n, c->sm_count, q);
+                                c->pkeys[0], c->pvals[0], n, c->sm_count, c->d_sticky, q);
             }
             ++launches;
             launch_radix_hist(c->pkeys[0], &cc->n_pairs, c->cap_pairs, tile_passes, hist_r, c->sm_count, q);
@@ -698,6 +763,7 @@ bgs_status bgs_render(bgs_context* c, const bgs_cloud* cloud, const bgs_view* vi
         CU(c, cudaEventRecord(c->ev[5], q));
         CU(c, cudaEventRecord(c->ev_done, q));
         CU(c, cudaMemcpyAsync(c->h_ctr, c->ctr, sizeof(FrameCounters), cudaMemcpyDeviceToHost, q));
+        CU(c, cudaMemcpyAsync(c->h_sticky, c->d_sticky, 4, cudaMemcpyDeviceToHost, q));
         if (async_own) CU(c, cudaEventRecord(c->ev_raster[fslot], q));
         if (async_host) {
             CU(c, cudaStreamWaitEvent(c->stream_copy, c->ev_raster[fslot], 0));
@@ -707,7 +773,7 @@ bgs_status bgs_render(bgs_context* c, const bgs_cloud* cloud, const bgs_view* vi
         } else if (out_rgba && !out_is_device_ptr) {
             CU(c, cudaMemcpyAsync(out_rgba, target, frame_bytes, cudaMemcpyDeviceToHost, q));
         }
-        c->pend_cloud = cloud; c->pend_fc = fc; c->pend_sort_all = sort_all; c->pend_by_slot = by_slot;
+        c->pend_cloud = cloud; c->pend_n = n; c->pend_fc = fc; c->pend_sort_all = sort_all; c->pend_by_slot = by_slot;
         c->pend_chunks = rounds;
         c->pend_tiles_x = tiles_x; c->pend_tiles_y = tiles_y; c->pend_W = W; c->pend_H = H; c->pend_target = target;
         // pre-clean the status rows for the next frame, off the critical path
@@ -724,6 +790,8 @@ bgs_status bgs_render(bgs_context* c, const bgs_cloud* cloud, const bgs_view* vi
         CU(c, cudaStreamSynchronize(q));
         CU(c, cudaGetLastError());
         c->launches = launches;
+        c->h_sticky[0] = 0;
+        CU(c, cudaMemsetAsync(c->d_sticky, 0, 4, q));   // synchronous frames report their own overflow right here
         const bgs_status fs = finish_frame(c);
         if (fs == BGS_NOT_READY) continue;   // pair buffer grown: redo the frame
         return fs;

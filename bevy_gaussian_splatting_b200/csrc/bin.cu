@@ -20,7 +20,7 @@ constexpr uint32_t BIN_BIG = 128u;   // larger than this: global queue, drained 
 __global__ void __launch_bounds__(BIN_THREADS)
 bin_emit_kernel(const SplatRec* __restrict__ recs, const uint32_t* __restrict__ perm, FrameCounters* __restrict__ ctr,
                 ChunkCounters* __restrict__ cc, uint32_t* __restrict__ status, int tiles_x, uint32_t capacity,
-                uint32_t* __restrict__ pair_keys, uint32_t* __restrict__ pair_vals) {
+                uint32_t* __restrict__ pair_keys, uint32_t* __restrict__ pair_vals, uint32_t* __restrict__ sticky_need) {
     __shared__ uint32_t s_wtot[BIN_THREADS / 32];
     __shared__ uint32_t s_base;
     __shared__ uint32_t s_tile;
@@ -73,6 +73,7 @@ bin_emit_kernel(const SplatRec* __restrict__ recs, const uint32_t* __restrict__ 
                     const uint32_t need = base + agg;
                     cc->n_pairs_needed = need;
                     cc->n_pairs = need < capacity ? need : capacity;
+                    atomicMax(sticky_need, need);   // survives the per-frame clear: bgs_sync sees every queued frame's need
                 }
             }
         }
@@ -136,7 +137,7 @@ bin_emit_coop_kernel(const SplatRec* __restrict__ recs, const uint32_t* __restri
                      ChunkCounters* __restrict__ cc, uint32_t frac_a, uint32_t frac_b, uint32_t num_tiles_total,
                      uint32_t* __restrict__ block_cnt, int tiles_x, uint32_t capacity, uint32_t* __restrict__ pair_keys,
                      uint32_t* __restrict__ pair_vals, uint32_t* __restrict__ q_rank, uint32_t* __restrict__ q_off,
-                     uint32_t q_cap, unsigned long long* __restrict__ tl) {
+                     uint32_t q_cap, unsigned long long* __restrict__ tl, uint32_t* __restrict__ sticky_need) {
     timeline_stamp(tl, 0);
     __shared__ uint32_t s_wtot[BIN_THREADS / 32];
     __shared__ uint32_t s_wbig[BIN_THREADS / 32];
@@ -218,6 +219,7 @@ bin_emit_coop_kernel(const SplatRec* __restrict__ recs, const uint32_t* __restri
         const uint32_t need = need64 > LB_VMASK ? LB_VMASK : (uint32_t)need64;
         cc->n_pairs_needed = need;
         cc->n_pairs = need < capacity ? need : capacity;
+        atomicMax(sticky_need, need);
     }
     uint32_t run = run64 > LB_VMASK ? LB_VMASK : (uint32_t)run64;
     for (uint32_t base = rlo; base < rhi; base += sub) {
@@ -375,12 +377,12 @@ __global__ void tile_ranges_kernel(const uint32_t* __restrict__ sorted_tile_ids,
 
 void launch_bin_emit(const SplatRec* recs, const uint32_t* perm, FrameCounters* ctr, ChunkCounters* cc, uint32_t* status,
                      int tiles_x, uint32_t capacity, uint32_t* pair_keys, uint32_t* pair_vals, uint32_t n_upper,
-                     int sm_count, cudaStream_t stream) {
+                     int sm_count, uint32_t* sticky_need, cudaStream_t stream) {
     uint32_t blocks = (n_upper + BIN_TILE - 1) / BIN_TILE;
     const uint32_t cap_blocks = (uint32_t)sm_count * 4u;
     if (blocks > cap_blocks) blocks = cap_blocks;
     if (blocks == 0) blocks = 1;
-    bin_emit_kernel<<<blocks, BIN_THREADS, 0, stream>>>(recs, perm, ctr, cc, status, tiles_x, capacity, pair_keys, pair_vals);
+    bin_emit_kernel<<<blocks, BIN_THREADS, 0, stream>>>(recs, perm, ctr, cc, status, tiles_x, capacity, pair_keys, pair_vals, sticky_need);
 }
 uint32_t bin_num_tiles(uint32_t n) { return (n + BIN_TILE - 1) / BIN_TILE; }
 
@@ -393,10 +395,10 @@ cudaError_t launch_bin_emit_coop(const SplatRec* recs, const uint32_t* perm, Fra
                                  uint32_t frac_a, uint32_t frac_b, uint32_t num_tiles_total, uint32_t* block_cnt,
                                  int tiles_x, uint32_t capacity, uint32_t* pair_keys, uint32_t* pair_vals,
                                  uint32_t* q_rank, uint32_t* q_off, uint32_t q_cap, unsigned long long* timeline,
-                                 uint32_t grid, cudaStream_t stream) {
+                                 uint32_t grid, uint32_t* sticky_need, cudaStream_t stream) {
     void* args[] = {(void*)&recs, (void*)&perm, (void*)&ctr, (void*)&cc, (void*)&frac_a, (void*)&frac_b, (void*)&num_tiles_total,
                     (void*)&block_cnt, (void*)&tiles_x, (void*)&capacity, (void*)&pair_keys,
-                    (void*)&pair_vals, (void*)&q_rank, (void*)&q_off, (void*)&q_cap, (void*)&timeline};
+                    (void*)&pair_vals, (void*)&q_rank, (void*)&q_off, (void*)&q_cap, (void*)&timeline, (void*)&sticky_need};
     return cudaLaunchCooperativeKernel((const void*)bin_emit_coop_kernel, dim3(grid), dim3(BIN_THREADS), args, 0, stream);
 }
 

@@ -36,7 +36,11 @@ class CloudTransform:
 class PlanarGaussian3dHandle:
     """A cloud resident in HBM (the role of `Handle<PlanarGaussian3d>` + its prepared GPU planes)."""
 
+    _next_serial = 0
+
     def __init__(self, plugin: "GaussianSplattingPlugin", cloud: PlanarGaussian3d, f16: bool = False):
+        PlanarGaussian3dHandle._next_serial += 1
+        self.serial = PlanarGaussian3dHandle._next_serial   # never reused (id() is, once a handle is collected)
         self._plugin = plugin
         self._lib = plugin._lib
         self.n = len(cloud)
@@ -113,7 +117,7 @@ class GaussianSplattingPlugin:
             return None
         code, dtype, ch = self.FORMATS[fmt]
         v = view.to_abi()
-        key = (dataclasses.astuple(settings), None if transform is None else transform.matrix.tobytes(), asynchronous, id(handle))
+        key = (dataclasses.astuple(settings), None if transform is None else transform.matrix.tobytes(), asynchronous, handle.serial)
         if getattr(self, "_us_cache", (None,))[0] != key:
             s_ = settings.to_abi()
             if asynchronous:

@@ -96,6 +96,9 @@ class CloudSettings:
     binning_rounds: Optional[bool] = None
 
     def to_abi(self) -> abi.bgs_settings:
+        if self.visualize_bounding_box:
+            # VISUALIZE_BOUNDING_BOX (gaussian.wgsl:486-495) is a debug overlay outside the hot path
+            raise NotImplementedError("CloudSettings.visualize_bounding_box is not supported by the C ABI")
         return abi.bgs_settings(
             gaussian_mode=int(self.gaussian_mode),
             rasterize_mode=int(self.rasterize_mode),

@@ -165,8 +165,13 @@ inline PlanarGaussian3d parse_ply_3d(std::istream& in) {
         else if (key == "rot_2") put(out.rotation, 4, 2);
         else if (key == "rot_3") put(out.rotation, 4, 3);
         else if (key.compare(0, 7, "f_rest_") == 0) {
-            const int i = std::atoi(key.c_str() + 7);
-            const int channel = i / 16, coefficient = (i % 15) + 1, idx = coefficient * 3 + channel;
+            // the reference does `parse::<usize>().unwrap()` (io/ply.rs): anything but decimal digits is a hard error
+            const char* dig = key.c_str() + 7;
+            if (*dig == 0 || std::strlen(dig) > 6) throw std::runtime_error("ply: bad property name " + key);
+            for (const char* q = dig; *q; ++q)
+                if (*q < '0' || *q > '9') throw std::runtime_error("ply: bad property name " + key);
+            const unsigned long i = std::strtoul(dig, nullptr, 10);
+            const unsigned long channel = i / 16, coefficient = (i % 15) + 1, idx = coefficient * 3 + channel;
             if (idx < 48) put(out.spherical_harmonic, 48, (size_t)idx);
         }
     }

@@ -24,7 +24,7 @@ def _uniform(s):
     return B.GaussianSplattingPlugin.cloud_uniform(s)
 
 
-def check_against_oracle(plugin, oracle, cloud, settings, view, f16=False, pixel_tol=PIXEL_TOL):
+def check_against_oracle(plugin, oracle, cloud, settings, view, f16=False, pixel_tol=PIXEL_TOL, ref_mode_too=False):
     h = plugin.add_cloud(cloud, f16=f16)
     try:
         img = plugin.render_view(h, settings, view, fmt="rgba32f")
@@ -61,6 +61,11 @@ def check_against_oracle(plugin, oracle, cloud, settings, view, f16=False, pixel
             assert np.abs(rec[drawn, 8:12] - col[drawn]).max() <= 1e-4
         err = float(np.abs(img - til["image"]).max())
         assert err <= pixel_tol, f"pixel L-inf {err}"
+        if ref_mode_too:
+            # the reference's own semantics (instanced quads blended back-to-front, no tiles, no early-out), directly
+            ref = oracle.render_ref(oc, view.to_abi(), u, settings.to_abi())
+            err_ref = float(np.abs(img - ref).max())
+            assert err_ref <= pixel_tol, f"pixel L-inf {err_ref} vs the oracle's ref_mode"
         # the second frame picks kernel variants from the first frame's counts (sort tile size, raster variant)
         img2 = plugin.render_view(h, settings, view, fmt="rgba32f")
         err2 = float(np.abs(img2 - til["image"]).max())
@@ -518,3 +523,25 @@ def test_visibility_render_scene_on_gpu(plugin, oracle):
         assert int((img8[..., :3].max(axis=2) > 8).sum()) <= 8
     finally:
         h.destroy()
+
+
+FULL_SIZE = [
+    # BASELINE.json configs at their full sizes, CUDA vs the oracle (not CUDA vs itself)
+    ("C2", 1_000_000, False, dict(global_scale=0.02)),
+    ("C3", 6_000_000, True, dict(global_scale=0.02)),                                          # the bench.py configuration
+    ("C4-colour", 2_000_000, False, dict(global_scale=0.02, gaussian_mode=B.GaussianMode.Gaussian2d, aabb=True)),
+    ("C4-depth", 2_000_000, False, dict(global_scale=0.02, gaussian_mode=B.GaussianMode.Gaussian2d, aabb=True,
+                                        rasterize_mode=B.RasterizeMode.Depth)),
+    ("C4-normal", 2_000_000, False, dict(global_scale=0.02, gaussian_mode=B.GaussianMode.Gaussian2d, aabb=True,
+                                         rasterize_mode=B.RasterizeMode.Normal)),
+]
+
+
+@pytest.mark.parametrize("name,n,f16,kw", FULL_SIZE, ids=[c[0] for c in FULL_SIZE])
+def test_full_size_vs_oracle(plugin, oracle, name, n, f16, kw):
+    """The benchmarked frame itself (and C2 / C4) against the oracle at 1920x1080: sorted (key, index) entries, tile
+    ranges, per-tile slices and projected geometry bit-exact; pixels <= 1e-3 vs the oracle's tile_mode AND vs its
+    ref_mode (the reference's back-to-front semantics) directly.  Covers the regimes only full sizes reach: 4096-entry
+    sort tiles, key-gen ranges that do not fit shared memory, > 65535-row grids, the footprint queues of the binning."""
+    cloud = B.random_gaussians_3d_seeded(n, 4 if name.startswith("C4") else 0)
+    check_against_oracle(plugin, oracle, cloud, B.CloudSettings(**kw), B.headless_view(1920, 1080), f16=f16, ref_mode_too=True)
