@@ -44,8 +44,56 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+class NvmlClockSampler:
+    """SM clock + throttle reasons sampled in-process through NVML every ~2 ms DURING the timed region (the timed
+    region of the default run lasts ~35 ms: a 100 ms nvidia-smi loop cannot see it)."""
+
+    def __init__(self, gpu_index: int):
+        import pynvml
+
+        self.nv = pynvml
+        pynvml.nvmlInit()
+        self.h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        self.sm, self.reasons, self.stop_flag, self.th = [], 0, False, None
+        self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+
+    def _loop(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                self.reasons |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def start(self):
+        self.th = threading.Thread(target=self._loop, daemon=True)
+        self.th.start()
+
+    def stop(self):
+        self.stop_flag = True
+        if self.th is not None:
+            self.th.join()
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        reasons = sorted(k for k, bit in names.items() if self.reasons & bit)
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_sm, "reasons": reasons,
+                "samples": len(self.sm), "source": "nvml, 2 ms period, inside the timed region"}
+
+
+def make_clock_sampler(gpu_index: int):
+    try:
+        return NvmlClockSampler(gpu_index)
+    except Exception:
+        return ClockSampler(gpu_index)
+
+
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """Fallback: nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -86,10 +134,28 @@ def make_cloud(n: int):
 
 
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_run(steps: int, warmup: int, budget_s: float, cloud=None):
+def host_cores() -> int:
+    """Cores the CPU arm may use: the process's affinity mask, NOT OMP_NUM_THREADS (torchrun exports 1)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def bench_config(views: int, world: int, extra: dict | None = None) -> dict:
+    """The config dict both arms print (same keys, so the driver's same_config check compares like with like)."""
+    cfg = {"workload": WORKLOAD, "n_gaussians": N_GAUSSIANS, "layout": "f16 planar (128 B/gaussian)", "width": WIDTH, "height": HEIGHT,
+           "global_scale": GLOBAL_SCALE, "views": views, "frame_format": "rgba8_srgb",
+           "parallelism": f"view-parallel x{world}, replicated cloud"}
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+def cpu_reference_run(steps: int, warmup: int, budget_s: float, cloud=None, keep_image: bool = False):
     """The reference's path on the host CPU: oracle ref_mode (back-to-front instanced quads, exactly
     the reference's blending semantics), OpenMP over all host cores.  kind = "port": the Rust/WGSL
-    reference cannot be built or run in this image."""
+    reference cannot be built or run in this image.  Best-of-`steps` (the box is shared)."""
     import bevy_gaussian_splatting_b200 as B
     from oracle import oracle as O
 
@@ -99,11 +165,11 @@ def cpu_reference_run(steps: int, warmup: int, budget_s: float, cloud=None):
     view = B.headless_view(WIDTH, HEIGHT)
     s = B.CloudSettings(global_scale=GLOBAL_SCALE)
     u = B.GaussianSplattingPlugin.cloud_uniform(s)
-    cores = O.num_threads()
+    cores = host_cores()
     # size the sample from one probe frame on a 1/6 prefix
     n_probe = min(len(cloud), 1_000_000)
     t0 = time.perf_counter()
-    O.render_ref(cloud.subset(n_probe), view.to_abi(), u, s.to_abi())
+    O.render_ref(cloud.subset(n_probe), view.to_abi(), u, s.to_abi(), threads=cores)
     t_probe = time.perf_counter() - t0
     est_full = t_probe * max(1.0, len(cloud) / n_probe) * 0.6 + 0.2
     frames = steps + warmup
@@ -111,30 +177,33 @@ def cpu_reference_run(steps: int, warmup: int, budget_s: float, cloud=None):
     if est_full * frames > budget_s:
         n_s = int(max(250_000, min(len(cloud), len(cloud) * budget_s / (est_full * frames))))
     sample = cloud.subset(n_s)
+    img = None
     for _ in range(warmup):
-        O.render_ref(sample, view.to_abi(), u, s.to_abi())
+        img = O.render_ref(sample, view.to_abi(), u, s.to_abi(), threads=cores)
     times = []
     for _ in range(steps):
         t0 = time.perf_counter()
-        O.render_ref(sample, view.to_abi(), u, s.to_abi())
+        img = O.render_ref(sample, view.to_abi(), u, s.to_abi(), threads=cores)
         times.append(time.perf_counter() - t0)
-    ms = 1000.0 * float(np.mean(times))
+    ms = 1000.0 * float(np.min(times))
     value = n_s / (ms / 1000.0) / 1e6
     desc = (f"first {n_s} of the {len(cloud)} gaussians of the same cloud, full 1920x1080 frame, oracle ref_mode "
-            f"(key-gen + stable sort + back-to-front quad blending), {steps} frames after {warmup} warm-up")
-    return value, ms, cores, desc, n_s
+            f"(key-gen + stable sort + back-to-front quad blending), best of {steps} frames after {warmup} warm-up, {cores} threads")
+    return value, ms, cores, desc, n_s, (img if keep_image and n_s == len(cloud) else None)
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    value, ms, cores, desc, n_s = cpu_reference_run(args.steps, args.warmup, budget_s=150.0)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    value, ms, cores, desc, n_s, _ = cpu_reference_run(max(args.steps, 5) if args.steps < 50 else 5, min(args.warmup, 2), budget_s=150.0)
     line = {
         "impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": "Msplats/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 3), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32 (f16-rounded inputs)", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample_gaussians": n_s},
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32 (f16-packed inputs)", "data": "synthetic",
+        "config": bench_config(1, world, {"note": "CPU arm: ONE view on rank 0's host cores (the reference has no multi-GPU path); "
+                                                  f"sample_gaussians={n_s}"}),
         "cpu_baseline": {"value": round(value, 3), "unit": "Msplats/s", "cores": cores, "kind": "port", "sample": desc},
         "e2e": {"value": round(value, 3), "unit": "Msplats/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -143,6 +212,29 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------
+def parity_block(plugin, handle, settings, view, cloud, ref_img):
+    """CUDA vs the oracle on the BENCHMARKED frame, outside any timed region: sorted (key, index) entries and tile
+    ranges bit-exact, pixels vs the oracle's ref_mode (the reference's back-to-front semantics) and tile_mode."""
+    from oracle import oracle as O
+
+    oc = cloud.rounded_to_f16()
+    u = plugin.cloud_uniform(settings, None, handle.aabb)
+    img = plugin.render_view(handle, settings, view, fmt="rgba32f")
+    got = plugin.sorted_entries()
+    rng = plugin.tile_ranges()
+    keys = O.keygen(oc.position_visibility, view.to_abi(), u, 32)
+    sk, si = O.radix_sort(keys, 32)
+    til = O.render_tiles(oc, view.to_abi(), u, settings.to_abi())
+    if ref_img is None:
+        ref_img = O.render_ref(oc, view.to_abi(), u, settings.to_abi(), threads=host_cores())
+    return {"config": "the benchmarked C3 frame (6M f16, 1920x1080), rgba32f accumulators",
+            "sorted_bit_exact": bool(np.array_equal(got[:, 0], sk) and np.array_equal(got[:, 1], si)),
+            "ranges_bit_exact": bool(np.array_equal(rng, til["tile_ranges"])),
+            "tile_slices_bit_exact": bool(np.array_equal(plugin.tile_entries(), til["tile_entries"])),
+            "linf_vs_ref_mode": float(np.abs(img - ref_img).max()), "linf_vs_tile_mode": float(np.abs(img - til["image"]).max()),
+            "tolerance": 1e-3}
+
+
 def run_cuda(args):
     import torch
 
@@ -164,21 +256,24 @@ def run_cuda(args):
 
     # FRAMES_IN_FLIGHT contexts on this GPU share the cloud; consecutive frames alternate between them, so one
     # frame's latency-bound front (key-gen, sorts, binning) overlaps the previous frame's raster.  Each context
-    # has its own stream + scratch (bgs.h: "distinct contexts may be used concurrently").
-    # (one NCCL communicator per context: 3 per GPU is validated at 2 GPUs, 2 per GPU at 8 GPUs -- larger jobs keep
-    # the configuration that was measured)
-    frames_in_flight = FRAMES_IN_FLIGHT if world <= 2 else min(FRAMES_IN_FLIGHT, 2)
+    # has its own streams + scratch (bgs.h: "distinct contexts may be used concurrently"); a rank's contexts share
+    # ONE NCCL communicator.
+    frames_in_flight = FRAMES_IN_FLIGHT
     plugins = [B.GaussianSplattingPlugin(local_rank) for _ in range(frames_in_flight)]
     plugin = plugins[0]
     cloud = make_cloud(N_GAUSSIANS)
     handle = plugin.add_cloud(cloud, f16=True)
     settings = B.CloudSettings(global_scale=GLOBAL_SCALE)
-    sessions = [MultiViewSession(rank, world, 0, plugin=p if world > 1 else None) for p in plugins]
+    sessions = []
+    for i, p in enumerate(plugins):
+        sessions.append(MultiViewSession(rank, world, 0, plugin=p if world > 1 else None,
+                                         share_comm_of=sessions[0] if (world > 1 and i > 0) else None))
     sess = sessions[0]
     view = sess.view(WIDTH, HEIGHT) if world > 1 else B.headless_view(WIDTH, HEIGHT)
     frame_bytes = WIDTH * HEIGHT * 4
     dev = torch.device("cuda", local_rank)
     streams = [torch.cuda.ExternalStream(p.stream_ptr, device=dev) for p in plugins]
+    copy_streams = [torch.cuda.ExternalStream(p.copy_stream_ptr, device=dev) for p in plugins]
     all_frames = [torch.empty(world * frame_bytes, dtype=torch.uint8, device="cuda") if (world > 1 and rank == 0) else None
                   for _ in plugins]
 
@@ -209,20 +304,32 @@ def run_cuda(args):
         step(i)
     assert sync_all()
     barrier()
-    clocks = ClockSampler(local_rank)
+    clocks = make_clock_sampler(local_rank)
     if rank == 0:
         clocks.start()
     e0 = torch.cuda.Event(enable_timing=True)
-    e1 = [torch.cuda.Event(enable_timing=True) for _ in plugins]
+    e1 = [torch.cuda.Event(enable_timing=True) for _ in range(2 * len(plugins))]
     e0.record(streams[0])
     for i in range(args.steps):
         step(i)
-    for ev, st_ in zip(e1, streams):
+    # the window ends when the LAST work of every stream has finished: render streams and copy/comm streams
+    # (async frames are gathered over NCCL on the copy/comm stream)
+    for ev, st_ in zip(e1, streams + copy_streams):
         ev.record(st_)
     assert sync_all(), "pair buffer overflowed inside the timed region"
     barrier()
-    ms_total = max(e0.elapsed_time(ev) for ev in e1)     # device time from the first frame's start to the last frame's end
+    ms_total = max(e0.elapsed_time(ev) for ev in e1)     # device time from the first frame's start to the last frame's / gather's end
     clk = clocks.stop() if rank == 0 else None
+    # ---- multi-GPU correctness on hardware: rank 0 re-renders every rank's view locally and compares it with the
+    #      gathered frames, byte for byte (outside the timed region)
+    gather_ok = None
+    if world > 1 and rank == 0:
+        gather_ok = True
+        k_last = (args.steps - 1) % frames_in_flight
+        gathered = all_frames[k_last].cpu().numpy().reshape(world, HEIGHT, WIDTH, 4)
+        for r in range(world):
+            local = plugin.render_view(handle, settings, MultiViewSession(r, world, 0).view(WIDTH, HEIGHT), fmt="rgba8_srgb")
+            gather_ok = gather_ok and bool(np.array_equal(local, gathered[r]))
     # per-frame / per-stage times (live CUDA events inside the library), one frame at a time on an idle GPU
     frame_us, stage_rows = [], []
     for _ in range(min(args.steps, 100)):
@@ -271,10 +378,10 @@ def run_cuda(args):
     n, nv, I = fs.n, fs.n_visible, int(fs.n_pairs)
     depth_passes = 4
     alg = {
-        "keygen": 16 * n + 8 * nv,                                        # positions in, compacted (key,id) out
-        "depth_sort": 4 * nv + depth_passes * 16 * nv,                    # histogram read + P x (8 in + 8 out)
+        "keygen": 16 * n + 4 * (n // 32) * 2 + (16 + 12) * nv,            # positions in, mask bits out + in, visible re-read + (key,id,slot) out
+        "depth_sort": depth_passes * 16 * nv,                             # P x (8 in + 8 out)  (histograms come from key-gen)
         "project": 4 * nv + (16 + 112) * nv + 48 * nv,                    # ids + f16 attrs (pos 16 + 16 + 96) + record
-        "bin": 8 * nv + 8 * I + (4 * I + 2 * 16 * I) + 4 * I + 8 * fs.tiles_x * fs.tiles_y,
+        "bin": 2 * 12 * nv + 8 * I + (4 * I + 2 * 16 * I) + 8 * fs.tiles_x * fs.tiles_y,   # 2 x (perm + bbox) + pairs out + hist read + 2 passes
         "raster": 4 * I + 48 * I + 4 * WIDTH * HEIGHT,
     }
     names = ["keygen", "depth_sort", "project", "bin", "raster"]
@@ -283,13 +390,20 @@ def run_cuda(args):
         us = float(stage_med[i])
         gbs = alg[nm] / (us * 1e-6) / 1e9 if us > 0 else 0.0
         stages.append({"stage": nm, "us": round(us, 1), "alg_bytes": int(alg[nm]), "gbs": round(gbs, 1), "frac": round(gbs / peak, 4)})
+    # north_star's "projection + sort stages": key-gen -> (depth sort || projection), as ONE segment of the frame
+    front_us = float(stage_med[5] - stage_med[3] - stage_med[4])
+    front_bytes = alg["keygen"] + alg["depth_sort"] + alg["project"]
+    proj_sort = {"what": "key-gen + depth sort + projection (sort and projection overlap on two streams)", "us": round(front_us, 1),
+                 "alg_bytes": int(front_bytes), "gbs": round(front_bytes / (front_us * 1e-6) / 1e9, 1),
+                 "frac": round(front_bytes / (front_us * 1e-6) / 1e9 / peak, 4), "target": 0.70}
     dom = max(stages, key=lambda s: s["us"])
     traffic_path = os.path.join(ROOT, "profiles", "traffic.json")
     traffic = None
     if os.path.exists(traffic_path):
         traffic = json.load(open(traffic_path)).get(dom["stage"])
     roofline = {"kernel": dom["stage"], "bound": "hbm", "achieved": dom["gbs"], "peak": peak, "unit": "GB/s",
-                "frac": dom["frac"], "traffic": traffic, "peak_source": peak_src,
+                "frac": dom["frac"], "traffic": traffic, "traffic_source": "static: ncu dram__bytes of the committed capture under profiles/ (not measured in this run)",
+                "peak_source": peak_src,
                 "note": "dominant kernel by time; raster is bound by instruction issue, not by HBM -- see roofline.issue and stages[]"}
     # the dominant kernel's OWN roofline: warp-instructions it executes per launch (ncu, profiles/traffic.json) against
     # the SMs' issue rate (4 warp-instructions per SM cycle) at the SM clock sampled during the timed region
@@ -304,11 +418,25 @@ def run_cuda(args):
                                  "unit": "G warp-inst/s", "frac": round(ach_gi / peak_gi, 4),
                                  "source": "ncu smsp__inst_executed.sum of the committed capture (profiles/), live CUDA-event time"}
 
-    # ---- CPU baseline beside it (rank 0, N=1 only): bounded sample, ~10-30 s of CPU work
-    cpu = None
+    # ---- CPU baseline beside it + parity of the benchmarked frame (rank 0, N=1 only; outside the timed regions)
+    cpu, parity = None, None
     if world == 1 and not args.no_cpu_baseline:
-        v, ms, cores, desc, _ = cpu_reference_run(steps=3, warmup=1, budget_s=25.0, cloud=cloud)
+        v, ms, cores, desc, _, ref_img = cpu_reference_run(steps=3, warmup=1, budget_s=25.0, cloud=cloud, keep_image=True)
         cpu = {"value": round(v, 3), "unit": "Msplats/s", "cores": cores, "kind": "port", "sample": desc}
+        parity = parity_block(plugin, handle, settings, view, cloud, ref_img)
+    # ---- the raw generator scale (global_scale 1.0, SURVEY.md §8d "also report 1.0 if it completes"): informational
+    raw = None
+    if world == 1 and not args.no_cpu_baseline:
+        s_raw = B.CloudSettings(global_scale=1.0)
+        rows = []
+        for _ in range(12):
+            plugin.render_view(handle, s_raw, view, fmt="rgba8_srgb", to_host=False)
+            rows.append(plugin.stage_times_us())
+        med = np.median(np.array(rows[4:]), axis=0)
+        fr = plugin.frame_stats()
+        raw = {"config": "same cloud and camera, global_scale 1.0 (raw generator), one frame at a time", "frame_ms_p50": round(float(med[5]) / 1000.0, 4),
+               "Msplats_per_s": round(N_GAUSSIANS / float(med[5]), 1), "rounds": int(fr.rounds), "n_pairs_emitted": int(fr.n_pairs),
+               "stage_us": [round(float(x), 1) for x in med[:5]]}
 
     views = world
     value = N_GAUSSIANS * views / (ms_step / 1000.0) / 1e6
@@ -316,17 +444,20 @@ def run_cuda(args):
         "metric": METRIC, "value": round(value, 1), "unit": "Msplats/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32 (f16-packed inputs)", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "views": views, "parallelism": f"view-parallel x{world}, replicated cloud",
-                   "n_visible": nv, "n_pairs": I, "l2": "inputs larger than L2 (768 MB cloud vs 126 MB)",
-                   "frames_in_flight": frames_in_flight,
-                   "frame_format": "rgba8_srgb"},
+        "config": bench_config(views, world, {"n_visible": nv, "n_pairs": I, "l2": "inputs larger than L2 (768 MB cloud vs 126 MB)",
+                                              "frames_in_flight": frames_in_flight,
+                                              "timing": "value: 3 frames in flight, CUDA events over render + copy/comm streams; "
+                                                        "stages[] / frame_ms_*: one frame at a time on an idle GPU"}),
         "frame_ms_p50": round(float(np.percentile(frame_us, 50)) / 1000.0, 4),
         "frame_ms_p95": round(float(np.percentile(frame_us, 95)) / 1000.0, 4),
+        "secondary_metric": {"name": "frame-time p50 ms (one frame at a time)", "value": round(float(np.percentile(frame_us, 50)) / 1000.0, 4),
+                             "fps": round(1e6 / float(np.percentile(frame_us, 50)), 1), "target_fps": 500},
         "fps_per_gpu": round(1000.0 / ms_step, 1),
         "e2e": {"value": round(N_GAUSSIANS * views / (e2e_ms / 1000.0) / 1e6, 1), "unit": "Msplats/s",
                 "ms_per_step": round(e2e_ms, 4), "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": frame_bytes},
         "gpu_launches": int(launches_per_frame * args.steps),
-        "roofline": roofline, "stages": stages, "cpu_baseline": cpu, "clocks": clk,
+        "roofline": roofline, "proj_sort_roofline": proj_sort, "stages": stages, "cpu_baseline": cpu, "parity": parity,
+        "gathered_frames_verified": gather_ok, "raw_scale_1": raw, "clocks": clk,
     }
     print(json.dumps(line), flush=True)
     for se in sessions:

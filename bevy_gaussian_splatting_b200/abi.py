@@ -90,6 +90,7 @@ SYMBOLS = [
     ("bgs_stage_times_us", C.c_int, [_P, C.POINTER(C.c_float * 6)]),
     ("bgs_last_error", C.c_char_p, [_P]),
     ("bgs_context_stream", _P, [_P]),
+    ("bgs_context_copy_stream", _P, [_P]),
     ("bgs_frame_device_ptr", _P, [_P]),
     ("bgs_last_launch_count", C.c_uint32, [_P]),
     ("bgs_nccl_unique_id", C.c_int, [_P]),

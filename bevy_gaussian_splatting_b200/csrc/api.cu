@@ -25,11 +25,11 @@ cudaError_t launch_keygen_coop(const float4* pos, uint32_t n, const FrameConsts&
 void launch_culled_flags(const float4* pos, uint32_t n, const FrameConsts& fc, uint32_t* flags, cudaStream_t stream);
 // radix.cu
 uint32_t radix_num_tiles(uint32_t capacity);
-void launch_radix_hist(const uint32_t* keys, const uint32_t* n_ptr, uint32_t capacity, int passes, uint32_t* hist,
-                       int sm_count, cudaStream_t stream);
-void launch_onesweep(const uint32_t* keys_in, const uint32_t* vals_in, uint32_t* keys_out, uint32_t* vals_out,
-                     const uint32_t* n_ptr, uint32_t capacity, uint32_t n_hint, const uint32_t* hist, uint32_t* status,
-                     uint32_t* tile_ctr, int shift, int sm_count, cudaStream_t stream, unsigned long long* tl = nullptr);
+int radix_coop_blocks_per_sm(int items);
+cudaError_t launch_radix_sort(uint32_t* keys0, uint32_t* vals0, uint32_t* keys1, uint32_t* vals1, const uint32_t* n_ptr,
+                              uint32_t capacity, uint32_t n_hint, uint32_t* hist, int compute_hist, void* status,
+                              size_t status_stride, uint32_t epoch, uint32_t* barrier, int passes, int shift0, uint2* ranges,
+                              int sm_count, int coop_per_sm, cudaStream_t stream, unsigned long long* tl);
 // project.cu
 void launch_depth_range(const float4* pos, uint32_t n, const uint32_t* sorted_payload, const uint32_t* slot_ids,
                         FrameCounters* ctr, const FrameConsts& fc, cudaStream_t stream);
@@ -37,7 +37,9 @@ void launch_repack(bool f16, const void* pos, const void* sh, const void* rot, c
                    cudaStream_t stream);
 void launch_project(bool f16, bool blocked, const float4* pos, const void* sh, const void* rot, const void* so,
                     const uint32_t* index_list, int by_slot, const FrameCounters* ctr, const FrameConsts& fc,
-                    SplatRec* recs, float4* extra, uint32_t n_hint, cudaStream_t stream);
+                    SplatRec* recs, float4* extra, uint32_t n_hint, int sm_count, int ctas_per_sm, const float* cutoff_tab,
+                    cudaStream_t stream);
+void launch_cutoff_table(float* tab, cudaStream_t stream);
 // bin.cu
 void launch_bin_emit(const SplatRec* recs, const uint32_t* perm, FrameCounters* ctr, ChunkCounters* cc, uint32_t* status, int tiles_x,
                      uint32_t capacity, uint32_t* pair_keys, uint32_t* pair_vals, uint32_t n_upper, int sm_count,
@@ -49,8 +51,6 @@ cudaError_t launch_bin_emit_coop(const SplatRec* recs, const uint32_t* perm, Fra
                                  int tiles_x, uint32_t capacity, uint32_t* pair_keys, uint32_t* pair_vals,
                                  uint32_t* q_rank, uint32_t* q_off, uint32_t q_cap, unsigned long long* timeline,
                                  uint32_t grid, uint32_t* sticky_need, cudaStream_t stream);
-void launch_tile_ranges(const uint32_t* sorted_tile_ids, const uint32_t* n_ptr, uint2* ranges, uint32_t capacity,
-                        int sm_count, cudaStream_t stream);
 // raster.cu
 void launch_raster(int mode, bool large_footprints, const SplatRec* recs, const float4* extra, const uint32_t* tile_entries,
                    const uint2* ranges, int W, int H, int tiles_x, int tiles_y, void* out, uint32_t format,
@@ -58,7 +58,6 @@ void launch_raster(int mode, bool large_footprints, const SplatRec* recs, const 
 void launch_raster_round(const SplatRec* recs, const uint32_t* tile_entries, const uint2* ranges, int W, int H, int tiles_x,
                          int tiles_y, void* out, uint32_t format, float4* state, unsigned char* tile_done,
                          uint32_t* tiles_done, int first, int last, cudaStream_t stream);
-void launch_status_clear(uint32_t* status, size_t stride, int passes, const uint32_t* n_ptr, int sm_count, cudaStream_t stream);
 }  // namespace bgs
 
 using namespace bgs;
@@ -80,6 +79,8 @@ struct bgs_context {
     int sm_count = 148;
     int coop = 0;                 // device supports cooperative launch
     uint32_t kg_grid = 0, bin_grid = 0;   // co-resident grid sizes of the cooperative kernels
+    int rs_per_sm = 0;                    // co-resident radix-sort CTAs per SM (radix.cu)
+    uint32_t sort_epoch = 0;              // look-back status epoch: +1 per sort launch (status words never need clearing)
     cudaStream_t stream = nullptr;    // render stream (high priority): everything but the projection
     cudaStream_t stream2 = nullptr;   // projection runs here, beside the depth sort
     cudaEvent_t ev[6] = {};
@@ -114,23 +115,23 @@ struct bgs_context {
     uint32_t cap_pairs = 0;
     uint32_t* pkeys[2] = {nullptr, nullptr};
     uint32_t* pvals[2] = {nullptr, nullptr};
-    // zeroed-per-frame arena: counters | hist | keygen status | bin status | ranges | radix status
+    // zeroed-per-frame arena: counters | hist | keygen status | bin status | ranges | done bytes
     uint8_t* arena = nullptr;
     size_t arena_bytes = 0;
     uint32_t arena_n = 0, arena_pairs = 0, arena_tiles = 0;
-    size_t arena_small_bytes = 0;      // [0, small): cleared at frame start; [small, end): look-back status rows,
-    bool status_clean_pending = false; // cleared right AFTER a frame on stream2 (off the critical path)
+    // look-back status rows of the two sorts (64-bit epoch-tagged words, cleared once at allocation)
+    void* status_depth = nullptr;      // [4][tiles(n)][256]
+    void* status_pairs = nullptr;      // [4][tiles(cap_pairs)][256]
+    uint32_t status_n = 0, status_np = 0;
     bool async_pending = false;        // a BGS_FLAG_ASYNC frame has been enqueued and not yet completed
     const bgs_cloud* pend_cloud = nullptr; uint32_t pend_n = 0; FrameConsts pend_fc; bool pend_sort_all = false, pend_by_slot = false;
     int pend_tiles_x = 0, pend_tiles_y = 0, pend_W = 0, pend_H = 0; const void* pend_target = nullptr;
-    cudaEvent_t ev_done = nullptr, ev_clean = nullptr;
+    cudaEvent_t ev_done = nullptr;
     FrameCounters* ctr = nullptr;
     uint32_t* hist = nullptr;          // [8 + 4 * MAX_CHUNKS][256]: depth passes 0..3, pair passes 4..7 (round 0), 8 + 4r.. (round r)
     uint32_t* status_keygen = nullptr;
     uint32_t* status_bin = nullptr;
-    uint2* ranges = nullptr;
-    uint32_t* status_depth = nullptr;  // [4][tiles(n)][256]
-    uint32_t* status_pairs = nullptr;  // [4][tiles(cap_pairs)][256]
+    uint2* ranges = nullptr;           // per tile (~start, end) into the sorted pair list (0, 0 = empty)
     // frame
     void* frame = nullptr;            // frames[0]
     void* frame_alt = nullptr;        // frames[1]: async frames delivered to host memory alternate targets so
@@ -143,6 +144,7 @@ struct bgs_context {
     FrameCounters* h_ctr = nullptr;    // pinned
     // largest n_pairs_needed of ANY frame since the last bgs_sync / synchronous render (device word outside the
     // per-frame arena + its pinned copy): a queued async frame that overflowed the pair buffer is never missed
+    float* cutoff_tab = nullptr;       // adaptive cutoff of every f16 opacity value (project.cu)
     uint32_t* d_sticky = nullptr;
     uint32_t* h_sticky = nullptr;
     std::vector<bgs_cloud*> clouds;    // clouds uploaded through this context (their ctx is nulled on destroy)
@@ -247,22 +249,45 @@ bgs_status ensure_arena(bgs_context* c, uint32_t n, uint32_t pairs, uint32_t til
     const size_t range_entries = chunk_tiles * MAX_CHUNKS > tiles ? chunk_tiles * MAX_CHUNKS : tiles;
     const size_t o_rng = off; off = align_up(off + range_entries * 8, 256);
     const size_t o_done = off; off = align_up(off + chunk_tiles, 256);
-    const size_t o_sd = off; off = align_up(off + (size_t)4 * radix_num_tiles(n) * 256 * 4, 256);
-    const size_t o_sp = off; off = align_up(off + (size_t)4 * radix_num_tiles(pairs) * 256 * 4, 256);
     CU(c, cudaMalloc(&c->arena, off));
     c->arena_bytes = off;
-    c->arena_small_bytes = o_sd;
-    c->status_clean_pending = false;
     c->ctr = reinterpret_cast<FrameCounters*>(c->arena + o_ctr);
     c->hist = reinterpret_cast<uint32_t*>(c->arena + o_hist);
     c->status_keygen = reinterpret_cast<uint32_t*>(c->arena + o_skg);
     c->status_bin = reinterpret_cast<uint32_t*>(c->arena + o_sbin);
     c->ranges = reinterpret_cast<uint2*>(c->arena + o_rng);
     c->tile_done = c->arena + o_done;
-    c->status_depth = reinterpret_cast<uint32_t*>(c->arena + o_sd);
-    c->status_pairs = reinterpret_cast<uint32_t*>(c->arena + o_sp);
     c->arena_n = n; c->arena_pairs = pairs; c->arena_tiles = tiles;
     return BGS_OK;
+}
+
+// look-back status rows of the sorts: 4 passes x tiles x 256 digits x 8 B, epoch-tagged (radix.cu), so they are
+// cleared exactly once -- here -- and never again
+bgs_status ensure_status(bgs_context* c, uint32_t n, uint32_t pairs) {
+    if (n > c->status_n) {
+        cudaFree(c->status_depth); c->status_depth = nullptr; c->status_n = 0;
+        const size_t bytes = (size_t)4 * radix_num_tiles(n) * 256 * 8;
+        CU(c, cudaMalloc(&c->status_depth, bytes));
+        CU(c, cudaMemsetAsync(c->status_depth, 0, bytes, c->stream));
+        c->status_n = n;
+    }
+    if (pairs > c->status_np) {
+        cudaFree(c->status_pairs); c->status_pairs = nullptr; c->status_np = 0;
+        const size_t bytes = (size_t)4 * radix_num_tiles(pairs) * 256 * 8;
+        CU(c, cudaMalloc(&c->status_pairs, bytes));
+        CU(c, cudaMemsetAsync(c->status_pairs, 0, bytes, c->stream));
+        c->status_np = pairs;
+    }
+    return BGS_OK;
+}
+
+uint32_t next_epoch(bgs_context* c) {
+    if (++c->sort_epoch >= (1u << 30)) {     // (2^30 sorts later) start over from clean rows
+        if (c->status_depth) cudaMemsetAsync(c->status_depth, 0, (size_t)4 * radix_num_tiles(c->status_n) * 256 * 8, c->stream);
+        if (c->status_pairs) cudaMemsetAsync(c->status_pairs, 0, (size_t)4 * radix_num_tiles(c->status_np) * 256 * 8, c->stream);
+        c->sort_epoch = 1;
+    }
+    return c->sort_epoch;
 }
 
 bgs_status ensure_frame(bgs_context* c, size_t bytes) {
@@ -296,7 +321,6 @@ bgs_status bgs_context_create(int cuda_device, bgs_context** out) {
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_done, cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_clean, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream_copy, cudaStreamNonBlocking);
     for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
         e = cudaEventCreateWithFlags(&c->ev_raster[i], cudaEventDisableTiming);
@@ -308,6 +332,8 @@ bgs_status bgs_context_create(int cuda_device, bgs_context** out) {
     if (e == cudaSuccess) e = cudaMallocHost(&c->h_sticky, 16);
     if (e == cudaSuccess) e = cudaMalloc(&c->d_sticky, 16);
     if (e == cudaSuccess) e = cudaMemset(c->d_sticky, 0, 16);
+    if (e == cudaSuccess) e = cudaMalloc(&c->cutoff_tab, 65536 * sizeof(float));
+    if (e == cudaSuccess) { launch_cutoff_table(c->cutoff_tab, c->stream); e = cudaStreamSynchronize(c->stream); }
     if (e == cudaSuccess) memset(c->h_sticky, 0, 16);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, cuda_device);
     if (e == cudaSuccess && getenv("BGS_TIMELINE")) e = cudaMalloc(&c->timeline, 4096 * 8 * sizeof(unsigned long long));
@@ -318,7 +344,8 @@ bgs_status bgs_context_create(int cuda_device, bgs_context** out) {
         if (const char* e = getenv("BGS_COOP_BLOCKS")) lim = atoi(e) > 0 ? atoi(e) : 4;   // second context's kernels)
         c->kg_grid = (uint32_t)(c->sm_count * (kb > lim ? lim : kb));
         c->bin_grid = (uint32_t)(c->sm_count * (bb > lim ? lim : bb));
-        if (c->kg_grid == 0 || c->bin_grid == 0 || c->kg_grid > 4096 || c->bin_grid > 4096) c->coop = 0;
+        c->rs_per_sm = radix_coop_blocks_per_sm(16);
+        if (c->kg_grid == 0 || c->bin_grid == 0 || c->kg_grid > 4096 || c->bin_grid > 4096 || c->rs_per_sm == 0) c->coop = 0;
     }
     if (const char* fr = getenv("BGS_CHUNK_FRACS")) {
         // tuning knob: cumulative round boundaries out of 65536, e.g. "256,2048,16384" = 4 rounds
@@ -331,6 +358,11 @@ bgs_status bgs_context_create(int cuda_device, bgs_context** out) {
         }
         for (int j = k + 1; j <= MAX_CHUNKS; ++j) c->chunk_frac[j] = 65536u;
         c->chunk_count = k + 1;
+    }
+    if (e == cudaSuccess && !c->coop) {
+        snprintf(c->err, sizeof(c->err), "device %d cannot co-schedule the cooperative kernels (sm_100a B200 expected)", cuda_device);
+        fprintf(stderr, "libbgs: %s\n", c->err);
+        e = cudaErrorNotSupported;
     }
     if (e != cudaSuccess) {
         // no CUDA device / driver: the product has no CPU path
@@ -368,9 +400,11 @@ void bgs_context_destroy(bgs_context* c) {
     if (c->h_ctr) cudaFreeHost(c->h_ctr);
     if (c->h_sticky) cudaFreeHost(c->h_sticky);
     cudaFree(c->d_sticky);
+    cudaFree(c->cutoff_tab);
     cudaFree(c->timeline);
     for (int i = 0; i < 6; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
-    for (cudaEvent_t e : {c->ev_fork, c->ev_join, c->ev_p0, c->ev_p1, c->ev_done, c->ev_clean}) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : {c->ev_fork, c->ev_join, c->ev_p0, c->ev_p1, c->ev_done}) if (e) cudaEventDestroy(e);
+    cudaFree(c->status_depth); cudaFree(c->status_pairs);
     if (c->stream) cudaStreamDestroy(c->stream);
     if (c->stream2) cudaStreamDestroy(c->stream2);
     delete c;
@@ -632,16 +666,11 @@ bgs_status bgs_render(bgs_context* c, const bgs_cloud* cloud, const bgs_view* vi
     for (int attempt = 0; attempt < 4; ++attempt) {
         s = ensure_arena(c, n, c->cap_pairs, num_tiles);
         if (s != BGS_OK) return s;
+        s = ensure_status(c, n, c->cap_pairs);
+        if (s != BGS_OK) return s;
         cudaStream_t q = c->stream;
         uint32_t launches = 0;
-        if (c->status_clean_pending) {
-            // the big look-back status rows were cleared on stream2 right after the previous frame
-            CU(c, cudaStreamWaitEvent(q, c->ev_clean, 0));
-            CU(c, cudaMemsetAsync(c->arena, 0, c->arena_small_bytes, q));
-        } else {
-            CU(c, cudaMemsetAsync(c->arena, 0, c->arena_bytes, q));
-        }
-        c->status_clean_pending = false;
+        CU(c, cudaMemsetAsync(c->arena, 0, c->arena_bytes, q));   // counters, histograms, ranges: ~0.6 MB
         CU(c, cudaEventRecord(c->ev[0], q));
         // ---- stage 1: key-gen (+ stable compaction of the visible set)
         // compact mode: keys[0][slot], slot_ids[slot] = gaussian index, vals[0][slot] = slot (sort payload)
@@ -664,30 +693,25 @@ bgs_status bgs_render(bgs_context* c, const bgs_cloud* cloud, const bgs_view* vi
         const uint32_t n_hint = c->n_vis_hint ? c->n_vis_hint + c->n_vis_hint / 4 + 1024 : n;
         // Depth colouring needs sorted[1] / sorted[N-1]: the projection then waits for the sort
         const bool overlap = by_slot && st->rasterize_mode != BGS_RASTERIZE_DEPTH;
+        if (overlap) CU(c, cudaEventRecord(c->ev_fork, q));
+        // ---- stage 2: depth radix sort: all P = depth_bits / 8 digit places in ONE cooperative launch (enqueued before
+        //      the projection so its one-CTA-per-SM grid becomes resident first; the projection fills the other half)
+        CU(c, launch_radix_sort(c->keys[0], c->vals[0], c->keys[1], c->vals[1], &c->ctr->n_sort, n,
+                                sort_all ? n : (c->n_vis_hint ? c->n_vis_hint : n), c->hist, hist_fused ? 0 : 1, c->status_depth,
+                                (size_t)radix_num_tiles(c->status_n) * 256, next_epoch(c), &c->ctr->barrier[1], depth_passes, 0,
+                                nullptr, c->sm_count, c->rs_per_sm, q,
+                                (c->timeline && getenv("BGS_TIMELINE_SORT")) ? c->timeline : nullptr));
+        ++launches;
         if (overlap) {
-            CU(c, cudaEventRecord(c->ev_fork, q));
             CU(c, cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
             CU(c, cudaEventRecord(c->ev_p0, c->stream2));
             launch_project(cloud->f16, cloud->blocks != nullptr, cloud->pos, cloud->blocks ? cloud->blocks : cloud->sh, cloud->rot, cloud->so, c->slot_ids, 1, c->ctr, fc, c->recs,
-                           raster_mode == 2 ? c->extra : nullptr, n_hint < n ? n_hint : n, c->stream2);
+                           raster_mode == 2 ? c->extra : nullptr, n_hint < n ? n_hint : n, c->sm_count, 2, c->cutoff_tab, c->stream2);
             ++launches;
             CU(c, cudaEventRecord(c->ev_p1, c->stream2));
             CU(c, cudaEventRecord(c->ev_join, c->stream2));
         }
-        // ---- stage 2: depth radix sort (P = depth_bits / 8 onesweep passes)
-        if (!hist_fused) {
-            launch_radix_hist(c->keys[0], &c->ctr->n_sort, n, depth_passes, c->hist, c->sm_count, q);
-            ++launches;
-        }
-        int cur = 0;
-        const size_t depth_status_stride = (size_t)radix_num_tiles(c->arena_n) * 256;
-        for (int p = 0; p < depth_passes; ++p) {
-            launch_onesweep(c->keys[cur], c->vals[cur], c->keys[cur ^ 1], c->vals[cur ^ 1], &c->ctr->n_sort, n,
-                            sort_all ? n : (c->n_vis_hint ? c->n_vis_hint : n), c->hist + p * 256, c->status_depth + p * depth_status_stride, &c->ctr->tile_ctr[1 + p],
-                            8 * p, c->sm_count, q, (p == 1 && c->timeline && getenv("BGS_TIMELINE_SORT")) ? c->timeline : nullptr);
-            ++launches;
-            cur ^= 1;
-        }
+        const int cur = depth_passes & 1;
         c->depth_result = cur;
         CU(c, cudaEventRecord(c->ev[2], q));
         if (overlap) {
@@ -701,7 +725,7 @@ bgs_status bgs_render(bgs_context* c, const bgs_cloud* cloud, const bgs_view* vi
             CU(c, cudaEventRecord(c->ev_p0, q));
             launch_project(cloud->f16, cloud->blocks != nullptr, cloud->pos, cloud->blocks ? cloud->blocks : cloud->sh, cloud->rot, cloud->so, by_slot ? c->slot_ids : c->vals[cur],
                            by_slot ? 1 : 0, c->ctr, fc, c->recs,
-                           raster_mode == 2 ? c->extra : nullptr, n_hint < n ? n_hint : n, q);
+                           raster_mode == 2 ? c->extra : nullptr, n_hint < n ? n_hint : n, c->sm_count, 0, c->cutoff_tab, q);
             ++launches;
             CU(c, cudaEventRecord(c->ev_p1, q));
         }
@@ -711,7 +735,6 @@ bgs_status bgs_render(bgs_context* c, const bgs_cloud* cloud, const bgs_view* vi
         //      blend state, the last one writing the frame (identical pixels either way).
         // kernel variant picked from the previous frame's mean footprint (pairs per visible splat); results are identical
         const bool large_fp = c->n_vis_hint > 0 && (uint64_t)c->n_pairs_hint >= 8ull * c->n_vis_hint;
-        const size_t pair_status_stride = (size_t)radix_num_tiles(c->arena_pairs) * 256;
         int pcur = 0;
         for (int r = 0; r < rounds; ++r) {
             ChunkCounters* cc = &c->ctr->chunk[r];
@@ -722,31 +745,22 @@ bgs_status bgs_render(bgs_context* c, const bgs_cloud* cloud, const bgs_view* vi
                 // the depth sort's spare ping-pong buffers (N words each) hold the large-footprint queue
                 CU(c, launch_bin_emit_coop(c->recs, by_slot ? c->vals[cur] : nullptr, c->ctr, cc, fa, fb, num_tiles,
                                            c->status_bin, tiles_x, c->cap_pairs, c->pkeys[0], c->pvals[0], c->keys[cur ^ 1],
-                                           c->vals[cur ^ 1], c->cap_n, c->timeline, c->bin_grid, c->d_sticky, q));
+                                           c->vals[cur ^ 1], c->cap_n, getenv("BGS_TIMELINE_SORT") ? nullptr : c->timeline, c->bin_grid, c->d_sticky, q));
             } else {
                 launch_bin_emit(c->recs, by_slot ? c->vals[cur] : nullptr, c->ctr, cc, c->status_bin, tiles_x, c->cap_pairs,
                                 c->pkeys[0], c->pvals[0], n, c->sm_count, c->d_sticky, q);
             }
             ++launches;
-            launch_radix_hist(c->pkeys[0], &cc->n_pairs, c->cap_pairs, tile_passes, hist_r, c->sm_count, q);
-            ++launches;
+            // stable tile-id sort of the pair list + per-tile ranges: histogram phase, both digit places and the range
+            // build in ONE cooperative launch
             uint32_t p_hint = c->n_pairs_hint ? c->n_pairs_hint : c->cap_pairs;
             if (rounds > 1) p_hint = c->chunk_hint_valid ? c->chunk_pairs_hint[r] : c->cap_pairs;
             if (p_hint > c->cap_pairs) p_hint = c->cap_pairs;
-            pcur = 0;
-            for (int p = 0; p < tile_passes; ++p) {
-                launch_onesweep(c->pkeys[pcur], c->pvals[pcur], c->pkeys[pcur ^ 1], c->pvals[pcur ^ 1], &cc->n_pairs,
-                                c->cap_pairs, p_hint, hist_r + p * 256, c->status_pairs + p * pair_status_stride,
-                                &cc->tile_ctr_sort[p], 8 * p, c->sm_count, q);
-                ++launches;
-                pcur ^= 1;
-            }
-            if (r + 1 < rounds) {   // the next round's sort reuses the look-back status rows
-                launch_status_clear(c->status_pairs, pair_status_stride, tile_passes, &cc->n_pairs, c->sm_count, q);
-                ++launches;
-            }
-            launch_tile_ranges(c->pkeys[pcur], &cc->n_pairs, rng, c->cap_pairs, c->sm_count, q);
+            CU(c, launch_radix_sort(c->pkeys[0], c->pvals[0], c->pkeys[1], c->pvals[1], &cc->n_pairs, c->cap_pairs, p_hint, hist_r, 1,
+                                    c->status_pairs, (size_t)radix_num_tiles(c->status_np) * 256, next_epoch(c), &cc->tile_ctr_sort[0],
+                                    tile_passes, 0, rng, c->sm_count, c->rs_per_sm, q, nullptr));
             ++launches;
+            pcur = tile_passes & 1;
             if (r + 1 == rounds) {
                 // (chunked frames: the earlier rounds' blends are accounted to stage 4)
                 CU(c, cudaEventRecord(c->ev[4], q));
@@ -776,11 +790,6 @@ bgs_status bgs_render(bgs_context* c, const bgs_cloud* cloud, const bgs_view* vi
         c->pend_cloud = cloud; c->pend_n = n; c->pend_fc = fc; c->pend_sort_all = sort_all; c->pend_by_slot = by_slot;
         c->pend_chunks = rounds;
         c->pend_tiles_x = tiles_x; c->pend_tiles_y = tiles_y; c->pend_W = W; c->pend_H = H; c->pend_target = target;
-        // pre-clean the status rows for the next frame, off the critical path
-        CU(c, cudaStreamWaitEvent(c->stream2, c->ev_done, 0));
-        CU(c, cudaMemsetAsync(c->arena + c->arena_small_bytes, 0, c->arena_bytes - c->arena_small_bytes, c->stream2));
-        CU(c, cudaEventRecord(c->ev_clean, c->stream2));
-        c->status_clean_pending = true;
         if (st->flags & BGS_FLAG_ASYNC) {
             c->launches = launches;
             c->async_pending = true;
@@ -841,7 +850,13 @@ bgs_status bgs_debug_tile_ranges(bgs_context* c, uint32_t* start_end) {
     if (!c->have_frame) return fail(c, BGS_NOT_READY, "no frame rendered yet");
     if (c->last_chunks > 1) return fail(c, BGS_NOT_READY, "the last frame was binned in %d rounds: set BGS_FLAG_NO_CHUNKS for the tile hooks", c->last_chunks);
     CU(c, cudaSetDevice(c->device));
-    CU(c, cudaMemcpy(start_end, c->ranges, (size_t)c->stats.tiles_x * c->stats.tiles_y * 8, cudaMemcpyDeviceToHost));
+    const size_t tiles = (size_t)c->stats.tiles_x * c->stats.tiles_y;
+    CU(c, cudaMemcpy(start_end, c->ranges, tiles * 8, cudaMemcpyDeviceToHost));
+    // device form: (~start, end), (0, 0) for an empty tile (the sort's last pass builds them with atomicMax)
+    for (size_t t = 0; t < tiles; ++t) {
+        if (start_end[2 * t + 1] == 0u) start_end[2 * t] = 0u;
+        else start_end[2 * t] = ~start_end[2 * t];
+    }
     return BGS_OK;
 }
 
@@ -947,6 +962,7 @@ bgs_status bgs_debug_timeline_(bgs_context* c, unsigned long long* out, uint32_t
 
 const char* bgs_last_error(const bgs_context* c) { return c ? c->err : "null context"; }
 void* bgs_context_stream(bgs_context* c) { return c ? (void*)c->stream : nullptr; }
+void* bgs_context_copy_stream(bgs_context* c) { return c ? (void*)c->stream_copy : nullptr; }
 const void* bgs_frame_device_ptr(bgs_context* c) {
     if (!c) return nullptr;
     return c->have_frame ? c->last_frame : (c->async_pending ? c->pend_target : nullptr);

@@ -124,29 +124,45 @@ bin_emit_kernel(const SplatRec* __restrict__ recs, const uint32_t* __restrict__ 
     // n_vis == 0: nothing was published; counters stay zero from the per-frame clear
 }
 
-// Cooperative variant (all CTAs co-resident).
-//   phase 1: count the tiles touched by this CTA's contiguous rank range, publish the CTA total
+// Cooperative variant (all CTAs co-resident).  Each CTA owns a contiguous range of front-to-back ranks.
+//   phase 1: per splat, the tiles its bbox touches; the CTA publishes THREE totals: pairs, medium-footprint splats,
+//            large-footprint splats (bboxes stay in registers when the range is a single sub-tile -- the usual case)
 //   -- grid barrier --
-//   phase 2: sum the earlier CTAs' totals in parallel (no chained look-back); emit small footprints
-//            directly; push large footprints (rank, pair offset) to a global queue
+//   phase 2: exclusive prefixes of the three totals over the earlier CTAs (parallel sums, no atomics, no chained
+//            look-back): tiny footprints (<= 4 tiles) are written right away by the owning thread; medium ones go to the
+//            front of the queue arrays, large ones to the back, each at its prefix position (rank order preserved)
 //   -- grid barrier --
-//   phase 3: all warps of the grid drain the queue (front-most splats cover hundreds of tiles and all
-//            sit in the first CTAs' ranges: without this the frame waits on a handful of CTAs)
+//   phase 3: the whole grid drains both queues, statically partitioned (warp w takes medium batches w, w + W, ...:
+//            a shared head counter cost one contended atomic per warp -- 4736 of them -- just to learn the queue was empty)
+__device__ __forceinline__ void block_sum_prefix3(const uint32_t* cnt3, uint32_t upto, uint64_t out[3], unsigned long long* s_red64 /*[3][8]*/) {
+    uint64_t v0 = 0, v1 = 0, v2 = 0;
+    for (uint32_t p = threadIdx.x; p < upto; p += BIN_THREADS) {
+        v0 += ld_volatile(cnt3 + 3 * p); v1 += ld_volatile(cnt3 + 3 * p + 1); v2 += ld_volatile(cnt3 + 3 * p + 2);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        v0 += __shfl_xor_sync(0xffffffffu, v0, o); v1 += __shfl_xor_sync(0xffffffffu, v1, o); v2 += __shfl_xor_sync(0xffffffffu, v2, o);
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) { s_red64[warp] = v0; s_red64[8 + warp] = v1; s_red64[16 + warp] = v2; }
+    __syncthreads();
+    out[0] = out[1] = out[2] = 0;
+#pragma unroll
+    for (int w = 0; w < BIN_THREADS / 32; ++w) { out[0] += s_red64[w]; out[1] += s_red64[8 + w]; out[2] += s_red64[16 + w]; }
+    __syncthreads();
+}
+
 __global__ void __launch_bounds__(BIN_THREADS)
 bin_emit_coop_kernel(const SplatRec* __restrict__ recs, const uint32_t* __restrict__ perm, FrameCounters* __restrict__ ctr,
                      ChunkCounters* __restrict__ cc, uint32_t frac_a, uint32_t frac_b, uint32_t num_tiles_total,
-                     uint32_t* __restrict__ block_cnt, int tiles_x, uint32_t capacity, uint32_t* __restrict__ pair_keys,
+                     uint32_t* __restrict__ block_cnt /* [grid][3] */, int tiles_x, uint32_t capacity, uint32_t* __restrict__ pair_keys,
                      uint32_t* __restrict__ pair_vals, uint32_t* __restrict__ q_rank, uint32_t* __restrict__ q_off,
                      uint32_t q_cap, unsigned long long* __restrict__ tl, uint32_t* __restrict__ sticky_need) {
     timeline_stamp(tl, 0);
-    __shared__ uint32_t s_wtot[BIN_THREADS / 32];
-    __shared__ uint32_t s_wbig[BIN_THREADS / 32];
-    __shared__ uint32_t s_wmed[BIN_THREADS / 32];
-    __shared__ uint32_t s_mbase;
-    __shared__ uint32_t s_red[BIN_THREADS / 32];
-    __shared__ unsigned long long s_red64[BIN_THREADS / 32];
-    __shared__ uint32_t s_total;
-    __shared__ uint32_t s_qbase;
+    __shared__ uint32_t s_wtot[3][BIN_THREADS / 32];
+    __shared__ unsigned long long s_red64[3 * 8];
+    __shared__ uint32_t s_tot[3];
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const uint32_t G = gridDim.x, b = blockIdx.x;
     const uint32_t n_vis = ctr->n_vis;
@@ -167,6 +183,7 @@ bin_emit_coop_kernel(const SplatRec* __restrict__ recs, const uint32_t* __restri
     if (ipt > COOP_ITEMS) ipt = COOP_ITEMS;
     if (ipt == 0) ipt = 1;
     const uint32_t sub = BIN_THREADS * ipt;
+    const bool single = rhi - rlo <= sub;     // one sub-tile: phase 2 reuses phase 1's registers
 
     auto tiles_of = [&](uint32_t r, uint32_t& bx, uint32_t& by, uint32_t& ri) -> uint32_t {
         if (r >= rhi) return 0u;
@@ -179,63 +196,63 @@ bin_emit_coop_kernel(const SplatRec* __restrict__ recs, const uint32_t* __restri
     };
 
     // ---- phase 1
-    uint32_t mine = 0u;
+    uint32_t bx[COOP_ITEMS], by[COOP_ITEMS], cnt[COOP_ITEMS], ri[COOP_ITEMS];
+    uint32_t mine = 0u, mmed = 0u, mbig = 0u;
     for (uint32_t base = rlo; base < rhi; base += sub) {
 #pragma unroll
         for (int j = 0; j < COOP_ITEMS; ++j) {
-            uint32_t bx, by, ri;
-            if ((uint32_t)j < ipt) mine += tiles_of(base + t * ipt + j, bx, by, ri);
+            bx[j] = 0u; by[j] = 0u; ri[j] = 0u;
+            cnt[j] = ((uint32_t)j < ipt) ? tiles_of(base + t * ipt + j, bx[j], by[j], ri[j]) : 0u;
+            mine += cnt[j];
+            mmed += (cnt[j] > BIN_TINY && cnt[j] <= BIN_BIG) ? 1u : 0u;
+            mbig += cnt[j] > BIN_BIG ? 1u : 0u;
         }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
-    if (lane == 0) s_red[warp] = mine;
+    for (int o = 16; o > 0; o >>= 1) {
+        mine += __shfl_xor_sync(0xffffffffu, mine, o); mmed += __shfl_xor_sync(0xffffffffu, mmed, o); mbig += __shfl_xor_sync(0xffffffffu, mbig, o);
+    }
+    if (lane == 0) { s_wtot[0][warp] = mine; s_wtot[1][warp] = mmed; s_wtot[2][warp] = mbig; }
     __syncthreads();
-    if (t == 0) {
+    if (t < 3) {
         uint32_t tot = 0u;
 #pragma unroll
-        for (int w = 0; w < BIN_THREADS / 32; ++w) tot += s_red[w];
-        s_total = tot > LB_VMASK ? LB_VMASK : tot;
-        st_volatile(block_cnt + b, s_total);
+        for (int w = 0; w < BIN_THREADS / 32; ++w) tot += s_wtot[t][w];
+        if (t == 0 && tot > LB_VMASK) tot = LB_VMASK;
+        s_tot[t] = tot;
+        st_volatile(block_cnt + 3 * b + t, tot);
     }
     timeline_stamp(tl, 1);
     grid_barrier(&cc->barrier, G);
     timeline_stamp(tl, 2);
 
-    // ---- phase 2 (sums saturate at 2^30 - 1: such a frame is rejected by the host)
-    uint64_t run64 = 0;
-    {
-        uint64_t v = 0;
-        for (uint32_t p = t; p < b; p += BIN_THREADS) v += ld_volatile(block_cnt + p);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0) s_red64[warp] = v;
-        __syncthreads();
-#pragma unroll
-        for (int w = 0; w < BIN_THREADS / 32; ++w) run64 += s_red64[w];
-    }
+    // ---- phase 2 (pair sums saturate at 2^30 - 1: such a frame is rejected by the host)
+    uint64_t pre[3];
+    block_sum_prefix3(block_cnt, b, pre, s_red64);
     if (b == G - 1 && t == 0) {
-        const uint64_t need64 = run64 + s_total;
+        const uint64_t need64 = pre[0] + s_tot[0];
         const uint32_t need = need64 > LB_VMASK ? LB_VMASK : (uint32_t)need64;
         cc->n_pairs_needed = need;
         cc->n_pairs = need < capacity ? need : capacity;
+        cc->med_count = (uint32_t)(pre[1] + s_tot[1]);
+        cc->big_count = (uint32_t)(pre[2] + s_tot[2]);
         atomicMax(sticky_need, need);
     }
-    uint32_t run = run64 > LB_VMASK ? LB_VMASK : (uint32_t)run64;
+    uint32_t run = pre[0] > LB_VMASK ? LB_VMASK : (uint32_t)pre[0];
+    uint32_t mrun = (uint32_t)pre[1], brun = (uint32_t)pre[2];
     for (uint32_t base = rlo; base < rhi; base += sub) {
         const uint32_t r0 = base + t * ipt;
-        uint32_t bx[COOP_ITEMS], by[COOP_ITEMS], cnt[COOP_ITEMS], ri[COOP_ITEMS];
-        uint32_t tmine = 0u, nbig = 0u;
+        uint32_t tmine = 0u, nbig = 0u, nmed = 0u;
 #pragma unroll
         for (int j = 0; j < COOP_ITEMS; ++j) {
-            bx[j] = 0u; by[j] = 0u; ri[j] = 0u;
-            cnt[j] = ((uint32_t)j < ipt) ? tiles_of(r0 + j, bx[j], by[j], ri[j]) : 0u;
+            if (!single) {
+                bx[j] = 0u; by[j] = 0u; ri[j] = 0u;
+                cnt[j] = ((uint32_t)j < ipt) ? tiles_of(r0 + j, bx[j], by[j], ri[j]) : 0u;
+            }
             tmine += cnt[j];
             nbig += cnt[j] > BIN_BIG ? 1u : 0u;
+            nmed += (cnt[j] > BIN_TINY && cnt[j] <= BIN_BIG) ? 1u : 0u;
         }
-        uint32_t nmed = 0u;
-#pragma unroll
-        for (int j = 0; j < COOP_ITEMS; ++j) nmed += (cnt[j] > BIN_TINY && cnt[j] <= BIN_BIG) ? 1u : 0u;
         uint32_t incl = tmine, bincl = nbig, mincl = nmed;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -244,26 +261,21 @@ bin_emit_coop_kernel(const SplatRec* __restrict__ recs, const uint32_t* __restri
             const uint32_t x = __shfl_up_sync(0xffffffffu, mincl, o);
             if (lane >= o) { incl += y; bincl += z; mincl += x; }
         }
-        if (lane == 31) { s_wtot[warp] = incl; s_wbig[warp] = bincl; s_wmed[warp] = mincl; }
+        if (lane == 31) { s_wtot[0][warp] = incl; s_wtot[1][warp] = mincl; s_wtot[2][warp] = bincl; }
         __syncthreads();
         uint32_t wprefix = 0u, ttotal = 0u, bprefix = 0u, btotal = 0u, mprefix = 0u, mtotal = 0u;
 #pragma unroll
         for (int w = 0; w < BIN_THREADS / 32; ++w) {
-            const uint32_t c = s_wtot[w], d = s_wbig[w], e = s_wmed[w];
+            const uint32_t c = s_wtot[0][w], e = s_wtot[1][w], d = s_wtot[2][w];
             if (w < warp) { wprefix += c; bprefix += d; mprefix += e; }
             ttotal += c; btotal += d; mtotal += e;
         }
-        if (t == 0) {   // one reservation per round in each global queue
-            if (btotal) s_qbase = atomicAdd(&cc->big_count, btotal);
-            if (mtotal) s_mbase = atomicAdd(&cc->med_count, mtotal);
-        }
-        __syncthreads();
         // footprint classes:  <= BIN_TINY tiles: written right here by the owning thread;
         //   <= BIN_BIG: medium queue (front of the queue arrays), drained 32 splats per warp in phase 3;
-        //   larger: big queue (back of the queue arrays), one splat per warp in phase 3
+        //   larger: big queue (back of the queue arrays), one splat (or a part of one) per warp in phase 3
         uint32_t off = run + wprefix + incl - tmine;
-        uint32_t qat = s_qbase + bprefix + bincl - nbig;
-        uint32_t mat = s_mbase + mprefix + mincl - nmed;
+        uint32_t qat = brun + bprefix + bincl - nbig;
+        uint32_t mat = mrun + mprefix + mincl - nmed;
 #pragma unroll
         for (int j = 0; j < COOP_ITEMS; ++j) {
             if (cnt[j] == 0u) continue;
@@ -286,7 +298,7 @@ bin_emit_coop_kernel(const SplatRec* __restrict__ recs, const uint32_t* __restri
             }
             off += cnt[j];
         }
-        run += ttotal;
+        run += ttotal; mrun += mtotal; brun += btotal;
         __syncthreads();
     }
     timeline_stamp(tl, 3);
@@ -295,12 +307,9 @@ bin_emit_coop_kernel(const SplatRec* __restrict__ recs, const uint32_t* __restri
 
     // ---- phase 3a: medium footprints, 32 per warp: each lane fetches one splat's (record, offset, bbox)
     //      so the memory latency is paid once per 32 splats; then the warp writes them one after another
+    const uint32_t gwarp = b * (BIN_THREADS / 32) + warp, total_warps = G * (BIN_THREADS / 32);
     const uint32_t nm = ld_volatile(&cc->med_count);
-    while (true) {
-        uint32_t mb = 0u;
-        if (lane == 0) mb = atomicAdd(&cc->med_head, 32u);
-        mb = __shfl_sync(0xffffffffu, mb, 0);
-        if (mb >= nm) break;
+    for (uint32_t mb = gwarp * 32u; mb < nm; mb += total_warps * 32u) {
         const uint32_t i = mb + lane;
         uint32_t m_ri = 0u, m_off = 0u, m_txlo = 0u, m_tylo = 0u, m_w = 1u, m_total = 0u;
         if (i < nm) {
@@ -326,20 +335,17 @@ bin_emit_coop_kernel(const SplatRec* __restrict__ recs, const uint32_t* __restri
             }
         }
     }
-    // ---- phase 3b: warps pull large-footprint splats from the back queue, one at a time
+    // ---- phase 3b: large footprints from the back queue, one (part of a) splat per warp
     //      (a few splats that each cover thousands of tiles -- the front of a heavy scene -- are cut into up to
     //      16 parts so the whole grid shares them)
     const uint32_t nq = ld_volatile(&cc->big_count);
     uint32_t part_shift = 0u;
-    while (part_shift < 4u && ((uint64_t)nq << (part_shift + 2u)) <= (uint64_t)G * (BIN_THREADS / 32)) ++part_shift;
+    while (part_shift < 4u && ((uint64_t)nq << (part_shift + 2u)) <= (uint64_t)total_warps) ++part_shift;
     const uint32_t n_tickets = nq << part_shift;
-    while (true) {
-        uint32_t q = 0u;
-        if (lane == 0) q = atomicAdd(&cc->big_head, 1u);
-        q = __shfl_sync(0xffffffffu, q, 0);
-        if (q >= n_tickets) break;
-        const uint32_t part = q & ((1u << part_shift) - 1u);
-        q >>= part_shift;
+    // (tickets are dealt round-robin starting at the LAST warp so the warps that drained medium batches get fewer)
+    for (uint32_t tk = total_warps - 1u - gwarp; tk < n_tickets; tk += total_warps) {
+        const uint32_t part = tk & ((1u << part_shift) - 1u);
+        const uint32_t q = tk >> part_shift;
         const uint32_t r = __ldcg(q_rank + (q_cap - 1u - q)), off = __ldcg(q_off + (q_cap - 1u - q));
         const uint2 bb = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const char*>(recs + r) + 24));
         const uint32_t txlo = (bb.x & 0xFFFFu) >> 4, txhi = (bb.x >> 16) >> 4;
@@ -363,16 +369,6 @@ bin_emit_coop_kernel(const SplatRec* __restrict__ recs, const uint32_t* __restri
         }
     }
     timeline_stamp(tl, 5);
-}
-
-__global__ void tile_ranges_kernel(const uint32_t* __restrict__ sorted_tile_ids, const uint32_t* __restrict__ n_ptr,
-                                   uint2* __restrict__ ranges) {
-    const uint32_t n = *n_ptr;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const uint32_t t = sorted_tile_ids[i];
-        if (i == 0 || sorted_tile_ids[i - 1] != t) ranges[t].x = i;
-        if (i == n - 1 || sorted_tile_ids[i + 1] != t) ranges[t].y = i + 1;
-    }
 }
 
 void launch_bin_emit(const SplatRec* recs, const uint32_t* perm, FrameCounters* ctr, ChunkCounters* cc, uint32_t* status,
@@ -400,15 +396,6 @@ cudaError_t launch_bin_emit_coop(const SplatRec* recs, const uint32_t* perm, Fra
                     (void*)&block_cnt, (void*)&tiles_x, (void*)&capacity, (void*)&pair_keys,
                     (void*)&pair_vals, (void*)&q_rank, (void*)&q_off, (void*)&q_cap, (void*)&timeline, (void*)&sticky_need};
     return cudaLaunchCooperativeKernel((const void*)bin_emit_coop_kernel, dim3(grid), dim3(BIN_THREADS), args, 0, stream);
-}
-
-void launch_tile_ranges(const uint32_t* sorted_tile_ids, const uint32_t* n_ptr, uint2* ranges, uint32_t capacity,
-                        int sm_count, cudaStream_t stream) {
-    uint32_t blocks = (capacity + 255) / 256;
-    const uint32_t cap_blocks = (uint32_t)sm_count * 8u;
-    if (blocks > cap_blocks) blocks = cap_blocks;
-    if (blocks == 0) blocks = 1;
-    tile_ranges_kernel<<<blocks, 256, 0, stream>>>(sorted_tile_ids, n_ptr, ranges);
 }
 
 }  // namespace bgs

@@ -107,58 +107,59 @@ keygen_compact_kernel(const float4* __restrict__ pos, uint32_t n, FrameConsts fc
     }
 }
 
-// Cooperative variant (all CTAs co-resident, launched with cudaLaunchCooperativeKernel): each CTA owns
-// a CONTIGUOUS range of tiles.  Phase 1 streams the positions once (16 B/gaussian), writes the
-// uncompacted keys (4 B/gaussian, L2-sized scratch) and publishes the CTA's visible count.  One grid
-// barrier.  Phase 2 sums the counts of all earlier CTAs in parallel (no chained look-back), re-reads
-// its own keys from L2 and writes the visible (key, index) pairs compacted in index order.
-// SMEM_KEYS: the CTA's keys stay in (dynamic) shared memory across the barrier instead of taking a round trip
-// through the global scratch (used whenever the CTA's range fits: <= 48 KB of keys).
-template <bool SMEM_KEYS>
+// Cooperative variant (all CTAs co-resident, launched with cudaLaunchCooperativeKernel): each CTA owns a
+// CONTIGUOUS range of 2048-gaussian tiles.
+//   phase 1 streams the positions once (16 B/gaussian, the only HBM traffic that scales with N), decides
+//           visibility, and keeps just ONE BIT per gaussian (warp ballots -> a 4 B mask word per 32 gaussians in an
+//           L2-resident scratch) plus the CTA's visible count.  No key is computed for the ~88 % that are culled.
+//   -- one grid barrier --
+//   phase 2 sums the counts of all earlier CTAs in parallel, scans its own mask words, and expands them: visible
+//           element e of the CTA (found by binary search over the word prefix + select-nth-bit) re-reads its position
+//           (L2 / 32 B sectors, visible ones only), computes the key and writes (key, index, slot) at run + e --
+//           fully coalesced, in index order, so the stable LSD sort sees the reference's tie order.
+//           The depth sort's digit histograms are accumulated on the way (shared-memory atomics, visible keys only).
+constexpr int KG_WORDS_PER_TILE = KG_TILE / 32;    // 64 mask words
+constexpr int KG_CHUNK_WORDS = 1024;               // phase 2 expands 1024 words (32 K gaussians) at a time
+
 __global__ void __launch_bounds__(KG_THREADS)
-keygen_coop_kernel(const float4* __restrict__ pos, uint32_t n, FrameConsts fc, uint32_t* __restrict__ keys_tmp,
+keygen_coop_kernel(const float4* __restrict__ pos, uint32_t n, FrameConsts fc, uint32_t* __restrict__ masks,
                    uint32_t* __restrict__ keys_out, uint32_t* __restrict__ ids_out, uint32_t* __restrict__ slots_out,
                    uint32_t* __restrict__ block_cnt, FrameCounters* __restrict__ ctr, uint32_t* __restrict__ hist,
                    int hist_passes) {
-    __shared__ uint32_t s_cnt[KG_ITEMS * (KG_THREADS / 32)];
     __shared__ uint32_t s_hist[4 * 256];   // digit histograms of the visible keys (the depth sort's pre-pass, fused)
-    __shared__ uint32_t s_off[KG_ITEMS * (KG_THREADS / 32)];
     __shared__ uint32_t s_red[KG_THREADS / 32];
     __shared__ uint32_t s_total;
-    extern __shared__ uint32_t s_keys_dyn[];
+    __shared__ uint32_t s_mask[KG_CHUNK_WORDS];
+    __shared__ uint32_t s_pref[KG_CHUNK_WORDS];   // exclusive prefix of popc(s_mask)
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const uint32_t G = gridDim.x, b = blockIdx.x;
     const uint32_t tiles_total = (n + KG_TILE - 1) / KG_TILE;
     const uint32_t t0 = (uint32_t)((uint64_t)b * tiles_total / G), t1 = (uint32_t)((uint64_t)(b + 1) * tiles_total / G);
-    const uint32_t culled = 0xFFFFFFFFu >> fc.key_shift;
 
-    // ---- phase 1: keys for every gaussian of this CTA's range, visible count
-    uint32_t mine = 0u;
+    // ---- phase 1: one visibility bit per gaussian of this CTA's range, visible count
+    uint32_t mine = 0u;                      // (warp-uniform: every lane counts its warp's ballots)
     uint32_t cmin_inv = 0u, cmax_p1 = 0u;   // Depth mode only: extremes of the culled indices
     for (uint32_t tile = t0; tile < t1; ++tile) {
-        const uint32_t tile_base = tile * KG_TILE;
+        // warp w covers 256 consecutive gaussians of the tile, item j = 32 consecutive ones (coalesced 512 B loads)
+        const uint32_t wbase = tile * KG_TILE + warp * (32 * KG_ITEMS);
         float4 p[KG_ITEMS];
 #pragma unroll
         for (int j = 0; j < KG_ITEMS; ++j) {
-            const uint32_t i = tile_base + j * KG_THREADS + t;
+            const uint32_t i = wbase + j * 32 + lane;
             p[j] = (i < n) ? __ldcs(pos + i) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
+        uint32_t myword = 0u;
 #pragma unroll
         for (int j = 0; j < KG_ITEMS; ++j) {
-            const uint32_t i = tile_base + j * KG_THREADS + t;
-            bool kvis;
-            const uint32_t kkey = key_of_fast(fc, p[j].x, p[j].y, p[j].z, kvis);
-            if (i < n) {
-                const uint32_t key = kvis ? kkey : culled;
-                if (SMEM_KEYS) s_keys_dyn[(tile - t0) * KG_TILE + j * KG_THREADS + t] = key;
-                else __stcg(keys_tmp + i, key);
-                mine += kvis ? 1u : 0u;
-                if (!kvis) { cmin_inv = max(cmin_inv, 0xFFFFFFFFu - i); cmax_p1 = max(cmax_p1, i + 1u); }
-            }
+            const uint32_t i = wbase + j * 32 + lane;
+            const bool v = (i < n) && visible_fast(fc, p[j].x, p[j].y, p[j].z);
+            const uint32_t bal = __ballot_sync(0xffffffffu, v);
+            mine += __popc(bal);
+            if (lane == j) myword = bal;
+            if (fc.rasterize_mode == BGS_RASTERIZE_DEPTH && i < n && !v) { cmin_inv = max(cmin_inv, 0xFFFFFFFFu - i); cmax_p1 = max(cmax_p1, i + 1u); }
         }
+        if (lane < KG_ITEMS) __stcg(masks + (size_t)tile * KG_WORDS_PER_TILE + warp * KG_ITEMS + lane, myword);
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
     if (lane == 0) s_red[warp] = mine;
     if (fc.rasterize_mode == BGS_RASTERIZE_DEPTH) {
 #pragma unroll
@@ -178,54 +179,66 @@ keygen_coop_kernel(const float4* __restrict__ pos, uint32_t n, FrameConsts fc, u
     }
     grid_barrier(&ctr->barrier[0], G);
 
-    // ---- phase 2: exclusive prefix over CTAs, then ordered compaction of this CTA's range
+    // ---- phase 2: exclusive prefix over CTAs, then ordered expansion of this CTA's mask words
     for (int i = t; i < hist_passes * 256; i += KG_THREADS) s_hist[i] = 0u;
     uint32_t run = block_sum_prefix<KG_THREADS>(block_cnt, b, s_red);
     if (b == G - 1 && t == 0) { ctr->n_vis = run + s_total; ctr->n_sort = run + s_total; }
-    for (uint32_t tile = t0; tile < t1; ++tile) {
-        const uint32_t tile_base = tile * KG_TILE;
-        uint32_t key[KG_ITEMS], prefix[KG_ITEMS];
-        uint32_t vis_bits = 0u;
+    const uint32_t w_begin = t0 * KG_WORDS_PER_TILE, w_end = t1 * KG_WORDS_PER_TILE;
+    for (uint32_t wc = w_begin; wc < w_end; wc += KG_CHUNK_WORDS) {
+        const uint32_t cw = min((uint32_t)KG_CHUNK_WORDS, w_end - wc);
+        // each thread owns 4 consecutive words of the chunk: local prefix, then a block scan of the per-thread sums
+        uint32_t m[4], c[4], tsum = 0u;
 #pragma unroll
-        for (int j = 0; j < KG_ITEMS; ++j) {
-            const uint32_t i = tile_base + j * KG_THREADS + t;
-            key[j] = (i < n) ? (SMEM_KEYS ? s_keys_dyn[(tile - t0) * KG_TILE + j * KG_THREADS + t] : __ldcg(keys_tmp + i)) : culled;
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t w = (uint32_t)t * 4u + k;
+            m[k] = (w < cw) ? __ldcg(masks + wc + w) : 0u;
+            c[k] = tsum;
+            tsum += __popc(m[k]);
         }
+        uint32_t incl = tsum;
 #pragma unroll
-        for (int j = 0; j < KG_ITEMS; ++j) {
-            const bool v = key[j] != culled;
-            const uint32_t bal = __ballot_sync(0xffffffffu, v);
-            prefix[j] = __popc(bal & lanemask_lt());
-            if (v) vis_bits |= 1u << j;
-            if (lane == 0) s_cnt[j * (KG_THREADS / 32) + warp] = __popc(bal);
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += y;
+        }
+        if (lane == 31) s_red[warp] = incl;
+        __syncthreads();
+        uint32_t wprefix = 0u, chunk_total = 0u;
+#pragma unroll
+        for (int w = 0; w < KG_THREADS / 32; ++w) {
+            const uint32_t v = s_red[w];
+            if (w < warp) wprefix += v;
+            chunk_total += v;
+        }
+        const uint32_t texcl = wprefix + incl - tsum;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            s_mask[t * 4 + k] = m[k];
+            s_pref[t * 4 + k] = texcl + c[k];
         }
         __syncthreads();
-        if (warp == 0) {
-            const uint32_t a = s_cnt[2 * lane], c2 = s_cnt[2 * lane + 1];
-            uint32_t incl = a + c2;
+        for (uint32_t e = t; e < chunk_total; e += KG_THREADS) {
+            // largest word w with s_pref[w] <= e (words with no visible gaussian share their successor's prefix: the
+            // search lands on the LAST of them or on the word itself; skip forward over empty words by construction:
+            // upper_bound - 1 always holds a word whose range [pref, pref + popc) contains e)
+            uint32_t lo = 0u, hi = KG_CHUNK_WORDS;             // invariant: s_pref[lo] <= e, (hi == size or s_pref[hi] > e)
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += y;
+            for (int it = 0; it < 10; ++it) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (s_pref[mid] <= e) lo = mid; else hi = mid;
             }
-            const uint32_t excl = incl - (a + c2);
-            s_off[2 * lane] = excl;
-            s_off[2 * lane + 1] = excl + a;
-            if (lane == 31) s_total = incl;
+            const uint32_t r = e - s_pref[lo];
+            const uint32_t bit = __fns(s_mask[lo], 0u, (int)r + 1);
+            const uint32_t i = (wc + lo) * 32u + bit;
+            const float4 p = __ldg(pos + i);
+            const uint32_t key = key_only(fc, p.x, p.y, p.z);
+            const uint32_t dst = run + e;
+            keys_out[dst] = key;
+            ids_out[dst] = i;          // compact slot -> gaussian index
+            slots_out[dst] = dst;      // the sort's payload: the compact slot
+            for (int pp = 0; pp < hist_passes; ++pp) atomicAdd(&s_hist[pp * 256 + ((key >> (8 * pp)) & 255u)], 1u);
         }
-        __syncthreads();
-#pragma unroll
-        for (int j = 0; j < KG_ITEMS; ++j) {
-            if (vis_bits & (1u << j)) {
-                const uint32_t dst = run + s_off[j * (KG_THREADS / 32) + warp] + prefix[j];
-                keys_out[dst] = key[j];
-                ids_out[dst] = tile_base + j * KG_THREADS + t;   // compact slot -> gaussian index
-                slots_out[dst] = dst;                            // the sort's payload: the compact slot
-                // (warp-aggregating the clustered upper digits with match.any was measured slower: +12 us on C3)
-                for (int p = 0; p < hist_passes; ++p) atomicAdd(&s_hist[p * 256 + ((key[j] >> (8 * p)) & 255u)], 1u);
-            }
-        }
-        run += s_total;
+        run += chunk_total;
         __syncthreads();
     }
     for (int i = t; i < hist_passes * 256; i += KG_THREADS) {
@@ -252,24 +265,18 @@ void launch_keygen(const float4* pos, uint32_t n, const FrameConsts& fc, int sor
 }
 uint32_t keygen_num_tiles(uint32_t n) { return (n + KG_TILE - 1) / KG_TILE; }
 
-constexpr size_t KG_SMEM_MAX = 5 * KG_TILE * 4;   // 40 KB of keys per CTA (static + dynamic stays under the 48 KB default limit)
 int keygen_coop_blocks_per_sm() {
-    // sized for the shared-memory variant at its largest footprint, so either variant is co-resident
     int b = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, keygen_coop_kernel<true>, KG_THREADS, KG_SMEM_MAX) != cudaSuccess) return 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, keygen_coop_kernel, KG_THREADS, 0) != cudaSuccess) return 0;
     return b;
 }
-cudaError_t launch_keygen_coop(const float4* pos, uint32_t n, const FrameConsts& fc, uint32_t* keys_tmp, uint32_t* keys_out,
+cudaError_t launch_keygen_coop(const float4* pos, uint32_t n, const FrameConsts& fc, uint32_t* masks, uint32_t* keys_out,
                                uint32_t* ids_out, uint32_t* slots_out, uint32_t* block_cnt, FrameCounters* ctr,
                                uint32_t* hist, int hist_passes, uint32_t grid, cudaStream_t stream) {
     FrameConsts fcc = fc;
-    void* args[] = {(void*)&pos, (void*)&n, (void*)&fcc, (void*)&keys_tmp, (void*)&keys_out, (void*)&ids_out,
+    void* args[] = {(void*)&pos, (void*)&n, (void*)&fcc, (void*)&masks, (void*)&keys_out, (void*)&ids_out,
                     (void*)&slots_out, (void*)&block_cnt, (void*)&ctr, (void*)&hist, (void*)&hist_passes};
-    const uint32_t tiles_total = (n + KG_TILE - 1) / KG_TILE;
-    const size_t need = (size_t)((tiles_total + grid - 1) / grid) * KG_TILE * 4;   // keys of the largest CTA range
-    if (need <= KG_SMEM_MAX)
-        return cudaLaunchCooperativeKernel((const void*)keygen_coop_kernel<true>, dim3(grid), dim3(KG_THREADS), args, need, stream);
-    return cudaLaunchCooperativeKernel((const void*)keygen_coop_kernel<false>, dim3(grid), dim3(KG_THREADS), args, 0, stream);
+    return cudaLaunchCooperativeKernel((const void*)keygen_coop_kernel, dim3(grid), dim3(KG_THREADS), args, 0, stream);
 }
 
 void launch_culled_flags(const float4* pos, uint32_t n, const FrameConsts& fc, uint32_t* flags, cudaStream_t stream) {

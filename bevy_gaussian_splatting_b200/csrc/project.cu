@@ -198,6 +198,305 @@ __global__ void depth_range_kernel(const float4* __restrict__ pos, uint32_t n, c
     ctr->depth_max = dist(first);
 }
 
+// gaussian.wgsl:228-232: cutoff = sqrt(max(9 + 2 ln(opacity), 1e-6)) (fixed-series ln, see project_math.cuh)
+__device__ __forceinline__ float adaptive_cutoff(float opacity) {
+    const float a = 9.0f + 2.0f * det_ln(opacity);
+    return sqrtf(a > 0.000001f ? a : 0.000001f);
+}
+// f16 clouds: the adaptive cutoff depends on the 16-bit opacity alone -> a 65536-entry table built once per context
+// by this very function (bit-identical to evaluating it in place, ~70 f64 instructions cheaper per gaussian)
+__global__ void cutoff_table_kernel(float* __restrict__ tab) {
+    const uint32_t h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h < 65536u) tab[h] = adaptive_cutoff(__half2float(__ushort_as_half((unsigned short)h)));
+}
+void launch_cutoff_table(float* tab, cudaStream_t stream) { cutoff_table_kernel<<<256, 256, 0, stream>>>(tab); }
+
+// One visible gaussian: projection + colour -> the 48 B record at recs[r] (+ the 2DGS extra record).
+// `load_sh(float sh[48])` fetches the SH coefficients (only called for RasterizeMode::Color); `cutoff_pre` is the
+// tabulated adaptive cutoff, or NaN to evaluate it here.
+template <class ShLoader>
+__device__ __forceinline__ void project_one(const FrameConsts& fc, const FrameCounters* __restrict__ ctr, uint32_t r, float4 p4,
+                                            const float q[4], const float so[4], float cutoff_pre, ShLoader load_sh,
+                                            SplatRec* __restrict__ recs, float4* __restrict__ extra) {
+    SplatRec rec;
+    rec.ux = 0.f; rec.uy = 0.f; rec.vx = 0.f; rec.vy = 0.f;
+    rec.bx = BBOX_EMPTY; rec.by = BBOX_EMPTY;
+    rec.r = 0.f; rec.g = 0.f; rec.b = 0.f;
+
+    const KeyOut k = key_of(fc, p4.x, p4.y, p4.z);
+    const float W = fc.W, H = fc.H;
+    const float hw = 0.5f * W, hh = 0.5f * H;
+    const float cx = k.ndc[0] * hw + hw;
+    const float cy = hh - k.ndc[1] * hh;
+    rec.cx = cx; rec.cy = cy;
+    const float opacity = so[3];
+    rec.op = opacity * fc.global_opacity;
+    const bool drawn = k.visible && !(fc.draw_mode == BGS_DRAW_SELECTED && p4.w < 0.5f);
+
+    float A[3][3];
+#pragma unroll
+    for (int rr = 0; rr < 3; ++rr)
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc) A[rr][cc] = fc.model[cc * 4 + rr];
+    // helpers.wgsl:137-158 as (row, col); the quaternion is NOT normalised
+    float Rm[3][3];
+    {
+        const float qr = q[0], x = q[1], y = q[2], z = q[3];
+        Rm[0][0] = 1.0f - 2.0f * (y * y + z * z);
+        Rm[1][0] = 2.0f * (x * y - qr * z);
+        Rm[2][0] = 2.0f * (x * z + qr * y);
+        Rm[0][1] = 2.0f * (x * y + qr * z);
+        Rm[1][1] = 1.0f - 2.0f * (x * x + z * z);
+        Rm[2][1] = 2.0f * (y * z - qr * x);
+        Rm[0][2] = 2.0f * (x * z - qr * y);
+        Rm[1][2] = 2.0f * (y * z + qr * x);
+        Rm[2][2] = 1.0f - 2.0f * (x * x + y * y);
+    }
+    const float sc[3] = {so[0] * fc.global_scale, so[1] * fc.global_scale, so[2] * fc.global_scale};
+
+    if (drawn) {
+        float cutoff = 3.0f;
+        if (fc.adaptive) {   // gaussian.wgsl:228-232
+            cutoff = cutoff_pre == cutoff_pre ? cutoff_pre : adaptive_cutoff(opacity);
+        }
+        if (fc.gaussian_mode == BGS_GAUSSIAN_3D) {
+        // gaussian_3d.wgsl:49-72
+        float M[3][3], Sg[3][3], X[3][3], TS[3][3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) M[i][j] = sc[i] * Rm[i][j];
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) Sg[i][j] = (M[0][i] * M[0][j] + M[1][i] * M[1][j]) + M[2][i] * M[2][j];
+        // identity model: T Sigma T^t == Sigma bit for bit as long as every entry of Sigma is finite and NON-ZERO
+        // (x*1 + y*0 + z*0 then only ever adds +-0 to a non-zero value); zero entries (axis-aligned splats) keep
+        // the multiply so that even the sign of a zero matches the oracle
+        const float mn = fminf(fminf(fminf(fabsf(Sg[0][0]), fabsf(Sg[0][1])), fminf(fabsf(Sg[0][2]), fabsf(Sg[1][1]))),
+                               fminf(fabsf(Sg[1][2]), fabsf(Sg[2][2])));
+        const float mx = fmaxf(fmaxf(fmaxf(fabsf(Sg[0][0]), fabsf(Sg[0][1])), fmaxf(fabsf(Sg[0][2]), fabsf(Sg[1][1]))),
+                               fmaxf(fabsf(Sg[1][2]), fabsf(Sg[2][2])));
+        if (fc.model_identity && mn > 0.0f && mx < __uint_as_float(0x7F800000u) && Sg[0][0] == Sg[0][0] &&
+            Sg[0][1] == Sg[0][1] && Sg[0][2] == Sg[0][2] && Sg[1][1] == Sg[1][1] && Sg[1][2] == Sg[1][2] && Sg[2][2] == Sg[2][2]) {
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) TS[i][j] = Sg[i][j];
+        } else {
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) X[i][j] = (A[i][0] * Sg[0][j] + A[i][1] * Sg[1][j]) + A[i][2] * Sg[2][j];
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) TS[i][j] = (X[i][0] * A[j][0] + X[i][1] * A[j][1]) + X[i][2] * A[j][2];
+        }
+        const float c3[6] = {TS[0][0], TS[1][0], TS[2][0], TS[1][1], TS[2][1], TS[2][2]};
+        const float Vrk[3][3] = {{c3[0], c3[1], c3[2]}, {c3[1], c3[3], c3[4]}, {c3[2], c3[4], c3[5]}};
+        // helpers.wgsl:8-47
+        float tv[4];
+        mat4_point(fc.view_from_world, k.pw[0], k.pw[1], k.pw[2], tv);
+        const float fx = fc.p00 * W, fy = fc.p11 * H;
+        const float sz = 1.0f / (tv[2] * tv[2]);
+        const float J00 = fx / tv[2], J20 = -(fx * tv[0]) * sz;
+        const float J11 = -fy / tv[2], J21 = (fy * tv[1]) * sz;
+        float Tm[3][2];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const float v0 = fc.view_from_world[i * 4 + 0], v1 = fc.view_from_world[i * 4 + 1],
+                        v2 = fc.view_from_world[i * 4 + 2];
+            Tm[i][0] = v0 * J00 + v2 * J20;
+            Tm[i][1] = v1 * J11 + v2 * J21;
+        }
+        float Y[3][2];
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int b = 0; b < 2; ++b) Y[i][b] = (Vrk[i][0] * Tm[0][b] + Vrk[i][1] * Tm[1][b]) + Vrk[i][2] * Tm[2][b];
+        const float a = ((Tm[0][0] * Y[0][0] + Tm[1][0] * Y[1][0]) + Tm[2][0] * Y[2][0]) + 0.3f;
+        const float b = (Tm[0][1] * Y[0][0] + Tm[1][1] * Y[1][0]) + Tm[2][1] * Y[2][0];
+        const float c = ((Tm[0][1] * Y[0][1] + Tm[1][1] * Y[1][1]) + Tm[2][1] * Y[2][1]) + 0.3f;
+        // helpers.wgsl:49-67
+        const float det = a * c - b * b;
+        const float mid = 0.5f * (a + c);
+        const float disc = fmaxf(0.0f, mid * mid - det);
+        const float term = sqrtf(disc);
+        const float l1 = mid + term;
+        if (fc.aabb) {
+            // helpers.wgsl:69-79 + gaussian.wgsl:299-309: square of half-side cutoff*sqrt(l1), conic
+            // record (USE_AABB): ux,uy,vx = conic.x,.y,.z; vy = quad half-side (half-pixels)
+            const float l2 = fmaxf(mid - term, 0.0f);
+            const float Rq = cutoff * fmaxf(sqrtf(l1), sqrtf(l2));
+            const float dinv = 1.0f / det;
+            rec.ux = c * dinv; rec.uy = -b * dinv; rec.vx = a * dinv; rec.vy = Rq;
+            const float h = 0.5f * Rq;
+            make_bbox(cx, cy, h, h, fc.Wi, fc.Hi, rec.bx, rec.by);
+        } else {
+        // helpers.wgsl:81-119 (USE_OBB)
+        const float aa = (a - c) * (a - c);
+        const float bb = sqrtf(aa + (4.0f * b) * b);
+        const float major = sqrtf(((a + c) + bb) * 0.5f);
+        const float minor = sqrtf(((a + c) - bb) * 0.5f);
+        const float Bx = cutoff * major, By = cutoff * minor;
+        const float evx = -b, evy = l1 - a;
+        const float el = sqrtf(evx * evx + evy * evy);
+        const float e1x = evx / el, e1y = evy / el;
+        const float e2x = e1y, e2y = -e1x;
+        rec.ux = (2.0f * e1x) / Bx; rec.uy = (-2.0f * e1y) / Bx;
+        rec.vx = (2.0f * e2x) / By; rec.vy = (-2.0f * e2y) / By;
+        const float hx = 0.5f * (fabsf(e1x) * Bx + fabsf(e2x) * By);
+        const float hy = 0.5f * (fabsf(e1y) * Bx + fabsf(e2y) * By);
+        if (rec.ux == rec.ux && rec.uy == rec.uy && rec.vx == rec.vx && rec.vy == rec.vy)
+            make_bbox(cx, cy, hx, hy, fc.Wi, fc.Hi, rec.bx, rec.by);
+        }
+        } else {
+            // ---- 2DGS surfel: gaussian_2d.wgsl:77-132 (homography) + :49-75 (quad)
+            float L[3][2];   // first two columns of A * R_std * S, R_std = transpose(Rm)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const float rc[3] = {Rm[j][0] * sc[j], Rm[j][1] * sc[j], Rm[j][2] * sc[j]};
+#pragma unroll
+                for (int i = 0; i < 3; ++i) L[i][j] = (A[i][0] * rc[0] + A[i][1] * rc[1]) + A[i][2] * rc[2];
+            }
+            float G[3][4];
+            mat4_dir(fc.clip_from_world, L[0][0], L[1][0], L[2][0], G[0]);
+            mat4_dir(fc.clip_from_world, L[0][1], L[1][1], L[2][1], G[1]);
+            mat4_point(fc.clip_from_world, k.pw[0], k.pw[1], k.pw[2], G[2]);
+            const float fxk = fc.p00 * W / 2.0f, fyk = fc.p11 * H / 2.0f;     // helpers.wgsl:122-135
+            const float cxk = (W - 1.0f) / 2.0f, cyk = (H - 1.0f) / 2.0f;
+            float T0[3], T1[3], T2[3];
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                T0[j] = fxk * G[j][0] + cxk * G[j][3];
+                T1[j] = fyk * G[j][1] + cyk * G[j][3];
+                T2[j] = G[j][3];
+            }
+            const float c2 = cutoff * cutoff;
+            const float test[3] = {c2, c2, -1.0f};
+            const float tt[3] = {test[0] * T2[0], test[1] * T2[1], test[2] * T2[2]};
+            const float d = dot3(tt, T2);
+            float Rq = 0.0f, mean0 = 0.0f, mean1 = 0.0f;
+            bool ok = !(fabsf(d) < 1.0e-4f);
+            if (ok) {
+                const float inv = 1.0f / d;
+                const float f[3] = {inv * test[0], inv * test[1], inv * test[2]};
+                const float t02[3] = {T0[0] * T2[0], T0[1] * T2[1], T0[2] * T2[2]};
+                const float t12[3] = {T1[0] * T2[0], T1[1] * T2[1], T1[2] * T2[2]};
+                mean0 = dot3(f, t02); mean1 = dot3(f, t12);
+                const float f0[3] = {f[0] * T0[0], f[1] * T0[1], f[2] * T0[2]};
+                const float f1[3] = {f[0] * T1[0], f[1] * T1[1], f[2] * T1[2]};
+                const float ex = mean0 * mean0 - dot3(f0, T0);
+                const float ey = mean1 * mean1 - dot3(f1, T1);
+                if (ex < 1.0e-4f || ey < 1.0e-4f) ok = false;
+                else Rq = fmaxf(fmaxf(sqrtf(ex), sqrtf(ey)), cutoff * 0.707106f);
+            }
+            if (ok) {
+                rec.ux = 2.0f / Rq; rec.uy = 0.0f; rec.vx = 0.0f; rec.vy = -2.0f / Rq;   // OBB branch: e1=(1,0), e2=(0,1)
+                const float h = 0.5f * Rq;
+                if (Rq == Rq) make_bbox(cx, cy, h, h, fc.Wi, fc.Hi, rec.bx, rec.by);
+                if (fc.aabb && extra != nullptr) {
+                    float4* e = extra + (size_t)r * 4;
+                    e[0] = make_float4(Rq, mean0, mean1, W / H);
+                    e[1] = make_float4(T0[0], T0[1], T0[2], 0.0f);
+                    e[2] = make_float4(T1[0], T1[1], T1[2], 0.0f);
+                    e[3] = make_float4(T2[0], T2[1], T2[2], 0.0f);
+                }
+            }
+        }
+
+        // colour source
+        float rgb[3] = {0.f, 0.f, 0.f};
+        if (fc.rasterize_mode == BGS_RASTERIZE_COLOR) {
+            float sh[48];
+            load_sh(sh);
+            // gaussian.wgsl:166-183,406-416
+            const float dlt[3] = {k.pw[0] - fc.cam[0], k.pw[1] - fc.cam[1], k.pw[2] - fc.cam[2]};
+            float dw[3], loc[3], dl[3];
+            normalize3(dlt, dw);
+            if (fc.model_identity) {     // the normalised model columns are the unit axes
+                loc[0] = dw[0]; loc[1] = dw[1]; loc[2] = dw[2];
+            } else {
+#pragma unroll
+                for (int cc = 0; cc < 3; ++cc) {
+                    const float col[3] = {A[0][cc], A[1][cc], A[2][cc]};
+                    float bn[3];
+                    normalize3(col, bn);
+                    loc[cc] = dot3(bn, dw);
+                }
+            }
+            normalize3(loc, dl);
+            // spherical_harmonics.wgsl:34-68
+            const float x = dl[0], y = dl[1], z = dl[2];
+            const float xx = x * x, yy = y * y, zz = z * z;
+            float basis[16];   // (the SH constants are folded in below: 16 multiplies instead of 48)
+            basis[0] = 1.0f;
+            basis[1] = y; basis[2] = z; basis[3] = x;
+            basis[4] = x * y; basis[5] = y * z; basis[6] = (2.0f * zz - xx) - yy;
+            basis[7] = x * z; basis[8] = xx - yy;
+            basis[9] = y * (3.0f * xx - yy);
+            basis[10] = (x * y) * z;
+            basis[11] = y * ((4.0f * zz - xx) - yy);
+            basis[12] = z * ((2.0f * zz - 3.0f * xx) - 3.0f * yy);
+            basis[13] = x * ((4.0f * zz - xx) - yy);
+            basis[14] = z * (xx - yy);
+            basis[15] = x * (xx - 3.0f * yy);
+#pragma unroll
+            for (int kk = 0; kk < 16; ++kk) basis[kk] *= c_shc[kk];
+#pragma unroll
+            for (int cc = 0; cc < 3; ++cc) {
+                float acc = 0.5f;
+#pragma unroll
+                for (int kk = 0; kk < 16; ++kk) acc = fmaf(sh[3 * kk + cc], basis[kk], acc);   // colour: FMA is fine
+                rgb[cc] = acc;
+            }
+            if (fc.color_space == 0u) {
+#pragma unroll
+                for (int cc = 0; cc < 3; ++cc) rgb[cc] = srgb_to_linear(rgb[cc]);
+            }
+        } else if (fc.rasterize_mode == BGS_RASTERIZE_DEPTH) {
+            // material/depth.wgsl:3-11
+            const float dlt[3] = {k.pw[0] - fc.cam[0], k.pw[1] - fc.cam[1], k.pw[2] - fc.cam[2]};
+            const float depth = sqrtf(dot3(dlt, dlt));
+            const float dmin = ctr->depth_min, dmax = ctr->depth_max;
+            if (fc.n_cloud >= 2u) {   // the reference reads sorted[1]: undefined for a 1-gaussian cloud (oracle: black)
+            float nd = (depth - dmin) / (dmax - dmin);
+            nd = fminf(fmaxf(nd, 0.0f), 1.0f);   // fmin/fmax ignore a NaN operand, like the oracle's
+            float t1 = (nd - 0.5f) / (1.0f - 0.5f); t1 = fminf(fmaxf(t1, 0.0f), 1.0f);
+            float t2 = (nd - 0.0f) / (0.5f - 0.0f); t2 = fminf(fmaxf(t2, 0.0f), 1.0f);
+            rgb[0] = t1 * t1 * (3.0f - 2.0f * t1);
+            rgb[1] = 1.0f - fabsf(nd - 0.5f) * 2.0f;
+            rgb[2] = 1.0f - t2 * t2 * (3.0f - 2.0f * t2);
+            }
+        } else if (fc.rasterize_mode == BGS_RASTERIZE_POSITION) {
+            // gaussian.wgsl:375-376: (transformed_position - min) / (max - min)
+#pragma unroll
+            for (int cc = 0; cc < 3; ++cc) rgb[cc] = (k.pw[cc] - fc.aabb_min[cc]) / (fc.aabb_max[cc] - fc.aabb_min[cc]);
+        } else if (fc.rasterize_mode == BGS_RASTERIZE_NORMAL) {
+            // gaussian.wgsl:350-368
+            float SR[3], Ln[3], wn[4];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) SR[i] = sc[i] * Rm[i][2];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) Ln[i] = (A[i][0] * SR[0] + A[i][1] * SR[1]) + A[i][2] * SR[2];
+            mat4_dir(fc.view_from_world, Ln[0], Ln[1], Ln[2], wn);
+            const float l = sqrtf(((wn[0] * wn[0] + wn[1] * wn[1]) + wn[2] * wn[2]) + wn[3] * wn[3]);
+#pragma unroll
+            for (int cc = 0; cc < 3; ++cc) rgb[cc] = 0.5f * (wn[cc] / l + 1.0f);
+        }
+        rec.r = rgb[0]; rec.g = rgb[1]; rec.b = rgb[2];
+        if (fc.draw_mode == BGS_DRAW_HIGHLIGHT_SELECTED && p4.w > 0.5f) {   // gaussian.wgsl:423-427
+            rec.r = 0.3f; rec.g = 1.0f; rec.b = 0.1f; rec.op = 1.0f;
+        }
+    }
+    // 48 B record, three 16 B stores
+    float4* out = reinterpret_cast<float4*>(recs + r);
+    out[0] = make_float4(rec.cx, rec.cy, rec.ux, rec.uy);
+    out[1] = make_float4(rec.vx, rec.vy, __uint_as_float(rec.bx), __uint_as_float(rec.by));
+    out[2] = make_float4(rec.r, rec.g, rec.b, rec.op);
+}
+
 template <bool F16, bool BLOCKED>
 __global__ void __launch_bounds__(128, 6)
 project_kernel(const float4* __restrict__ pos, const void* __restrict__ sh_p, const void* __restrict__ rot_p,
@@ -212,283 +511,136 @@ project_kernel(const float4* __restrict__ pos, const void* __restrict__ sh_p, co
         float sh[48], q[4], so[4];
         const bool need_sh = fc.rasterize_mode == BGS_RASTERIZE_COLOR;
         const float4 p4 = Attr<F16, BLOCKED>::load(pos, sh_p, rot_p, so_p, id, sh, q, so, need_sh);
-
-        SplatRec rec;
-        rec.ux = 0.f; rec.uy = 0.f; rec.vx = 0.f; rec.vy = 0.f;
-        rec.bx = BBOX_EMPTY; rec.by = BBOX_EMPTY;
-        rec.r = 0.f; rec.g = 0.f; rec.b = 0.f;
-
-        const KeyOut k = key_of(fc, p4.x, p4.y, p4.z);
-        const float W = fc.W, H = fc.H;
-        const float hw = 0.5f * W, hh = 0.5f * H;
-        const float cx = k.ndc[0] * hw + hw;
-        const float cy = hh - k.ndc[1] * hh;
-        rec.cx = cx; rec.cy = cy;
-        const float opacity = so[3];
-        rec.op = opacity * fc.global_opacity;
-        const bool drawn = k.visible && !(fc.draw_mode == BGS_DRAW_SELECTED && p4.w < 0.5f);
-
-        float A[3][3];
+        project_one(fc, ctr, r, p4, q, so, __uint_as_float(0x7FC00000u),
+                    [&](float* out) {
 #pragma unroll
-        for (int rr = 0; rr < 3; ++rr)
+                        for (int i = 0; i < 48; ++i) out[i] = sh[i];
+                    },
+                    recs, extra);
+    }
+}
+
+// ---- TMA ring variant (gaussian-major blocks): each warp streams batches of 32 gaussians through a ring of
+// shared-memory stages.  Every lane issues ONE bulk async copy (cp.async.bulk, SASS UBLKCP) of its gaussian's whole
+// block -- 128 B (f16) / 256 B (f32) -- tracked by the stage's mbarrier (expect_tx = bytes of the batch); the copies
+// of the next STAGES - 1 batches are in flight while the warp computes the current one from shared memory, so the
+// gather's latency hides behind the ~1000 instructions per gaussian regardless of the register budget.
+// Rows are padded by 16 B (144 / 272 B stride): lane l reading 16 B chunk c touches bank group (l + c) mod 8, so the
+// per-lane LDS.128 of a batch are conflict-free.
+constexpr int PR_THREADS = 128;
+constexpr int PR_WARPS = PR_THREADS / 32;
+template <bool F16> struct Ring {
+    static constexpr int ROW = F16 ? 128 : 256;
+    static constexpr int ROWP = ROW + 16;
+    static constexpr int STAGES = F16 ? 3 : 2;
+    static constexpr int WARP_BYTES = STAGES * 32 * ROWP;
+    static constexpr int SMEM = PR_WARPS * WARP_BYTES;
+};
+__device__ __forceinline__ void pr_mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void pr_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void pr_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void pr_mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ float h_lo(uint32_t w) { return __half2float(__ushort_as_half((unsigned short)(w & 0xFFFFu))); }
+__device__ __forceinline__ float h_hi(uint32_t w) { return __half2float(__ushort_as_half((unsigned short)(w >> 16))); }
+
+template <bool F16>
+__global__ void __launch_bounds__(PR_THREADS, F16 ? 4 : 3)
+project_ring_kernel(const void* __restrict__ blocks, const uint32_t* __restrict__ index_list, int by_slot,
+                    const FrameCounters* __restrict__ ctr, FrameConsts fc, SplatRec* __restrict__ recs,
+                    float4* __restrict__ extra, const float* __restrict__ cutoff_tab) {
+    using R = Ring<F16>;
+    extern __shared__ __align__(128) unsigned char s_ring[];
+    __shared__ __align__(8) unsigned long long s_bar[PR_WARPS][R::STAGES];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t n_vis = ctr->n_vis;
+    const uint32_t nb = (n_vis + 31u) >> 5;
+    const uint32_t wg = blockIdx.x * PR_WARPS + warp, nw = gridDim.x * PR_WARPS;
+    const uint32_t a_ring = (uint32_t)__cvta_generic_to_shared(s_ring) + (uint32_t)warp * R::WARP_BYTES;
+    const uint32_t a_bar = (uint32_t)__cvta_generic_to_shared(&s_bar[warp][0]);
+    if (lane == 0) {
 #pragma unroll
-            for (int cc = 0; cc < 3; ++cc) A[rr][cc] = fc.model[cc * 4 + rr];
-        // helpers.wgsl:137-158 as (row, col); the quaternion is NOT normalised
-        float Rm[3][3];
-        {
-            const float qr = q[0], x = q[1], y = q[2], z = q[3];
-            Rm[0][0] = 1.0f - 2.0f * (y * y + z * z);
-            Rm[1][0] = 2.0f * (x * y - qr * z);
-            Rm[2][0] = 2.0f * (x * z + qr * y);
-            Rm[0][1] = 2.0f * (x * y + qr * z);
-            Rm[1][1] = 1.0f - 2.0f * (x * x + z * z);
-            Rm[2][1] = 2.0f * (y * z - qr * x);
-            Rm[0][2] = 2.0f * (x * z - qr * y);
-            Rm[1][2] = 2.0f * (y * z + qr * x);
-            Rm[2][2] = 1.0f - 2.0f * (x * x + y * y);
+        for (int s = 0; s < R::STAGES; ++s) pr_mbar_init(a_bar + 8u * s, 1u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    auto issue = [&](uint32_t k) {
+        const uint32_t batch = wg + k * nw;
+        if (batch >= nb) return;                       // (warp-uniform)
+        const int s = (int)(k % R::STAGES);
+        const uint32_t r = batch * 32u + lane;
+        const bool valid = r < n_vis;
+        uint32_t id = 0u;
+        if (valid) id = by_slot ? __ldg(index_list + r) : __ldg(index_list + (n_vis - 1u - r));
+        const uint32_t cnt = __popc(__ballot_sync(0xffffffffu, valid));
+        if (lane == 0) pr_mbar_expect_tx(a_bar + 8u * s, cnt * (uint32_t)R::ROW);
+        __syncwarp();
+        if (valid)
+            pr_bulk_g2s(a_ring + (uint32_t)(s * 32 + lane) * R::ROWP, reinterpret_cast<const char*>(blocks) + (size_t)id * R::ROW,
+                        (uint32_t)R::ROW, a_bar + 8u * s);
+    };
+#pragma unroll
+    for (int k = 0; k < R::STAGES; ++k) issue((uint32_t)k);
+
+    for (uint32_t k = 0;; ++k) {
+        const uint32_t batch = wg + k * nw;
+        if (batch >= nb) break;
+        const int s = (int)(k % R::STAGES);
+        pr_mbar_wait(a_bar + 8u * s, (k / R::STAGES) & 1u);
+        const uint32_t r = batch * 32u + lane;
+        if (r < n_vis) {
+            const uint4* row = reinterpret_cast<const uint4*>(s_ring + (size_t)warp * R::WARP_BYTES + (size_t)(s * 32 + lane) * R::ROWP);
+            float q[4], so[4];
+            float cutoff_pre = __uint_as_float(0x7FC00000u);
+            const uint4 pw = row[0];
+            const float4 p4 = make_float4(__uint_as_float(pw.x), __uint_as_float(pw.y), __uint_as_float(pw.z), __uint_as_float(pw.w));
+            if (F16) {
+                const uint4 w = row[1];
+                q[0] = h_hi(w.x); q[1] = h_lo(w.x); q[2] = h_hi(w.y); q[3] = h_lo(w.y);
+                so[0] = h_hi(w.z); so[1] = h_lo(w.z); so[2] = h_hi(w.w); so[3] = h_lo(w.w);
+                if (fc.adaptive) cutoff_pre = __ldg(cutoff_tab + (w.w & 0xFFFFu));
+            } else {
+                const uint4 a = row[1], b = row[2];
+                q[0] = __uint_as_float(a.x); q[1] = __uint_as_float(a.y); q[2] = __uint_as_float(a.z); q[3] = __uint_as_float(a.w);
+                so[0] = __uint_as_float(b.x); so[1] = __uint_as_float(b.y); so[2] = __uint_as_float(b.z); so[3] = __uint_as_float(b.w);
+            }
+            project_one(fc, ctr, r, p4, q, so, cutoff_pre,
+                        [&](float* sh) {
+                            if (F16) {
+#pragma unroll
+                                for (int i = 0; i < 6; ++i) {
+                                    const uint4 v = row[2 + i];
+                                    sh[8 * i] = h_lo(v.x); sh[8 * i + 1] = h_hi(v.x); sh[8 * i + 2] = h_lo(v.y); sh[8 * i + 3] = h_hi(v.y);
+                                    sh[8 * i + 4] = h_lo(v.z); sh[8 * i + 5] = h_hi(v.z); sh[8 * i + 6] = h_lo(v.w); sh[8 * i + 7] = h_hi(v.w);
+                                }
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < 12; ++i) {
+                                    const uint4 v = row[3 + i];
+                                    sh[4 * i] = __uint_as_float(v.x); sh[4 * i + 1] = __uint_as_float(v.y);
+                                    sh[4 * i + 2] = __uint_as_float(v.z); sh[4 * i + 3] = __uint_as_float(v.w);
+                                }
+                            }
+                        },
+                        recs, extra);
         }
-        const float sc[3] = {so[0] * fc.global_scale, so[1] * fc.global_scale, so[2] * fc.global_scale};
-
-        if (drawn) {
-            float cutoff = 3.0f;
-            if (fc.adaptive) {   // gaussian.wgsl:228-232
-                const float a = 9.0f + 2.0f * det_ln(opacity);
-                cutoff = sqrtf(a > 0.000001f ? a : 0.000001f);
-            }
-            if (fc.gaussian_mode == BGS_GAUSSIAN_3D) {
-            // gaussian_3d.wgsl:49-72
-            float M[3][3], Sg[3][3], X[3][3], TS[3][3];
-#pragma unroll
-            for (int i = 0; i < 3; ++i)
-#pragma unroll
-                for (int j = 0; j < 3; ++j) M[i][j] = sc[i] * Rm[i][j];
-#pragma unroll
-            for (int i = 0; i < 3; ++i)
-#pragma unroll
-                for (int j = 0; j < 3; ++j) Sg[i][j] = (M[0][i] * M[0][j] + M[1][i] * M[1][j]) + M[2][i] * M[2][j];
-            // identity model: T Sigma T^t == Sigma bit for bit as long as every entry of Sigma is finite and NON-ZERO
-            // (x*1 + y*0 + z*0 then only ever adds +-0 to a non-zero value); zero entries (axis-aligned splats) keep
-            // the multiply so that even the sign of a zero matches the oracle
-            const float mn = fminf(fminf(fminf(fabsf(Sg[0][0]), fabsf(Sg[0][1])), fminf(fabsf(Sg[0][2]), fabsf(Sg[1][1]))),
-                                   fminf(fabsf(Sg[1][2]), fabsf(Sg[2][2])));
-            const float mx = fmaxf(fmaxf(fmaxf(fabsf(Sg[0][0]), fabsf(Sg[0][1])), fmaxf(fabsf(Sg[0][2]), fabsf(Sg[1][1]))),
-                                   fmaxf(fabsf(Sg[1][2]), fabsf(Sg[2][2])));
-            if (fc.model_identity && mn > 0.0f && mx < __uint_as_float(0x7F800000u) && Sg[0][0] == Sg[0][0] &&
-                Sg[0][1] == Sg[0][1] && Sg[0][2] == Sg[0][2] && Sg[1][1] == Sg[1][1] && Sg[1][2] == Sg[1][2] && Sg[2][2] == Sg[2][2]) {
-#pragma unroll
-                for (int i = 0; i < 3; ++i)
-#pragma unroll
-                    for (int j = 0; j < 3; ++j) TS[i][j] = Sg[i][j];
-            } else {
-#pragma unroll
-            for (int i = 0; i < 3; ++i)
-#pragma unroll
-                for (int j = 0; j < 3; ++j) X[i][j] = (A[i][0] * Sg[0][j] + A[i][1] * Sg[1][j]) + A[i][2] * Sg[2][j];
-#pragma unroll
-            for (int i = 0; i < 3; ++i)
-#pragma unroll
-                for (int j = 0; j < 3; ++j) TS[i][j] = (X[i][0] * A[j][0] + X[i][1] * A[j][1]) + X[i][2] * A[j][2];
-            }
-            const float c3[6] = {TS[0][0], TS[1][0], TS[2][0], TS[1][1], TS[2][1], TS[2][2]};
-            const float Vrk[3][3] = {{c3[0], c3[1], c3[2]}, {c3[1], c3[3], c3[4]}, {c3[2], c3[4], c3[5]}};
-            // helpers.wgsl:8-47
-            float tv[4];
-            mat4_point(fc.view_from_world, k.pw[0], k.pw[1], k.pw[2], tv);
-            const float fx = fc.p00 * W, fy = fc.p11 * H;
-            const float sz = 1.0f / (tv[2] * tv[2]);
-            const float J00 = fx / tv[2], J20 = -(fx * tv[0]) * sz;
-            const float J11 = -fy / tv[2], J21 = (fy * tv[1]) * sz;
-            float Tm[3][2];
-#pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                const float v0 = fc.view_from_world[i * 4 + 0], v1 = fc.view_from_world[i * 4 + 1],
-                            v2 = fc.view_from_world[i * 4 + 2];
-                Tm[i][0] = v0 * J00 + v2 * J20;
-                Tm[i][1] = v1 * J11 + v2 * J21;
-            }
-            float Y[3][2];
-#pragma unroll
-            for (int i = 0; i < 3; ++i)
-#pragma unroll
-                for (int b = 0; b < 2; ++b) Y[i][b] = (Vrk[i][0] * Tm[0][b] + Vrk[i][1] * Tm[1][b]) + Vrk[i][2] * Tm[2][b];
-            const float a = ((Tm[0][0] * Y[0][0] + Tm[1][0] * Y[1][0]) + Tm[2][0] * Y[2][0]) + 0.3f;
-            const float b = (Tm[0][1] * Y[0][0] + Tm[1][1] * Y[1][0]) + Tm[2][1] * Y[2][0];
-            const float c = ((Tm[0][1] * Y[0][1] + Tm[1][1] * Y[1][1]) + Tm[2][1] * Y[2][1]) + 0.3f;
-            // helpers.wgsl:49-67
-            const float det = a * c - b * b;
-            const float mid = 0.5f * (a + c);
-            const float disc = fmaxf(0.0f, mid * mid - det);
-            const float term = sqrtf(disc);
-            const float l1 = mid + term;
-            if (fc.aabb) {
-                // helpers.wgsl:69-79 + gaussian.wgsl:299-309: square of half-side cutoff*sqrt(l1), conic
-                // record (USE_AABB): ux,uy,vx = conic.x,.y,.z; vy = quad half-side (half-pixels)
-                const float l2 = fmaxf(mid - term, 0.0f);
-                const float Rq = cutoff * fmaxf(sqrtf(l1), sqrtf(l2));
-                const float dinv = 1.0f / det;
-                rec.ux = c * dinv; rec.uy = -b * dinv; rec.vx = a * dinv; rec.vy = Rq;
-                const float h = 0.5f * Rq;
-                make_bbox(cx, cy, h, h, fc.Wi, fc.Hi, rec.bx, rec.by);
-            } else {
-            // helpers.wgsl:81-119 (USE_OBB)
-            const float aa = (a - c) * (a - c);
-            const float bb = sqrtf(aa + (4.0f * b) * b);
-            const float major = sqrtf(((a + c) + bb) * 0.5f);
-            const float minor = sqrtf(((a + c) - bb) * 0.5f);
-            const float Bx = cutoff * major, By = cutoff * minor;
-            const float evx = -b, evy = l1 - a;
-            const float el = sqrtf(evx * evx + evy * evy);
-            const float e1x = evx / el, e1y = evy / el;
-            const float e2x = e1y, e2y = -e1x;
-            rec.ux = (2.0f * e1x) / Bx; rec.uy = (-2.0f * e1y) / Bx;
-            rec.vx = (2.0f * e2x) / By; rec.vy = (-2.0f * e2y) / By;
-            const float hx = 0.5f * (fabsf(e1x) * Bx + fabsf(e2x) * By);
-            const float hy = 0.5f * (fabsf(e1y) * Bx + fabsf(e2y) * By);
-            if (rec.ux == rec.ux && rec.uy == rec.uy && rec.vx == rec.vx && rec.vy == rec.vy)
-                make_bbox(cx, cy, hx, hy, fc.Wi, fc.Hi, rec.bx, rec.by);
-            }
-            } else {
-                // ---- 2DGS surfel: gaussian_2d.wgsl:77-132 (homography) + :49-75 (quad)
-                float L[3][2];   // first two columns of A * R_std * S, R_std = transpose(Rm)
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    const float rc[3] = {Rm[j][0] * sc[j], Rm[j][1] * sc[j], Rm[j][2] * sc[j]};
-#pragma unroll
-                    for (int i = 0; i < 3; ++i) L[i][j] = (A[i][0] * rc[0] + A[i][1] * rc[1]) + A[i][2] * rc[2];
-                }
-                float G[3][4];
-                mat4_dir(fc.clip_from_world, L[0][0], L[1][0], L[2][0], G[0]);
-                mat4_dir(fc.clip_from_world, L[0][1], L[1][1], L[2][1], G[1]);
-                mat4_point(fc.clip_from_world, k.pw[0], k.pw[1], k.pw[2], G[2]);
-                const float fxk = fc.p00 * W / 2.0f, fyk = fc.p11 * H / 2.0f;     // helpers.wgsl:122-135
-                const float cxk = (W - 1.0f) / 2.0f, cyk = (H - 1.0f) / 2.0f;
-                float T0[3], T1[3], T2[3];
-#pragma unroll
-                for (int j = 0; j < 3; ++j) {
-                    T0[j] = fxk * G[j][0] + cxk * G[j][3];
-                    T1[j] = fyk * G[j][1] + cyk * G[j][3];
-                    T2[j] = G[j][3];
-                }
-                const float c2 = cutoff * cutoff;
-                const float test[3] = {c2, c2, -1.0f};
-                const float tt[3] = {test[0] * T2[0], test[1] * T2[1], test[2] * T2[2]};
-                const float d = dot3(tt, T2);
-                float Rq = 0.0f, mean0 = 0.0f, mean1 = 0.0f;
-                bool ok = !(fabsf(d) < 1.0e-4f);
-                if (ok) {
-                    const float inv = 1.0f / d;
-                    const float f[3] = {inv * test[0], inv * test[1], inv * test[2]};
-                    const float t02[3] = {T0[0] * T2[0], T0[1] * T2[1], T0[2] * T2[2]};
-                    const float t12[3] = {T1[0] * T2[0], T1[1] * T2[1], T1[2] * T2[2]};
-                    mean0 = dot3(f, t02); mean1 = dot3(f, t12);
-                    const float f0[3] = {f[0] * T0[0], f[1] * T0[1], f[2] * T0[2]};
-                    const float f1[3] = {f[0] * T1[0], f[1] * T1[1], f[2] * T1[2]};
-                    const float ex = mean0 * mean0 - dot3(f0, T0);
-                    const float ey = mean1 * mean1 - dot3(f1, T1);
-                    if (ex < 1.0e-4f || ey < 1.0e-4f) ok = false;
-                    else Rq = fmaxf(fmaxf(sqrtf(ex), sqrtf(ey)), cutoff * 0.707106f);
-                }
-                if (ok) {
-                    rec.ux = 2.0f / Rq; rec.uy = 0.0f; rec.vx = 0.0f; rec.vy = -2.0f / Rq;   // OBB branch: e1=(1,0), e2=(0,1)
-                    const float h = 0.5f * Rq;
-                    if (Rq == Rq) make_bbox(cx, cy, h, h, fc.Wi, fc.Hi, rec.bx, rec.by);
-                    if (fc.aabb && extra != nullptr) {
-                        float4* e = extra + (size_t)r * 4;
-                        e[0] = make_float4(Rq, mean0, mean1, W / H);
-                        e[1] = make_float4(T0[0], T0[1], T0[2], 0.0f);
-                        e[2] = make_float4(T1[0], T1[1], T1[2], 0.0f);
-                        e[3] = make_float4(T2[0], T2[1], T2[2], 0.0f);
-                    }
-                }
-            }
-
-            // colour source
-            float rgb[3] = {0.f, 0.f, 0.f};
-            if (fc.rasterize_mode == BGS_RASTERIZE_COLOR) {
-                // gaussian.wgsl:166-183,406-416
-                const float dlt[3] = {k.pw[0] - fc.cam[0], k.pw[1] - fc.cam[1], k.pw[2] - fc.cam[2]};
-                float dw[3], loc[3], dl[3];
-                normalize3(dlt, dw);
-                if (fc.model_identity) {     // the normalised model columns are the unit axes
-                    loc[0] = dw[0]; loc[1] = dw[1]; loc[2] = dw[2];
-                } else {
-#pragma unroll
-                    for (int cc = 0; cc < 3; ++cc) {
-                        const float col[3] = {A[0][cc], A[1][cc], A[2][cc]};
-                        float bn[3];
-                        normalize3(col, bn);
-                        loc[cc] = dot3(bn, dw);
-                    }
-                }
-                normalize3(loc, dl);
-                // spherical_harmonics.wgsl:34-68
-                const float x = dl[0], y = dl[1], z = dl[2];
-                const float xx = x * x, yy = y * y, zz = z * z;
-                float basis[16];   // (the SH constants are folded in below: 16 multiplies instead of 48)
-                basis[0] = 1.0f;
-                basis[1] = y; basis[2] = z; basis[3] = x;
-                basis[4] = x * y; basis[5] = y * z; basis[6] = (2.0f * zz - xx) - yy;
-                basis[7] = x * z; basis[8] = xx - yy;
-                basis[9] = y * (3.0f * xx - yy);
-                basis[10] = (x * y) * z;
-                basis[11] = y * ((4.0f * zz - xx) - yy);
-                basis[12] = z * ((2.0f * zz - 3.0f * xx) - 3.0f * yy);
-                basis[13] = x * ((4.0f * zz - xx) - yy);
-                basis[14] = z * (xx - yy);
-                basis[15] = x * (xx - 3.0f * yy);
-#pragma unroll
-                for (int kk = 0; kk < 16; ++kk) basis[kk] *= c_shc[kk];
-#pragma unroll
-                for (int cc = 0; cc < 3; ++cc) {
-                    float acc = 0.5f;
-#pragma unroll
-                    for (int kk = 0; kk < 16; ++kk) acc = fmaf(sh[3 * kk + cc], basis[kk], acc);   // colour: FMA is fine
-                    rgb[cc] = acc;
-                }
-                if (fc.color_space == 0u) {
-#pragma unroll
-                    for (int cc = 0; cc < 3; ++cc) rgb[cc] = srgb_to_linear(rgb[cc]);
-                }
-            } else if (fc.rasterize_mode == BGS_RASTERIZE_DEPTH) {
-                // material/depth.wgsl:3-11
-                const float dlt[3] = {k.pw[0] - fc.cam[0], k.pw[1] - fc.cam[1], k.pw[2] - fc.cam[2]};
-                const float depth = sqrtf(dot3(dlt, dlt));
-                const float dmin = ctr->depth_min, dmax = ctr->depth_max;
-                if (fc.n_cloud >= 2u) {   // the reference reads sorted[1]: undefined for a 1-gaussian cloud (oracle: black)
-                float nd = (depth - dmin) / (dmax - dmin);
-                nd = fminf(fmaxf(nd, 0.0f), 1.0f);   // fmin/fmax ignore a NaN operand, like the oracle's
-                float t1 = (nd - 0.5f) / (1.0f - 0.5f); t1 = fminf(fmaxf(t1, 0.0f), 1.0f);
-                float t2 = (nd - 0.0f) / (0.5f - 0.0f); t2 = fminf(fmaxf(t2, 0.0f), 1.0f);
-                rgb[0] = t1 * t1 * (3.0f - 2.0f * t1);
-                rgb[1] = 1.0f - fabsf(nd - 0.5f) * 2.0f;
-                rgb[2] = 1.0f - t2 * t2 * (3.0f - 2.0f * t2);
-                }
-            } else if (fc.rasterize_mode == BGS_RASTERIZE_POSITION) {
-                // gaussian.wgsl:375-376: (transformed_position - min) / (max - min)
-#pragma unroll
-                for (int cc = 0; cc < 3; ++cc) rgb[cc] = (k.pw[cc] - fc.aabb_min[cc]) / (fc.aabb_max[cc] - fc.aabb_min[cc]);
-            } else if (fc.rasterize_mode == BGS_RASTERIZE_NORMAL) {
-                // gaussian.wgsl:350-368
-                float SR[3], Ln[3], wn[4];
-#pragma unroll
-                for (int i = 0; i < 3; ++i) SR[i] = sc[i] * Rm[i][2];
-#pragma unroll
-                for (int i = 0; i < 3; ++i) Ln[i] = (A[i][0] * SR[0] + A[i][1] * SR[1]) + A[i][2] * SR[2];
-                mat4_dir(fc.view_from_world, Ln[0], Ln[1], Ln[2], wn);
-                const float l = sqrtf(((wn[0] * wn[0] + wn[1] * wn[1]) + wn[2] * wn[2]) + wn[3] * wn[3]);
-#pragma unroll
-                for (int cc = 0; cc < 3; ++cc) rgb[cc] = 0.5f * (wn[cc] / l + 1.0f);
-            }
-            rec.r = rgb[0]; rec.g = rgb[1]; rec.b = rgb[2];
-            if (fc.draw_mode == BGS_DRAW_HIGHLIGHT_SELECTED && p4.w > 0.5f) {   // gaussian.wgsl:423-427
-                rec.r = 0.3f; rec.g = 1.0f; rec.b = 0.1f; rec.op = 1.0f;
-            }
-        }
-        // 48 B record, three 16 B stores
-        float4* out = reinterpret_cast<float4*>(recs + r);
-        out[0] = make_float4(rec.cx, rec.cy, rec.ux, rec.uy);
-        out[1] = make_float4(rec.vx, rec.vy, __uint_as_float(rec.bx), __uint_as_float(rec.by));
-        out[2] = make_float4(rec.r, rec.g, rec.b, rec.op);
+        __syncwarp();                                  // every lane is done with the stage before it is refilled
+        issue(k + (uint32_t)R::STAGES);
     }
 }
 
@@ -499,16 +651,35 @@ void launch_depth_range(const float4* pos, uint32_t n, const uint32_t* sorted_pa
 
 void launch_project(bool f16, bool blocked, const float4* pos, const void* sh, const void* rot, const void* so,
                     const uint32_t* index_list, int by_slot, const FrameCounters* ctr, const FrameConsts& fc,
-                    SplatRec* recs, float4* extra, uint32_t n_hint, cudaStream_t stream) {
-    // grid sized from a hint (last frame's visible count + head-room); the grid-stride loop keeps any
-    // n_vis correct.  Short-lived CTAs (not a persistent grid) so a concurrent sort can interleave.
+                    SplatRec* recs, float4* extra, uint32_t n_hint, int sm_count, int ctas_per_sm, const float* cutoff_tab,
+                    cudaStream_t stream) {
+    if (blocked) {
+        // TMA ring over the gaussian-major blocks (`sh` carries the block array): a persistent grid of at most
+        // ctas_per_sm CTAs per SM (2 when a depth sort shares the SMs, else the occupancy limit)
+        static bool attr_set[64] = {};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+            cudaFuncSetAttribute(project_ring_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Ring<true>::SMEM);
+            cudaFuncSetAttribute(project_ring_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Ring<false>::SMEM);
+            if (dev >= 0 && dev < 64) attr_set[dev] = true;
+        }
+        const int occ = f16 ? 4 : 3;
+        if (ctas_per_sm <= 0 || ctas_per_sm > occ) ctas_per_sm = occ;
+        uint32_t blocks = (n_hint + PR_THREADS - 1) / PR_THREADS;
+        const uint32_t cap = (uint32_t)(sm_count * ctas_per_sm);
+        if (blocks > cap) blocks = cap;
+        if (blocks == 0) blocks = 1;
+        if (f16) project_ring_kernel<true><<<blocks, PR_THREADS, Ring<true>::SMEM, stream>>>(sh, index_list, by_slot, ctr, fc, recs, extra, cutoff_tab);
+        else project_ring_kernel<false><<<blocks, PR_THREADS, Ring<false>::SMEM, stream>>>(sh, index_list, by_slot, ctr, fc, recs, extra, cutoff_tab);
+        return;
+    }
+    // planar planes (BGS_LAYOUT=planar): per-thread gather.  Grid sized from a hint (last frame's visible count +
+    // head-room); the grid-stride loop keeps any n_vis correct.
     uint32_t blocks = (n_hint + 127) / 128;
     if (blocks > 65535u * 8u) blocks = 65535u * 8u;
     if (blocks < 148u) blocks = 148u;
-    // blocked layout: `sh` carries the block array
-    if (f16 && blocked) project_kernel<true, true><<<blocks, 128, 0, stream>>>(pos, sh, rot, so, index_list, by_slot, ctr, fc, recs, extra);
-    else if (f16) project_kernel<true, false><<<blocks, 128, 0, stream>>>(pos, sh, rot, so, index_list, by_slot, ctr, fc, recs, extra);
-    else if (blocked) project_kernel<false, true><<<blocks, 128, 0, stream>>>(pos, sh, rot, so, index_list, by_slot, ctr, fc, recs, extra);
+    if (f16) project_kernel<true, false><<<blocks, 128, 0, stream>>>(pos, sh, rot, so, index_list, by_slot, ctr, fc, recs, extra);
     else project_kernel<false, false><<<blocks, 128, 0, stream>>>(pos, sh, rot, so, index_list, by_slot, ctr, fc, recs, extra);
 }
 

@@ -87,6 +87,42 @@ __device__ __forceinline__ uint32_t key_of_fast(const FrameConsts& c, float px, 
     return key >> c.key_shift;
 }
 
+// The visibility decision of key_of_fast alone (key-gen phase 1: one bit per gaussian, no key).
+__device__ __forceinline__ bool visible_fast(const FrameConsts& c, float px, float py, float pz) {
+    float pw[4];
+    if (c.model_identity && (fabsf(px) + fabsf(py)) + fabsf(pz) < __uint_as_float(0x7F800000u)) {
+        pw[0] = px; pw[1] = py; pw[2] = pz;
+    } else {
+        mat4_point(c.model, px, py, pz, pw);
+    }
+    float cl[4];
+    mat4_point(c.clip_from_world, pw[0], pw[1], pw[2], cl);
+    const float den = cl[3] + 0.000000001f;
+    float rc;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(den));
+    const float ax = fabsf(cl[0] * rc), ay = fabsf(cl[1] * rc), z = cl[2] * rc;
+    const float ad = fabsf(den);
+    const bool sure_in = ax < 1.0999f && ay < 1.0999f && z > 1e-6f && z < 0.9999f;
+    const bool sure_out = ax > 1.1001f || ay > 1.1001f || z < -1e-6f || z > 1.0001f;
+    const bool den_ok = ad > 1e-30f && ad < 1e30f;
+    if (den_ok && (sure_in || sure_out)) return sure_in;
+    const float nx = cl[0] / den, ny = cl[1] / den, nz = cl[2] / den;
+    return fabsf(nx) < 1.1f && fabsf(ny) < 1.1f && fabsf(nz - 0.5f) < 0.5f;
+}
+
+// The key of a gaussian already known to be visible (key-gen phase 2): same pw, same d2 as key_of.
+__device__ __forceinline__ uint32_t key_only(const FrameConsts& c, float px, float py, float pz) {
+    float pw[4];
+    if (c.model_identity && (fabsf(px) + fabsf(py)) + fabsf(pz) < __uint_as_float(0x7F800000u)) {
+        pw[0] = px; pw[1] = py; pw[2] = pz;
+    } else {
+        mat4_point(c.model, px, py, pz, pw);
+    }
+    const float dx = pw[0] - c.cam[0], dy = pw[1] - c.cam[1], dz = pw[2] - c.cam[2];
+    const float d2 = (dx * dx + dy * dy) + dz * dz;
+    return (0xFFFFFFFFu - __float_as_uint(d2)) >> c.key_shift;
+}
+
 // Fixed-series natural log in f64 (the policy replacement for WGSL log(), gaussian.wgsl:229):
 // x = m 2^e, m in [sqrt(1/2), sqrt 2); s = (m-1)/(m+1); ln x = e ln2 + 2 s P(s^2), rounded to f32.
 __device__ __forceinline__ float det_ln(float xf) {

@@ -1,313 +1,374 @@
-// radix.cu -- stage 2 (and the tile-id sort of stage 4): stable LSD radix sort, 8-bit digits,
-// ONE global sweep per digit place ("onesweep": per-tile warp-level ranking + decoupled
-// look-back across tiles; no separate count / scan-over-tiles dispatches).
+// radix.cu -- stage 2 (and the tile-id sort of stage 4): stable LSD radix sort, 8-bit digits, ALL digit
+// places of one sort inside ONE cooperative launch.
 //
-// Replaces radix_sort_b / radix_sort_c_count_tiles / radix_sort_c_scan_tiles /
-// radix_sort_c_scatter (src/sort/radix.wgsl:110-279) and the 3P+3 dispatches of run_radix_sort
-// (src/sort/radix.rs:672-754).  Same contract: ascending by key, stable (ties keep input order),
-// P = depth_bits / 8 passes (src/render/mod.rs:715-745).  Entry count comes from device memory
-// (n_ptr) so no host round-trip sits between key-gen and the sort.
+// Replaces radix_sort_b / radix_sort_c_count_tiles / radix_sort_c_scan_tiles / radix_sort_c_scatter
+// (src/sort/radix.wgsl:110-279) and the 3P+3 dispatches of run_radix_sort (src/sort/radix.rs:672-754).  Same
+// contract: ascending by key, stable (ties keep input order), P = depth_bits / 8 passes
+// (src/render/mod.rs:715-745).  The entry count comes from device memory (n_ptr): no host round-trip sits
+// between key-gen and the sort.
 //
-// HBM-bound: per pass 8 B read + 8 B written per entry; histogram pre-pass reads 4 B per entry.
+// Each pass is a "onesweep": a CTA loads a tile, ranks it per warp (stable), publishes the tile's digit counts,
+// obtains its global digit offsets by decoupled look-back over the predecessors' counts, and scatters.  The
+// passes of a sort are separated by a grid barrier instead of a kernel boundary (the keys/payload of a depth
+// sort at C3 are 5.8 MB: they never leave L2), tiles are assigned statically (tile = blockIdx.x + k * grid:
+// all CTAs are co-resident, predecessors are always in flight), and the look-back status words carry a
+// per-launch epoch so they never need clearing.
+//   optional phase 0: the digit histograms of all passes (pair sort; the depth sort gets them from key-gen)
+//   optional epilogue of the last pass: per-tile ranges of the sorted pair list (a7) -- replaces a separate
+//   pass over the sorted keys.
+//
+// HBM/L2-bound: per pass 8 B read + 8 B written per entry; histogram phase reads 4 B per entry.
 #include "common.cuh"
 
 namespace bgs {
 
-constexpr int RS_THREADS = 256;
-constexpr int RS_WARPS = RS_THREADS / 32;
-constexpr int RS_ITEMS_MIN = 8;                  // small sorts: 2048-entry tiles (latency), large: 4096 (throughput)
-constexpr int LB_BATCH = 8;                       // look-back loads in flight per thread
+constexpr int RS_THREADS = 512;                   // fat CTAs, one (two for > 1.2 M entries) per SM: a single-wave sort has
+constexpr int RS_WARPS = RS_THREADS / 32;         // <= 148 (296) tiles, so the look-back walks (traffic ~ tiles^2 x 2 KB)
+                                                  // stay short; 512 x 64 registers leave half an SM to a concurrent kernel
+constexpr int RS_TABLE_WORDS = RS_WARPS * 256;    // one peer-mask table (all warps)
+constexpr int LB_BATCH = 16;                      // look-back loads in flight per thread
 
-// ---- digit histograms for all passes in one read of the keys -----------------------------
-constexpr int HS_THREADS = 256;
-constexpr int HS_ITEMS = 16;
-
-__global__ void __launch_bounds__(HS_THREADS)
-radix_hist_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ n_ptr, int passes,
-                  uint32_t* __restrict__ hist /* [passes][256] */) {
-    __shared__ uint32_t s_hist[4 * 256];
-    const uint32_t n = *n_ptr;
-    for (int i = threadIdx.x; i < passes * 256; i += HS_THREADS) s_hist[i] = 0u;
-    __syncthreads();
-    const uint32_t chunk = HS_THREADS * HS_ITEMS;
-    for (uint32_t base = blockIdx.x * chunk; base < n; base += gridDim.x * chunk) {
-        uint32_t k[HS_ITEMS];
-#pragma unroll
-        for (int j = 0; j < HS_ITEMS; ++j) {
-            const uint32_t i = base + j * HS_THREADS + threadIdx.x;
-            k[j] = (i < n) ? __ldcs(keys + i) : 0u;
-        }
-        for (int p = 0; p < passes; ++p) {
-            // a thread's consecutive keys often share the high digits (depth keys): merge runs
-            // before touching shared memory to keep same-bin atomic contention low
-            uint32_t run_d = 0xFFFFFFFFu, run_c = 0u;
-#pragma unroll
-            for (int j = 0; j < HS_ITEMS; ++j) {
-                const uint32_t i = base + j * HS_THREADS + threadIdx.x;
-                if (i >= n) break;
-                const uint32_t d = (k[j] >> (8 * p)) & 255u;
-                if (d == run_d) { ++run_c; }
-                else {
-                    if (run_c) atomicAdd(&s_hist[p * 256 + run_d], run_c);
-                    run_d = d; run_c = 1u;
-                }
-            }
-            if (run_c) atomicAdd(&s_hist[p * 256 + run_d], run_c);
-        }
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < passes * 256; i += HS_THREADS) {
-        const uint32_t c = s_hist[i];
-        if (c) atomicAdd(&hist[i], c);
-    }
+// status word: [63:34] epoch, [33:32] flag (1 = tile aggregate, 2 = inclusive prefix), [31:0] value
+constexpr unsigned long long ST_AGG = 1ull << 32, ST_INC = 2ull << 32;
+__device__ __forceinline__ unsigned long long ld_status(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_status(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void stamp_clk(unsigned long long* tl, int slot) {   // debug: SM cycles, exact intra-CTA deltas
+    if (tl != nullptr && threadIdx.x == 0) tl[slot] = (unsigned long long)clock64();
 }
 
-// ---- one digit place ------------------------------------------------------------------------
-template <int RS_ITEMS>
-__global__ void __launch_bounds__(RS_THREADS, 4)
-onesweep_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
-                uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
-                const uint32_t* __restrict__ n_ptr, const uint32_t* __restrict__ hist /* raw counts [256] */,
-                uint32_t* __restrict__ status /* [tiles][256], zeroed */, uint32_t* __restrict__ tile_ctr,
-                int shift, unsigned long long* __restrict__ tl) {
+struct SortParams {
+    uint32_t* keys[2];
+    uint32_t* vals[2];
+    const uint32_t* n_ptr;          // entries to sort (device)
+    uint32_t* hist;                 // [passes][256] raw digit counts (zero on entry when compute_hist)
+    unsigned long long* status;     // [passes][status_stride] look-back words
+    size_t status_stride;           // words per pass = max tiles * 256
+    uint32_t epoch;                 // unique per launch within the status array's lifetime, never 0
+    uint32_t* barrier;              // grid barrier word, zero on entry
+    int passes;
+    int shift0;                     // pass p sorts on bits [shift0 + 8p, shift0 + 8p + 8)
+    int compute_hist;
+    uint2* ranges;                  // non-null: the keys are tile ids; the last pass emits ranges[id] = (~start, end)
+    unsigned long long* tl;         // debug timeline (BGS_TIMELINE_SORT): per tile of pass 1, 8 clock64 stamps
+};
+
+constexpr size_t radix_smem_bytes(int items) {
+    const size_t tile = (size_t)RS_THREADS * items;
+    const size_t kv = tile > (size_t)RS_TABLE_WORDS ? tile : (size_t)RS_TABLE_WORDS;
+    return (2 * kv + (size_t)RS_WARPS * 256 + 256 + 256 + RS_WARPS) * 4;
+}
+
+template <int RS_ITEMS, bool MASK_TABLE>
+__global__ void __launch_bounds__(RS_THREADS, 2)
+radix_coop_kernel(SortParams P) {
     constexpr int RS_TILE = RS_THREADS * RS_ITEMS;
-    __shared__ uint32_t s_keys[RS_TILE];
-    __shared__ uint32_t s_vals[RS_TILE];
-    __shared__ uint32_t s_whist[RS_WARPS][256];   // per-warp digit counts -> per-warp exclusive offsets
-    __shared__ uint32_t s_binstart[256];          // tile-local exclusive digit offsets
-    __shared__ uint32_t s_gbase[256];             // global destination of digit d's run, minus s_binstart[d]
-    __shared__ uint32_t s_wtot[RS_WARPS];
-    __shared__ uint32_t s_tile;
+    constexpr int KV_WORDS = RS_TILE > RS_TABLE_WORDS ? RS_TILE : RS_TABLE_WORDS;
+    extern __shared__ __align__(16) uint32_t s_dyn[];
+    uint32_t* s_keys = s_dyn;                                   // [KV_WORDS]  (first: peer-mask table B)
+    uint32_t* s_vals = s_keys + KV_WORDS;                       // [KV_WORDS]  (first: peer-mask table A)
+    uint32_t (*s_whist)[256] = reinterpret_cast<uint32_t (*)[256]>(s_vals + KV_WORDS);   // per-warp digit counts -> offsets
+    uint32_t* s_binstart = &s_whist[0][0] + RS_WARPS * 256;     // [256] tile-local exclusive digit offsets
+    uint32_t* s_gbase = s_binstart + 256;                       // [256] global destination of digit d's run, minus s_binstart[d]
+    uint32_t* s_wtot = s_gbase + 256;                           // [RS_WARPS]
 
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    const uint32_t n = *n_ptr;
+    const uint32_t G = gridDim.x;
+    const uint32_t n = *P.n_ptr;
     const uint32_t num_tiles = (n + RS_TILE - 1) / RS_TILE;
+    uint32_t bar_target = 0u;
 
-    while (true) {
-        if (t == 0) s_tile = atomicAdd(tile_ctr, 1u);
-#pragma unroll
-        for (int i = 0; i < RS_WARPS; ++i) s_whist[i][t] = 0u;
-        if (RS_ITEMS == RS_ITEMS_MIN) {
-#pragma unroll
-            for (int i = 0; i < RS_WARPS; ++i) s_vals[i * 256 + t] = 0u;   // the peer-mask table
-        }
+    // ---- phase 0 (optional): digit histograms of every pass in one read of the keys
+    if (P.compute_hist) {
+        uint32_t* s_hist = &s_whist[0][0];        // [passes <= 4][256]
+        for (int i = t; i < P.passes * 256; i += RS_THREADS) s_hist[i] = 0u;
         __syncthreads();
-        const uint32_t tile = s_tile;
-        if (tile >= num_tiles) break;
-        const uint32_t tile_base = tile * RS_TILE;
-        unsigned long long* tlt = tl ? tl + (size_t)(tile < 4096u ? tile : 4095u) * 8 - (size_t)blockIdx.x * 8 : nullptr;
-        timeline_stamp(tlt, 0);
-
-        // warp-striped load: warp w owns [w*512, (w+1)*512) of the tile; item j = 32 consecutive entries
-        uint32_t k[RS_ITEMS];
-        const uint32_t my_base = tile_base + warp * (32 * RS_ITEMS) + lane;
+        const uint32_t* kin = P.keys[0];
+        for (uint32_t base = blockIdx.x * RS_TILE; base < n; base += G * RS_TILE) {
+            uint32_t k[RS_ITEMS];
 #pragma unroll
-        for (int j = 0; j < RS_ITEMS; ++j) {
-            const uint32_t i = my_base + j * 32;
-            k[j] = (i < n) ? __ldcs(keys_in + i) : 0xFFFFFFFFu;   // padding sorts to the tile's tail
-        }
-        // stable in-warp ranking: entries of one digit are ranked in (item, lane) order
-        uint32_t rank[RS_ITEMS];
-#pragma unroll
-        for (int j = 0; j < RS_ITEMS; ++j) {
-            const uint32_t d = (k[j] >> shift) & 255u;
-#ifdef RS_MATCH_BALLOT
-            // 8 ballots + mask intersections instead of one MATCH.ANY (which issues at a fraction of the ALU rate)
-            uint32_t peers = 0xffffffffu;
-#pragma unroll
-            for (int bit = 0; bit < 8; ++bit) {
-                const bool on = (d >> bit) & 1u;
-                const uint32_t m = __ballot_sync(0xffffffffu, on);
-                peers &= on ? m : ~m;
+            for (int j = 0; j < RS_ITEMS; ++j) {
+                const uint32_t i = base + j * RS_THREADS + t;
+                k[j] = (i < n) ? __ldcg(kin + i) : 0u;
             }
-#else
-            uint32_t peers;
-            if (RS_ITEMS == RS_ITEMS_MIN) {
-                // small (latency-bound) sorts: peers via a per-warp mask table in shared memory (aliases s_vals,
-                // unused until the scatter): one ATOMS.OR per lane, conflicts only among lanes sharing the digit.
-                // Measured on B200 (C3): -8 us on the depth sort, -12 us on the pair sort vs MATCH.ANY.
-                uint32_t* mm = s_vals + warp * 256;
-                atomicOr(&mm[d], 1u << lane);
-                __syncwarp();
-                peers = mm[d];
-                __syncwarp();
-                if (lane == 31 - __clz(peers)) mm[d] = 0u;
-            } else {
-                // large (throughput-bound) sorts: MATCH.ANY (the mask table loses there: 232 vs 190 us at 6 M entries)
-                peers = __match_any_sync(0xffffffffu, d);
-            }
-#endif
-            const int leader = 31 - __clz(peers);
-            uint32_t old = 0u;
-            if (lane == leader) {
-                old = s_whist[warp][d];
-                s_whist[warp][d] = old + __popc(peers);
-            }
-            old = __shfl_sync(0xffffffffu, old, leader);
-            rank[j] = old + __popc(peers & lanemask_lt());
-            __syncwarp();
-        }
-        timeline_stamp(tlt, 1);
-        __syncthreads();
-
-        // thread t owns digit t: exclusive scan across warps, tile totals
-        uint32_t cnt = 0u;
+            for (int p = 0; p < P.passes; ++p) {
+                // a thread's consecutive keys often share a digit (clustered tile ids / depth keys): merge runs
+                uint32_t run_d = 0xFFFFFFFFu, run_c = 0u;
 #pragma unroll
-        for (int w = 0; w < RS_WARPS; ++w) {
-            const uint32_t c = s_whist[w][t];
-            s_whist[w][t] = cnt;
-            cnt += c;
-        }
-        const uint32_t tile_end = tile_base + RS_TILE;
-        const uint32_t pad = (tile_end > n) ? (tile_end - n) : 0u;
-        const uint32_t cnt_valid = (t == 255) ? cnt - pad : cnt;   // padding is all digit 255
-
-        // tile-local exclusive scan over digits (padding included: it defines smem positions)
-        uint32_t incl = cnt;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += y;
-        }
-        if (lane == 31) s_wtot[warp] = incl;
-        // global exclusive scan of the raw histogram (tile 0 seeds the look-back chain with it)
-        uint32_t gh_incl = 0u, gh = 0u;
-        if (tile == 0) {
-            gh = hist[t];
-            gh_incl = gh;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t y = __shfl_up_sync(0xffffffffu, gh_incl, o);
-                if (lane >= o) gh_incl += y;
-            }
-        }
-        __syncthreads();
-        uint32_t wprefix = 0u;
-        for (int w = 0; w < warp; ++w) wprefix += s_wtot[w];
-        const uint32_t binstart = wprefix + incl - cnt;
-        s_binstart[t] = binstart;
-
-        timeline_stamp(tlt, 2);
-        // decoupled look-back, one digit per thread
-        uint32_t excl;
-        uint32_t* my_status = status + (size_t)tile * 256 + t;
-        if (tile == 0) {
-            __syncthreads();                      // s_wtot reuse below
-            if (lane == 31) s_wtot[warp] = gh_incl;
-            __syncthreads();
-            uint32_t gp = 0u;
-            for (int w = 0; w < warp; ++w) gp += s_wtot[w];
-            excl = gp + gh_incl - gh;
-            st_volatile(my_status, LB_INC | ((excl + cnt_valid) & LB_VMASK));
-        } else {
-            st_volatile(my_status, LB_AGG | cnt_valid);
-            excl = 0u;
-#ifdef BGS_EXP_NOLOOKBACK
-            if (false)
-#endif
-            {
-            // look back over the predecessors' per-digit words, LB_BATCH independent loads in flight
-            const uint32_t* ps = my_status;
-            uint32_t back = tile;
-            bool found = false;
-            while (!found) {
-                uint32_t w[LB_BATCH];
-#pragma unroll
-                for (int q = 0; q < LB_BATCH; ++q)
-                    w[q] = ((uint32_t)q < back) ? ld_volatile(ps - 256 * (q + 1)) : (LB_INC | 0u);
-#pragma unroll
-                for (int q = 0; q < LB_BATCH; ++q) {
-                    if (!found) {
-                        uint32_t x = w[q];
-                        while ((x >> 30) == 0u) x = ld_volatile(ps - 256 * (q + 1));
-                        excl += x & LB_VMASK;
-                        found = (x >> 30) == 2u;
+                for (int j = 0; j < RS_ITEMS; ++j) {
+                    const uint32_t i = base + j * RS_THREADS + t;
+                    if (i >= n) break;
+                    const uint32_t d = (k[j] >> (P.shift0 + 8 * p)) & 255u;
+                    if (d == run_d) { ++run_c; }
+                    else {
+                        if (run_c) atomicAdd(&s_hist[p * 256 + run_d], run_c);
+                        run_d = d; run_c = 1u;
                     }
                 }
-                ps -= 256 * LB_BATCH;
-                back = back > (uint32_t)LB_BATCH ? back - LB_BATCH : 0u;
+                if (run_c) atomicAdd(&s_hist[p * 256 + run_d], run_c);
             }
-            }
-            st_volatile(my_status, LB_INC | ((excl + cnt_valid) & LB_VMASK));
-        }
-        s_gbase[t] = excl - binstart;
-        __syncthreads();
-        timeline_stamp(tlt, 3);
-
-        // scatter into tile-sorted order in shared memory
-#pragma unroll
-        for (int j = 0; j < RS_ITEMS; ++j) {
-            const uint32_t d = (k[j] >> shift) & 255u;
-            const uint32_t pos = s_binstart[d] + s_whist[warp][d] + rank[j];
-            const uint32_t i = my_base + j * 32;
-            s_keys[pos] = k[j];
-            s_vals[pos] = (i < n) ? __ldcs(vals_in + i) : 0u;
         }
         __syncthreads();
-        // coalesced write-out: consecutive positions of one digit land on consecutive addresses
-        const uint32_t valid = RS_TILE - pad;
-#pragma unroll 4
-        for (uint32_t p = t; p < valid; p += RS_THREADS) {
-            const uint32_t kk = s_keys[p];
-            const uint32_t dst = s_gbase[(kk >> shift) & 255u] + p;
-            keys_out[dst] = kk;
-            vals_out[dst] = s_vals[p];
+        for (int i = t; i < P.passes * 256; i += RS_THREADS) {
+            const uint32_t c = s_hist[i];
+            if (c) atomicAdd(&P.hist[i], c);
         }
-        timeline_stamp(tlt, 4);
-        __syncthreads();
+        bar_target += G;
+        grid_barrier(P.barrier, bar_target);
     }
-}
 
-// Clears the look-back status rows a sort over *n_ptr entries has used (passes rows of `stride` words), so the same
-// rows can serve the next sort of the frame (chunked frames run one pair sort per round).
-__global__ void status_clear_kernel(uint32_t* __restrict__ status, size_t stride, int passes, const uint32_t* __restrict__ n_ptr) {
-    const uint32_t n = *n_ptr;
-    const uint32_t t = RS_THREADS * RS_ITEMS_MIN;
-    const size_t words = (size_t)((n + t - 1) / t) * 256u / 4u;   // uint4 stores
-    for (int p = 0; p < passes; ++p) {
-        uint4* row = reinterpret_cast<uint4*>(status + (size_t)p * stride);
-        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < words; i += (size_t)gridDim.x * blockDim.x)
-            row[i] = make_uint4(0u, 0u, 0u, 0u);
+    const unsigned long long ep = (unsigned long long)P.epoch << 34;
+    int cur = 0;
+    for (int p = 0; p < P.passes; ++p, cur ^= 1) {
+        const int shift = P.shift0 + 8 * p;
+        // (selects, not P.keys[cur]: a dynamically indexed kernel parameter would be copied to local memory)
+        const uint32_t* __restrict__ keys_in = cur ? P.keys[1] : P.keys[0];
+        const uint32_t* __restrict__ vals_in = cur ? P.vals[1] : P.vals[0];
+        uint32_t* __restrict__ keys_out = cur ? P.keys[0] : P.keys[1];
+        uint32_t* __restrict__ vals_out = cur ? P.vals[0] : P.vals[1];
+        unsigned long long* status = P.status + (size_t)p * P.status_stride;
+        const bool emit_ranges = P.ranges != nullptr && p == P.passes - 1;
+
+        for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += G) {
+            const uint32_t tile_base = tile * RS_TILE;
+            unsigned long long* tlt = (P.tl && p == 1) ? P.tl + (size_t)(tile < 4096u ? tile : 4095u) * 8 : nullptr;
+            stamp_clk(tlt, 0);
+            // warp-striped load: warp w owns [w*32*ITEMS, (w+1)*32*ITEMS) of the tile; item j = 32 consecutive entries
+            uint32_t k[RS_ITEMS];
+            const uint32_t my_base = tile_base + warp * (32 * RS_ITEMS) + lane;
+#pragma unroll
+            for (int j = 0; j < RS_ITEMS; ++j) {
+                const uint32_t i = my_base + j * 32;
+                k[j] = (i < n) ? __ldcg(keys_in + i) : 0xFFFFFFFFu;   // padding sorts to the tile's tail
+            }
+            // (thread t clears column t & 255 of 8 of the 32 per-warp rows; ditto the two peer-mask tables)
+#pragma unroll
+            for (int i = 0; i < RS_WARPS * 256 / RS_THREADS; ++i) (&s_whist[0][0])[i * RS_THREADS + t] = 0u;
+            if (MASK_TABLE) {
+#pragma unroll
+                for (int i = 0; i < RS_TABLE_WORDS / RS_THREADS; ++i) { s_vals[i * RS_THREADS + t] = 0u; s_keys[i * RS_THREADS + t] = 0u; }
+            }
+            __syncthreads();
+
+            // stable in-warp ranking: entries of one digit are ranked in (item, lane) order
+            uint32_t rank[RS_ITEMS];
+#pragma unroll
+            for (int j = 0; j < RS_ITEMS; ++j) {
+                const uint32_t d = (k[j] >> shift) & 255u;
+                uint32_t peers, old;
+                if (MASK_TABLE) {
+                    // small (latency-bound) sorts: peers via a per-warp mask table in shared memory (the tables alias
+                    // s_vals / s_keys, unused until the scatter; even / odd items alternate tables so the clear of one
+                    // item never races the next item's ORs): one ATOMS.OR per lane, conflicts only among lanes sharing
+                    // the digit.  Measured on B200 (C3): -8 us on the depth sort vs MATCH.ANY.
+                    uint32_t* mm = ((j & 1) ? s_keys : s_vals) + warp * 256;
+                    atomicOr(&mm[d], 1u << lane);
+                    __syncwarp();
+                    peers = mm[d];
+                    old = s_whist[warp][d];               // every lane reads the running count itself (broadcast)
+                    __syncwarp();
+                    if (lane == 31 - __clz(peers)) { mm[d] = 0u; s_whist[warp][d] = old + __popc(peers); }
+                } else {
+                    // large (throughput-bound) sorts: MATCH.ANY (the mask table loses there: 232 vs 190 us at 6 M entries)
+                    peers = __match_any_sync(0xffffffffu, d);
+                    old = s_whist[warp][d];
+                    __syncwarp();
+                    if (lane == 31 - __clz(peers)) s_whist[warp][d] = old + __popc(peers);
+                    __syncwarp();
+                }
+                rank[j] = old + __popc(peers & lanemask_lt());
+            }
+            stamp_clk(tlt, 1);
+            __syncthreads();
+
+            const uint32_t tile_end = tile_base + RS_TILE;
+            const uint32_t pad = (tile_end > n) ? (tile_end - n) : 0u;
+            // threads 0..255 own one digit each: exclusive scan across warps, tile totals, look-back
+            uint32_t cnt = 0u, cnt_valid = 0u, incl = 0u, gh = 0u, gh_incl = 0u;
+            unsigned long long* my_status = status + (size_t)tile * 256 + (t & 255);
+            if (t < 256) {
+#pragma unroll 8
+                for (int w = 0; w < RS_WARPS; ++w) {
+                    const uint32_t c = s_whist[w][t];
+                    s_whist[w][t] = cnt;
+                    cnt += c;
+                }
+                cnt_valid = (t == 255) ? cnt - pad : cnt;   // padding is all digit 255
+                if (tile != 0) st_status(my_status, ep | ST_AGG | cnt_valid);   // published as early as possible
+                // tile-local exclusive scan over digits (padding included: it defines smem positions)
+                incl = cnt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += y;
+                }
+                // tile 0 seeds the chain with the exclusive scan of the global histogram
+                if (tile == 0) {
+                    gh = __ldcg(P.hist + p * 256 + t);
+                    gh_incl = gh;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const uint32_t y = __shfl_up_sync(0xffffffffu, gh_incl, o);
+                        if (lane >= o) gh_incl += y;
+                    }
+                }
+                if (lane == 31) { s_wtot[warp] = incl; s_wtot[8 + warp] = gh_incl; }
+            }
+            __syncthreads();
+            uint32_t binstart = 0u, excl = 0u;
+            if (t < 256) {
+                uint32_t wprefix = 0u, gp = 0u;
+                for (int w = 0; w < warp; ++w) { wprefix += s_wtot[w]; gp += s_wtot[8 + w]; }
+                binstart = wprefix + incl - cnt;
+                s_binstart[t] = binstart;
+                if (tile == 0) {
+                    excl = gp + gh_incl - gh;
+                    st_status(my_status, ep | ST_INC | (excl + cnt_valid));
+                }
+            }
+            __syncthreads();
+            stamp_clk(tlt, 2);
+
+            // scatter into tile-sorted order in shared memory (the predecessors' words arrive meanwhile; the mask
+            // tables aliasing s_keys / s_vals were last touched before the two barriers above)
+#pragma unroll
+            for (int j = 0; j < RS_ITEMS; ++j) {
+                const uint32_t d = (k[j] >> shift) & 255u;
+                const uint32_t i = my_base + j * 32;
+                const uint32_t pos = rank[j] + s_binstart[d] + s_whist[warp][d];
+                s_keys[pos] = k[j];
+                s_vals[pos] = (i < n) ? __ldcg(vals_in + i) : 0u;
+            }
+            stamp_clk(tlt, 3);
+
+            // decoupled look-back, one digit per thread
+            if (t < 256) {
+                if (tile != 0) {
+                    const unsigned long long* ps = my_status;
+                    uint32_t back = tile;
+                    bool found = false;
+                    while (!found) {
+                        unsigned long long w[LB_BATCH];
+#pragma unroll
+                        for (int q = 0; q < LB_BATCH; ++q)
+                            w[q] = ((uint32_t)q < back) ? ld_status(ps - 256 * (q + 1)) : (ep | ST_INC);
+#pragma unroll
+                        for (int q = 0; q < LB_BATCH; ++q) {
+                            if (!found) {
+                                unsigned long long x = w[q];
+                                while ((x >> 34) != (ep >> 34) || ((x >> 32) & 3ull) == 0ull) x = ld_status(ps - 256 * (q + 1));
+                                excl += (uint32_t)x;
+                                found = ((x >> 32) & 3ull) == 2ull;
+                            }
+                        }
+                        ps -= 256 * LB_BATCH;
+                        back = back > (uint32_t)LB_BATCH ? back - LB_BATCH : 0u;
+                    }
+                    st_status(my_status, ep | ST_INC | (excl + cnt_valid));
+                }
+                s_gbase[t] = excl - binstart;
+            }
+            __syncthreads();
+            stamp_clk(tlt, 4);
+
+            // coalesced write-out: consecutive positions of one digit land on consecutive addresses
+            const uint32_t valid = RS_TILE - pad;
+#pragma unroll 4
+            for (uint32_t q = t; q < valid; q += RS_THREADS) {
+                const uint32_t kk = s_keys[q];
+                const uint32_t dst = s_gbase[(kk >> shift) & 255u] + q;
+                keys_out[dst] = kk;
+                vals_out[dst] = s_vals[q];
+                if (emit_ranges) {
+                    // equal tile ids are contiguous in the tile (the input is sorted by the lower digits, the ranking is
+                    // stable) and in the output: each run's first / last element records the slice bounds
+                    if (q == 0u || s_keys[q - 1] != kk) atomicMax(&P.ranges[kk].x, ~dst);
+                    if (q == valid - 1u || s_keys[q + 1] != kk) atomicMax(&P.ranges[kk].y, dst + 1u);
+                }
+            }
+            stamp_clk(tlt, 5);
+            __syncthreads();
+        }
+        if (p + 1 < P.passes) {
+            bar_target += G;
+            grid_barrier(P.barrier, bar_target);
+        }
     }
 }
 
 // ---- host-side launch helpers ------------------------------------------------------------------
-// status rows are sized for the smallest tile so either variant fits
+// look-back status rows (tiles per pass) a sort of up to `capacity` entries may need: launch_radix_sort never picks
+// a tile smaller than capacity / rows entries
 uint32_t radix_num_tiles(uint32_t capacity) {
-    const uint32_t t = RS_THREADS * RS_ITEMS_MIN;
-    return (capacity + t - 1) / t;
+    const uint32_t need = capacity / (RS_THREADS * 16u) + 1u;
+    return need > 4096u ? need : 4096u;
 }
 
-void launch_radix_hist(const uint32_t* keys, const uint32_t* n_ptr, uint32_t capacity, int passes, uint32_t* hist,
-                       int sm_count, cudaStream_t stream) {
-    const uint32_t chunk = HS_THREADS * HS_ITEMS;
-    uint32_t blocks = (capacity + chunk - 1) / chunk;
-    const uint32_t cap_blocks = (uint32_t)sm_count * 4u;
-    if (blocks > cap_blocks) blocks = cap_blocks;
-    if (blocks == 0) blocks = 1;
-    radix_hist_kernel<<<blocks, HS_THREADS, 0, stream>>>(keys, n_ptr, passes, hist);
+namespace {
+template <int ITEMS, bool MASK>
+cudaError_t radix_launch_variant(const SortParams& P, uint32_t grid, cudaStream_t stream) {
+    static bool attr_set[64] = {};   // per device (the opt-in shared-memory size is a per-device function attribute)
+    const size_t smem = radix_smem_bytes(ITEMS);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(radix_coop_kernel<ITEMS, MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    }
+    SortParams p = P;
+    void* args[] = {(void*)&p};
+    return cudaLaunchCooperativeKernel((const void*)radix_coop_kernel<ITEMS, MASK>, dim3(grid), dim3(RS_THREADS), args, smem, stream);
+}
+}  // namespace
+
+// co-resident CTAs per SM of the largest variant (2 expected: 82 KB of shared memory, 64 registers x 512 threads)
+int radix_coop_blocks_per_sm(int) {
+    int b = 0;
+    if (cudaFuncSetAttribute(radix_coop_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)radix_smem_bytes(16)) != cudaSuccess) return 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, radix_coop_kernel<16, false>, RS_THREADS, radix_smem_bytes(16)) != cudaSuccess) return 0;
+    return b;
 }
 
-void launch_onesweep(const uint32_t* keys_in, const uint32_t* vals_in, uint32_t* keys_out, uint32_t* vals_out,
-                     const uint32_t* n_ptr, uint32_t capacity, uint32_t n_hint, const uint32_t* hist, uint32_t* status,
-                     uint32_t* tile_ctr, int shift, int sm_count, cudaStream_t stream, unsigned long long* tl) {
-    // n_hint (expected entry count, e.g. last frame's) only picks the tile size; correctness never depends on it
-    const bool small = n_hint <= (uint32_t)sm_count * 4u * (RS_THREADS * 16u);
-    const uint32_t tile = RS_THREADS * (small ? 8u : 16u);
-    uint32_t blocks = (capacity + tile - 1) / tile;
-    const uint32_t cap_blocks = (uint32_t)sm_count * 4u;   // persistent: blocks pull tiles from the ticket counter
-    if (blocks > cap_blocks) blocks = cap_blocks;
-    if (blocks == 0) blocks = 1;
-    if (small)
-        onesweep_kernel<8><<<blocks, RS_THREADS, 0, stream>>>(keys_in, vals_in, keys_out, vals_out, n_ptr, hist, status,
-                                                               tile_ctr, shift, tl);
-    else
-        onesweep_kernel<16><<<blocks, RS_THREADS, 0, stream>>>(keys_in, vals_in, keys_out, vals_out, n_ptr, hist, status,
-                                                                tile_ctr, shift, tl);
-}
-
-void launch_status_clear(uint32_t* status, size_t stride, int passes, const uint32_t* n_ptr, int sm_count, cudaStream_t stream) {
-    status_clear_kernel<<<sm_count * 2, 256, 0, stream>>>(status, stride, passes, n_ptr);
+// One stable LSD sort of *n_ptr (key, payload) entries on bits [shift0, shift0 + 8 * passes).  The result lands in
+// keys[passes & 1] / vals[passes & 1].  n_hint (expected entry count, e.g. last frame's) only picks the tile size and
+// the grid -- one wave of sm_count (or 2 x sm_count) fat CTAs covers the sort whenever the count allows; correctness
+// never depends on it.  `coop_per_sm` = radix_coop_blocks_per_sm().
+cudaError_t launch_radix_sort(uint32_t* keys0, uint32_t* vals0, uint32_t* keys1, uint32_t* vals1, const uint32_t* n_ptr,
+                              uint32_t capacity, uint32_t n_hint, uint32_t* hist, int compute_hist, void* status,
+                              size_t status_stride, uint32_t epoch, uint32_t* barrier, int passes, int shift0, uint2* ranges,
+                              int sm_count, int coop_per_sm, cudaStream_t stream, unsigned long long* tl) {
+    SortParams P;
+    P.keys[0] = keys0; P.keys[1] = keys1; P.vals[0] = vals0; P.vals[1] = vals1;
+    P.n_ptr = n_ptr; P.hist = hist; P.status = reinterpret_cast<unsigned long long*>(status); P.status_stride = status_stride;
+    P.epoch = epoch; P.barrier = barrier; P.passes = passes; P.shift0 = shift0; P.compute_hist = compute_hist;
+    P.ranges = ranges; P.tl = tl;
+    if (n_hint > capacity) n_hint = capacity;
+    // items per thread so that one wave of tiles covers the expected count with ~6 % head-room
+    const uint64_t want = (uint64_t)n_hint + n_hint / 16 + 1024;
+    uint32_t grid = (uint32_t)sm_count;
+    uint32_t items = (uint32_t)((want + (uint64_t)grid * RS_THREADS - 1) / ((uint64_t)grid * RS_THREADS));
+    if (items > 16 && coop_per_sm >= 2) {
+        grid = 2u * (uint32_t)sm_count;
+        items = (uint32_t)((want + (uint64_t)grid * RS_THREADS - 1) / ((uint64_t)grid * RS_THREADS));
+    }
+    // never more tiles than status rows, whatever the actual count turns out to be
+    const uint32_t rows = (uint32_t)(status_stride / 256);
+    const uint32_t min_items = (uint32_t)(((uint64_t)capacity + (uint64_t)rows * RS_THREADS - 1) / ((uint64_t)rows * RS_THREADS));
+    if (items < min_items) items = min_items;
+    if (items <= 2) return radix_launch_variant<2, true>(P, grid, stream);
+    if (items <= 4) return radix_launch_variant<4, true>(P, grid, stream);
+    if (items <= 6) return radix_launch_variant<6, true>(P, grid, stream);
+    if (items <= 8) return radix_launch_variant<8, true>(P, grid, stream);
+    if (items <= 10) return radix_launch_variant<10, true>(P, grid, stream);
+    if (items <= 12) return radix_launch_variant<12, true>(P, grid, stream);
+    if (items <= 16) return radix_launch_variant<16, true>(P, grid, stream);
+    return radix_launch_variant<16, false>(P, grid, stream);   // multi-wave (throughput-bound) sorts: MATCH.ANY ranking
 }
 
 }  // namespace bgs

@@ -110,7 +110,8 @@ raster_kernel(const SplatRec* __restrict__ recs, const float4* __restrict__ extr
     const float fx = (float)px + 0.5f, fy = (float)py + 0.5f;
     const float rcx = (float)wx0 + 4.0f, rcy = (float)wy0 + 2.0f;   // centre of the warp's pixel centres
     const float tcx = (float)(tile_x * TILE_PX) + 8.0f, tcy = (float)(tile_y * TILE_PX) + 8.0f;   // tile centre
-    const uint2 range = ranges[tile];
+    uint2 range = ranges[tile];
+    range.x = ~range.x;                  // stored as (~start, end): the sort's last pass builds it with atomicMax (radix.cu)
 
     const uint32_t a_ent = (uint32_t)__cvta_generic_to_shared(&s_ent[0][0]);
     const uint32_t a_bar = (uint32_t)__cvta_generic_to_shared(&s_bar[0]);
@@ -392,6 +393,7 @@ raster2_kernel(const SplatRec* __restrict__ recs, const uint32_t* __restrict__ t
     const bool in0 = px0 < W && py < H, in1 = px0 + 1 < W && py < H;
     const float fx0 = (float)px0 + 0.5f, fx1 = (float)px0 + 1.5f, fy = (float)py + 0.5f;
     uint2 range = ranges[tile];
+    range.x = ~range.x;                  // stored as (~start, end), (0, 0) = empty (radix.cu)
 
     // T < T_STOP <=> pixel done; lim = 1 while alive, -1 once done (folds the "alive" test into |u| <= lim)
     float T0 = in0 ? 1.0f : 0.0f, T1 = in1 ? 1.0f : 0.0f;
@@ -405,7 +407,7 @@ raster2_kernel(const SplatRec* __restrict__ recs, const uint32_t* __restrict__ t
         st = state + ((size_t)tile * R2_THREADS + t) * 2;
         if (!first) {
             const bool done = tile_done[tile] != 0;             // every pixel saturated in an earlier round
-            if (!last && (done || range.x == range.y)) return;  // nothing to blend, state unchanged
+            if (!last && (done || range.x >= range.y)) return;  // nothing to blend, state unchanged
             const float4 s0 = st[0], s1 = st[1];
             r0 = s0.x; g0 = s0.y; b0 = s0.z; T0 = s0.w;
             r1 = s1.x; g1 = s1.y; b1 = s1.z; T1 = s1.w;

@@ -42,11 +42,18 @@ def broadcast_unique_id(make_id, rank: int, root: int = 0) -> bytes:
 
 
 class MultiViewSession:
-    def __init__(self, rank: int, world: int, root: int = 0, plugin=None):
+    def __init__(self, rank: int, world: int, root: int = 0, plugin=None, share_comm_of: "MultiViewSession | None" = None):
+        """`share_comm_of`: reuse another session's NCCL communicator (the contexts of one rank -- frames in flight --
+        share ONE communicator; every rank issues its gathers in the same order, which is all NCCL asks for)."""
         self.rank, self.world, self.root, self.plugin = rank, world, root, plugin
         self._comm = C.c_void_p()
         self._lib = None
-        if plugin is not None:
+        self._owns_comm = True
+        if plugin is not None and share_comm_of is not None:
+            self._lib = plugin._lib
+            self._comm = share_comm_of._comm
+            self._owns_comm = False
+        elif plugin is not None:
             self._lib = plugin._lib
 
             def make_id():
@@ -83,6 +90,9 @@ class MultiViewSession:
         return None if out is None else np.stack([o.numpy() for o in out])
 
     def destroy(self):
+        if not self._owns_comm:
+            self._comm = C.c_void_p()
+            return
         if self._comm and self._lib is not None:
             self._lib.bgs_nccl_comm_destroy(self._comm)
             self._comm = C.c_void_p()

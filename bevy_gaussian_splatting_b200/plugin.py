@@ -186,6 +186,10 @@ class GaussianSplattingPlugin:
         return int(self._lib.bgs_context_stream(self._ctx) or 0)
 
     @property
+    def copy_stream_ptr(self) -> int:
+        return int(self._lib.bgs_context_copy_stream(self._ctx) or 0)
+
+    @property
     def frame_device_ptr(self) -> int:
         return int(self._lib.bgs_frame_device_ptr(self._ctx) or 0)
 

@@ -147,6 +147,9 @@ bgs_status bgs_stage_times_us(bgs_context* ctx, float out[6]);
 const char* bgs_last_error(const bgs_context* ctx);
 /* The CUDA stream (cudaStream_t) all of this context's work is launched on. */
 void* bgs_context_stream(bgs_context* ctx);
+/* The copy/comm stream (cudaStream_t): async frames delivered to host memory or gathered over NCCL are consumed here,
+ * so device-side timing of a multi-frame window must cover this stream as well as the render stream. */
+void* bgs_context_copy_stream(bgs_context* ctx);
 /* Device pointer of the last frame in `out_format` layout (valid until the next render). */
 const void* bgs_frame_device_ptr(bgs_context* ctx);
 /* Kernel launches issued by the last bgs_render. */

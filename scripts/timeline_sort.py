@@ -11,10 +11,12 @@ for _ in range(5): pl.render_view(h, s, v, fmt="rgba8_srgb", to_host=False)
 buf = np.zeros((4096, 8), np.uint64); g = C.c_uint32()
 lib = pl._lib; lib.bgs_debug_timeline_.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32)]
 lib.bgs_debug_timeline_(pl._ctx, buf.ctypes.data_as(C.c_void_p), C.byref(g))
-nt = (721340 + 2047) // 2048
-t = buf[:nt, :5].astype(np.int64); t = (t - t[:, :1]) / 1965.0   # clock64 cycles -> us at 1.965 GHz, per-tile origin
-for i, nm in enumerate(["tile start", "ranked", "pre-lookback", "post-lookback", "written"]):
-    col = t[:, i]; print(f"{nm:14s} min {col.min():7.1f} median {np.median(col):7.1f} max {col.max():7.1f} us")
+nt = int((buf[:, 0] != 0).sum())
+print("tiles stamped:", nt)
+t = buf[:nt, :6].astype(np.int64); t = (t - t[:, :1]) / 1965.0   # clock64 cycles -> us at 1.965 GHz, per-tile origin
+names = ["tile start", "ranked", "scanned", "smem scatter", "post-lookback", "written"]
+for i, nm in enumerate(names):
+    col = t[:, i]; print(f"{nm:14s} min {col.min():7.2f} median {np.median(col):7.2f} max {col.max():7.2f} us")
 print("per-phase medians:", np.median(np.diff(t, axis=1), axis=0).round(2))
-print("look-back duration by tile idx (every 32):", (t[::32, 3] - t[::32, 2]).round(1))
+print("look-back duration by tile idx (every 16):", (t[::16, 4] - t[::16, 3]).round(2))
 print(pl.stage_times_us())
