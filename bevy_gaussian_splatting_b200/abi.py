@@ -20,6 +20,8 @@ BGS_FLAG_SORT_ALL = 1
 BGS_FLAG_ASYNC = 2
 BGS_FLAG_NO_CHUNKS = 4
 BGS_FLAG_CHUNKS = 8
+BGS_FLAG_PREMULTIPLIED_OUT = 16
+BGS_FLAG_BLEND_OVER_TARGET = 32
 
 
 class bgs_view(C.Structure):

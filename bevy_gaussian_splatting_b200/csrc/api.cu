@@ -19,9 +19,9 @@ void launch_keygen(const float4* pos, uint32_t n, const FrameConsts& fc, int sor
                    uint32_t* ids_out, uint32_t* slots_out, uint32_t* status, FrameCounters* ctr, cudaStream_t stream);
 uint32_t keygen_num_tiles(uint32_t n);
 int keygen_coop_blocks_per_sm();
-cudaError_t launch_keygen_coop(const float4* pos, uint32_t n, const FrameConsts& fc, uint32_t* keys_tmp, uint32_t* keys_out,
+cudaError_t launch_keygen_coop(const float4* pos, uint32_t n, const FrameConsts& fc, uint32_t* masks, uint32_t* keys_out,
                                uint32_t* ids_out, uint32_t* slots_out, uint32_t* block_cnt, FrameCounters* ctr,
-                               uint32_t* hist, int hist_passes, uint32_t grid, cudaStream_t stream);
+                               uint32_t* hist, int hist_passes, uint32_t grid, unsigned long long* tl, cudaStream_t stream);
 void launch_culled_flags(const float4* pos, uint32_t n, const FrameConsts& fc, uint32_t* flags, cudaStream_t stream);
 // radix.cu
 uint32_t radix_num_tiles(uint32_t capacity);
@@ -78,11 +78,19 @@ struct bgs_context {
     int device = 0;
     int sm_count = 148;
     int coop = 0;                 // device supports cooperative launch
-    uint32_t kg_grid = 0, bin_grid = 0;   // co-resident grid sizes of the cooperative kernels
+    uint32_t kg_grid = 0, bin_grid = 0;   // co-resident grid sizes of the cooperative kernels (synchronous frames: latency)
+    uint32_t kg_grid_async = 0, bin_grid_async = 0;   // ... of queued (BGS_FLAG_ASYNC) frames: 2 CTAs per SM.  A latency-bound
+                                          // cooperative grid holds its registers while it waits; with several frames in flight
+                                          // a smaller grid leaves that room to the other frames' issue-bound blend
+                                          // (measured at C3, 3 contexts: 0.333 -> 0.309 ms per frame, profiles/r2_experiments.md)
     int rs_per_sm = 0;                    // co-resident radix-sort CTAs per SM (radix.cu)
     uint32_t sort_epoch = 0;              // look-back status epoch: +1 per sort launch (status words never need clearing)
     cudaStream_t stream = nullptr;    // render stream (high priority): everything but the projection
     cudaStream_t stream2 = nullptr;   // projection runs here, beside the depth sort
+    cudaStream_t stream_r = nullptr;  // LOW priority: the tile blend of one-round frames.  With several contexts in flight the
+                                      // latency-bound front of the next frame (high priority, cooperative grids) takes SMs as
+                                      // the previous frame's short-lived raster CTAs retire, instead of queueing behind them
+    cudaEvent_t ev_front = nullptr, ev_rdone = nullptr;
     cudaEvent_t ev[6] = {};
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_p0 = nullptr, ev_p1 = nullptr;
     unsigned long long* timeline = nullptr;   // BGS_TIMELINE=1: per-CTA phase stamps of bin_emit_coop (debug)
@@ -207,8 +215,9 @@ bgs_status ensure_cloud_scratch(bgs_context* c, uint32_t n) {
     cudaFree(c->slot_ids); c->slot_ids = nullptr;
     c->cap_n = 0;
     for (int i = 0; i < 2; ++i) {
-        CU(c, cudaMalloc(&c->keys[i], (size_t)n * 4));
-        CU(c, cudaMalloc(&c->vals[i], (size_t)n * 4));
+        // (>= 1024 words: keys[1] doubles as key-gen's visibility-mask scratch, one word per 32 gaussians rounded up to a tile)
+        CU(c, cudaMalloc(&c->keys[i], (size_t)(n < 1024u ? 1024u : n) * 4));
+        CU(c, cudaMalloc(&c->vals[i], (size_t)(n < 1024u ? 1024u : n) * 4));
     }
     CU(c, cudaMalloc(&c->slot_ids, (size_t)n * 4));
     CU(c, cudaMalloc(&c->recs, (size_t)n * sizeof(SplatRec)));
@@ -295,6 +304,8 @@ bgs_status ensure_frame(bgs_context* c, size_t bytes) {
     cudaFree(c->frame); cudaFree(c->frame_alt); c->frame = c->frame_alt = nullptr; c->frame_bytes = 0;
     CU(c, cudaMalloc(&c->frame, bytes));
     CU(c, cudaMalloc(&c->frame_alt, bytes));
+    CU(c, cudaMemsetAsync(c->frame, 0, bytes, c->stream));       // (BGS_FLAG_BLEND_OVER_TARGET reads the target)
+    CU(c, cudaMemsetAsync(c->frame_alt, 0, bytes, c->stream));
     c->frame_bytes = bytes;
     c->copy_pending[0] = c->copy_pending[1] = false;
     return BGS_OK;
@@ -316,7 +327,10 @@ bgs_status bgs_context_create(int cuda_device, bgs_context** out) {
     int prio_lo = 0, prio_hi = 0;
     if (e == cudaSuccess) e = cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
     if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_hi);
-    if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, prio_lo);
+    if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, (prio_lo + prio_hi) / 2);
+    if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&c->stream_r, cudaStreamNonBlocking, prio_lo);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_front, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_rdone, cudaEventDisableTiming);
     for (int i = 0; i < 6 && e == cudaSuccess; ++i) e = cudaEventCreate(&c->ev[i]);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
@@ -344,6 +358,11 @@ bgs_status bgs_context_create(int cuda_device, bgs_context** out) {
         if (const char* e = getenv("BGS_COOP_BLOCKS")) lim = atoi(e) > 0 ? atoi(e) : 4;   // second context's kernels)
         c->kg_grid = (uint32_t)(c->sm_count * (kb > lim ? lim : kb));
         c->bin_grid = (uint32_t)(c->sm_count * (bb > lim ? lim : bb));
+        int lim_a = 2;
+        if (const char* e = getenv("BGS_COOP_BLOCKS_ASYNC")) lim_a = atoi(e) > 0 ? atoi(e) : 2;
+        if (lim_a > lim) lim_a = lim;
+        c->kg_grid_async = (uint32_t)(c->sm_count * (kb > lim_a ? lim_a : kb));
+        c->bin_grid_async = (uint32_t)(c->sm_count * (bb > lim_a ? lim_a : bb));
         c->rs_per_sm = radix_coop_blocks_per_sm(16);
         if (c->kg_grid == 0 || c->bin_grid == 0 || c->kg_grid > 4096 || c->bin_grid > 4096 || c->rs_per_sm == 0) c->coop = 0;
     }
@@ -389,6 +408,9 @@ void bgs_context_destroy(bgs_context* c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->stream2) cudaStreamSynchronize(c->stream2);
+    if (c->stream_r) { cudaStreamSynchronize(c->stream_r); cudaStreamDestroy(c->stream_r); }
+    if (c->ev_front) cudaEventDestroy(c->ev_front);
+    if (c->ev_rdone) cudaEventDestroy(c->ev_rdone);
     if (c->stream_copy) { cudaStreamSynchronize(c->stream_copy); cudaStreamDestroy(c->stream_copy); }
     for (int i = 0; i < 2; ++i) { if (c->ev_raster[i]) cudaEventDestroy(c->ev_raster[i]); if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]); }
     cudaFree(c->frame_alt);
@@ -478,6 +500,7 @@ void bgs_cloud_destroy(bgs_cloud* cl) {
                 if (c->async_pending || c->pend_cloud == cl) {
                     cudaStreamSynchronize(c->stream);
                     cudaStreamSynchronize(c->stream2);
+                    cudaStreamSynchronize(c->stream_r);
                     cudaStreamSynchronize(c->stream_copy);
                 }
                 if (c->pend_cloud == cl) { c->pend_cloud = nullptr; c->pend_n = 0; }
@@ -642,9 +665,13 @@ bgs_status bgs_render(bgs_context* c, const bgs_cloud* cloud, const bgs_view* vi
     // frame k off the render stream (the D2H copy, the NCCL gather: both on the copy/comm stream) overlaps frame k+1
     const bool async_own = (st->flags & BGS_FLAG_ASYNC) && !(out_rgba && out_is_device_ptr);
     const bool async_host = async_own && out_rgba;
+    // output mode of the blend kernels: format | mode << 8 (raster.cu)
+    const bool blend_over = (st->flags & BGS_FLAG_BLEND_OVER_TARGET) != 0;
+    const uint32_t raster_format = out_format | ((blend_over ? 2u : ((st->flags & BGS_FLAG_PREMULTIPLIED_OUT) ? 1u : 0u)) << 8);
     int fslot = 0;
     if (async_own) {
-        fslot = c->frame_toggle; c->frame_toggle ^= 1;
+        if (blend_over) fslot = c->frame_toggle ^ 1;            // keep blending into the frame the previous call produced
+        else { fslot = c->frame_toggle; c->frame_toggle ^= 1; }
         target = fslot ? c->frame_alt : c->frame;
     }
 
@@ -679,8 +706,10 @@ bgs_status bgs_render(bgs_context* c, const bgs_cloud* cloud, const bgs_view* vi
         bool hist_fused = false;   // the cooperative key-gen also produces the depth sort's digit histograms
         if (!sort_all && c->coop) {
             // cooperative: uncompacted keys go through keys[1] (scratch until the first sort pass overwrites it)
+            // (keys[1] = visibility-mask scratch until the sort's first pass overwrites it)
             CU(c, launch_keygen_coop(cloud->pos, n, fc, c->keys[1], c->keys[0], c->slot_ids, c->vals[0], c->status_keygen,
-                                     c->ctr, c->hist, depth_passes, c->kg_grid, q));
+                                     c->ctr, c->hist, depth_passes, (st->flags & BGS_FLAG_ASYNC) ? c->kg_grid_async : c->kg_grid,
+                                     (c->timeline && getenv("BGS_TIMELINE_KEYGEN")) ? c->timeline : nullptr, q));
             hist_fused = true;
         } else {
             launch_keygen(cloud->pos, n, fc, sort_all ? 1 : 0, c->keys[0], sort_all ? c->vals[0] : c->slot_ids,
@@ -745,7 +774,8 @@ bgs_status bgs_render(bgs_context* c, const bgs_cloud* cloud, const bgs_view* vi
                 // the depth sort's spare ping-pong buffers (N words each) hold the large-footprint queue
                 CU(c, launch_bin_emit_coop(c->recs, by_slot ? c->vals[cur] : nullptr, c->ctr, cc, fa, fb, num_tiles,
                                            c->status_bin, tiles_x, c->cap_pairs, c->pkeys[0], c->pvals[0], c->keys[cur ^ 1],
-                                           c->vals[cur ^ 1], c->cap_n, getenv("BGS_TIMELINE_SORT") ? nullptr : c->timeline, c->bin_grid, c->d_sticky, q));
+                                           c->vals[cur ^ 1], c->cap_n, (getenv("BGS_TIMELINE_SORT") || getenv("BGS_TIMELINE_KEYGEN")) ? nullptr : c->timeline,
+                                           (st->flags & BGS_FLAG_ASYNC) ? c->bin_grid_async : c->bin_grid, c->d_sticky, q));
             } else {
                 launch_bin_emit(c->recs, by_slot ? c->vals[cur] : nullptr, c->ctr, cc, c->status_bin, tiles_x, c->cap_pairs,
                                 c->pkeys[0], c->pvals[0], n, c->sm_count, c->d_sticky, q);
@@ -766,10 +796,16 @@ bgs_status bgs_render(bgs_context* c, const bgs_cloud* cloud, const bgs_view* vi
                 CU(c, cudaEventRecord(c->ev[4], q));
                 if (async_own && c->copy_pending[fslot]) CU(c, cudaStreamWaitEvent(q, c->ev_copied[fslot], 0));   // target free again
             }
-            if (rounds == 1)
-                launch_raster(raster_mode, large_fp, c->recs, c->extra, c->pvals[pcur], rng, W, H, tiles_x, tiles_y, target, out_format, q);
-            else
-                launch_raster_round(c->recs, c->pvals[pcur], rng, W, H, tiles_x, tiles_y, target, out_format, c->state,
+            if (rounds == 1) {
+                // the blend runs on the LOW-priority stream; the render stream resumes once it is done
+                static int split = -1;
+                if (split < 0) { const char* e = getenv("BGS_RASTER_PRIO"); split = (e && atoi(e) == 0) ? 0 : 1; }
+                cudaStream_t qr = split ? c->stream_r : q;
+                if (split) { CU(c, cudaEventRecord(c->ev_front, q)); CU(c, cudaStreamWaitEvent(qr, c->ev_front, 0)); }
+                launch_raster(raster_mode, large_fp, c->recs, c->extra, c->pvals[pcur], rng, W, H, tiles_x, tiles_y, target, raster_format, qr);
+                if (split) { CU(c, cudaEventRecord(c->ev_rdone, qr)); CU(c, cudaStreamWaitEvent(q, c->ev_rdone, 0)); }
+            } else
+                launch_raster_round(c->recs, c->pvals[pcur], rng, W, H, tiles_x, tiles_y, target, raster_format, c->state,
                                     c->tile_done, &c->ctr->tiles_done, r == 0, r + 1 == rounds, q);
             ++launches;
         }

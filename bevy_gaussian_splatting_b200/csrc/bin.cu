@@ -185,24 +185,33 @@ bin_emit_coop_kernel(const SplatRec* __restrict__ recs, const uint32_t* __restri
     const uint32_t sub = BIN_THREADS * ipt;
     const bool single = rhi - rlo <= sub;     // one sub-tile: phase 2 reuses phase 1's registers
 
-    auto tiles_of = [&](uint32_t r, uint32_t& bx, uint32_t& by, uint32_t& ri) -> uint32_t {
-        if (r >= rhi) return 0u;
-        ri = perm ? __ldg(perm + (n_vis - 1u - r)) : r;   // rank -> record index
-        const uint2 bb = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const char*>(recs + ri) + 24));
-        bx = bb.x; by = bb.y;
-        const uint32_t xlo = bb.x & 0xFFFFu, xhi = bb.x >> 16, ylo = bb.y & 0xFFFFu, yhi = bb.y >> 16;
-        if (xlo <= xhi && ylo <= yhi) return ((xhi >> 4) - (xlo >> 4) + 1u) * ((yhi >> 4) - (ylo >> 4) + 1u);
-        return 0u;
+    // the bboxes of this thread's ranks [r0, r0 + ipt): all rank -> record-index loads first, then all bbox loads
+    // (two dependent L2 round trips for the whole batch instead of two per splat)
+    uint32_t bx[COOP_ITEMS], by[COOP_ITEMS], cnt[COOP_ITEMS], ri[COOP_ITEMS];
+    auto load_items = [&](uint32_t r0) {
+#pragma unroll
+        for (int j = 0; j < COOP_ITEMS; ++j) {
+            const uint32_t r = r0 + j;
+            const bool ok = (uint32_t)j < ipt && r < rhi;
+            ri[j] = ok ? (perm ? __ldg(perm + (n_vis - 1u - r)) : r) : 0xFFFFFFFFu;   // rank -> record index
+        }
+#pragma unroll
+        for (int j = 0; j < COOP_ITEMS; ++j) {
+            uint2 bb = make_uint2(1u, 1u);                                             // (empty bbox: lo = 1 > hi = 0)
+            if (ri[j] != 0xFFFFFFFFu) bb = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const char*>(recs + ri[j]) + 24));
+            bx[j] = bb.x; by[j] = bb.y;
+            const uint32_t xlo = bb.x & 0xFFFFu, xhi = bb.x >> 16, ylo = bb.y & 0xFFFFu, yhi = bb.y >> 16;
+            cnt[j] = (xlo <= xhi && ylo <= yhi) ? ((xhi >> 4) - (xlo >> 4) + 1u) * ((yhi >> 4) - (ylo >> 4) + 1u) : 0u;
+            if (ri[j] == 0xFFFFFFFFu) ri[j] = 0u;
+        }
     };
 
     // ---- phase 1
-    uint32_t bx[COOP_ITEMS], by[COOP_ITEMS], cnt[COOP_ITEMS], ri[COOP_ITEMS];
     uint32_t mine = 0u, mmed = 0u, mbig = 0u;
     for (uint32_t base = rlo; base < rhi; base += sub) {
+        load_items(base + t * ipt);
 #pragma unroll
         for (int j = 0; j < COOP_ITEMS; ++j) {
-            bx[j] = 0u; by[j] = 0u; ri[j] = 0u;
-            cnt[j] = ((uint32_t)j < ipt) ? tiles_of(base + t * ipt + j, bx[j], by[j], ri[j]) : 0u;
             mine += cnt[j];
             mmed += (cnt[j] > BIN_TINY && cnt[j] <= BIN_BIG) ? 1u : 0u;
             mbig += cnt[j] > BIN_BIG ? 1u : 0u;
@@ -243,12 +252,9 @@ bin_emit_coop_kernel(const SplatRec* __restrict__ recs, const uint32_t* __restri
     for (uint32_t base = rlo; base < rhi; base += sub) {
         const uint32_t r0 = base + t * ipt;
         uint32_t tmine = 0u, nbig = 0u, nmed = 0u;
+        if (!single) load_items(r0);
 #pragma unroll
         for (int j = 0; j < COOP_ITEMS; ++j) {
-            if (!single) {
-                bx[j] = 0u; by[j] = 0u; ri[j] = 0u;
-                cnt[j] = ((uint32_t)j < ipt) ? tiles_of(r0 + j, bx[j], by[j], ri[j]) : 0u;
-            }
             tmine += cnt[j];
             nbig += cnt[j] > BIN_BIG ? 1u : 0u;
             nmed += (cnt[j] > BIN_TINY && cnt[j] <= BIN_BIG) ? 1u : 0u;
@@ -307,7 +313,9 @@ bin_emit_coop_kernel(const SplatRec* __restrict__ recs, const uint32_t* __restri
 
     // ---- phase 3a: medium footprints, 32 per warp: each lane fetches one splat's (record, offset, bbox)
     //      so the memory latency is paid once per 32 splats; then the warp writes them one after another
-    const uint32_t gwarp = b * (BIN_THREADS / 32) + warp, total_warps = G * (BIN_THREADS / 32);
+    // warp w of CTA b is global warp w * G + b: consecutive batches (the queues are in rank order, so the first ones hold
+    // the nearest = largest footprints) land on different CTAs / SMs
+    const uint32_t gwarp = (uint32_t)warp * G + b, total_warps = G * (BIN_THREADS / 32);
     const uint32_t nm = ld_volatile(&cc->med_count);
     for (uint32_t mb = gwarp * 32u; mb < nm; mb += total_warps * 32u) {
         const uint32_t i = mb + lane;

@@ -117,7 +117,9 @@ keygen_compact_kernel(const float4* __restrict__ pos, uint32_t n, FrameConsts fc
 //           element e of the CTA (found by binary search over the word prefix + select-nth-bit) re-reads its position
 //           (L2 / 32 B sectors, visible ones only), computes the key and writes (key, index, slot) at run + e --
 //           fully coalesced, in index order, so the stable LSD sort sees the reference's tie order.
-//           The depth sort's digit histograms are accumulated on the way (shared-memory atomics, visible keys only).
+//           The depth sort's digit histograms are accumulated on the way (shared-memory atomics, visible keys only:
+//           at ~2 cycles per lane-atomic they are most of this phase's ~12 us -- measured with and without the
+//           position re-read, with thread-per-element and thread-per-word expansions, profiles/r2_experiments.md).
 constexpr int KG_WORDS_PER_TILE = KG_TILE / 32;    // 64 mask words
 constexpr int KG_CHUNK_WORDS = 1024;               // phase 2 expands 1024 words (32 K gaussians) at a time
 
@@ -125,7 +127,8 @@ __global__ void __launch_bounds__(KG_THREADS)
 keygen_coop_kernel(const float4* __restrict__ pos, uint32_t n, FrameConsts fc, uint32_t* __restrict__ masks,
                    uint32_t* __restrict__ keys_out, uint32_t* __restrict__ ids_out, uint32_t* __restrict__ slots_out,
                    uint32_t* __restrict__ block_cnt, FrameCounters* __restrict__ ctr, uint32_t* __restrict__ hist,
-                   int hist_passes) {
+                   int hist_passes, unsigned long long* __restrict__ tl) {
+    timeline_stamp(tl, 0);
     __shared__ uint32_t s_hist[4 * 256];   // digit histograms of the visible keys (the depth sort's pre-pass, fused)
     __shared__ uint32_t s_red[KG_THREADS / 32];
     __shared__ uint32_t s_total;
@@ -177,12 +180,15 @@ keygen_coop_kernel(const float4* __restrict__ pos, uint32_t n, FrameConsts fc, u
         s_total = tot;
         st_volatile(block_cnt + b, tot);
     }
+    timeline_stamp(tl, 1);
     grid_barrier(&ctr->barrier[0], G);
+    timeline_stamp(tl, 2);
 
     // ---- phase 2: exclusive prefix over CTAs, then ordered expansion of this CTA's mask words
     for (int i = t; i < hist_passes * 256; i += KG_THREADS) s_hist[i] = 0u;
     uint32_t run = block_sum_prefix<KG_THREADS>(block_cnt, b, s_red);
     if (b == G - 1 && t == 0) { ctr->n_vis = run + s_total; ctr->n_sort = run + s_total; }
+    timeline_stamp(tl, 3);
     const uint32_t w_begin = t0 * KG_WORDS_PER_TILE, w_end = t1 * KG_WORDS_PER_TILE;
     for (uint32_t wc = w_begin; wc < w_end; wc += KG_CHUNK_WORDS) {
         const uint32_t cw = min((uint32_t)KG_CHUNK_WORDS, w_end - wc);
@@ -241,10 +247,12 @@ keygen_coop_kernel(const float4* __restrict__ pos, uint32_t n, FrameConsts fc, u
         run += chunk_total;
         __syncthreads();
     }
+    timeline_stamp(tl, 4);
     for (int i = t; i < hist_passes * 256; i += KG_THREADS) {
         const uint32_t c = s_hist[i];
         if (c) atomicAdd(&hist[i], c);
     }
+    timeline_stamp(tl, 5);
 }
 
 // Debug hook: rebuild the reference's full sorted_entry_buffer (sort/mod.rs:323-329) from the
@@ -272,10 +280,10 @@ int keygen_coop_blocks_per_sm() {
 }
 cudaError_t launch_keygen_coop(const float4* pos, uint32_t n, const FrameConsts& fc, uint32_t* masks, uint32_t* keys_out,
                                uint32_t* ids_out, uint32_t* slots_out, uint32_t* block_cnt, FrameCounters* ctr,
-                               uint32_t* hist, int hist_passes, uint32_t grid, cudaStream_t stream) {
+                               uint32_t* hist, int hist_passes, uint32_t grid, unsigned long long* tl, cudaStream_t stream) {
     FrameConsts fcc = fc;
     void* args[] = {(void*)&pos, (void*)&n, (void*)&fcc, (void*)&masks, (void*)&keys_out, (void*)&ids_out,
-                    (void*)&slots_out, (void*)&block_cnt, (void*)&ctr, (void*)&hist, (void*)&hist_passes};
+                    (void*)&slots_out, (void*)&block_cnt, (void*)&ctr, (void*)&hist, (void*)&hist_passes, (void*)&tl};
     return cudaLaunchCooperativeKernel((const void*)keygen_coop_kernel, dim3(grid), dim3(KG_THREADS), args, 0, stream);
 }
 

@@ -9,6 +9,8 @@
 // Geometry (centre, OBB uv rows, pixel bbox) is bit-exact vs the oracle: compiled -fmad=false.
 #include <cuda_fp16.h>
 
+#include <cstdlib>
+
 #include "project_math.cuh"
 
 namespace bgs {
@@ -64,7 +66,7 @@ struct Attr;
 template <>
 struct Attr<false, true> {
     __device__ static float4 load(const float4*, const void* blocks, const void*, const void*, uint32_t id, float* sh,
-                                  float q[4], float so[4], bool need_sh) {
+                                  float q[4], float so[4], bool need_sh, uint32_t* = nullptr) {
         const float4* b = reinterpret_cast<const float4*>(blocks) + (size_t)id * 16;
         const float4 p = __ldg(b), r = __ldg(b + 1), s = __ldg(b + 2);
         q[0] = r.x; q[1] = r.y; q[2] = r.z; q[3] = r.w;
@@ -84,9 +86,10 @@ struct Attr<true, true> {
     __device__ static float lo(uint32_t w) { return __half2float(__ushort_as_half((unsigned short)(w & 0xFFFFu))); }
     __device__ static float hi(uint32_t w) { return __half2float(__ushort_as_half((unsigned short)(w >> 16))); }
     __device__ static float4 load(const float4*, const void* blocks, const void*, const void*, uint32_t id, float* sh,
-                                  float q[4], float so[4], bool need_sh) {
+                                  float q[4], float so[4], bool need_sh, uint32_t* op_bits = nullptr) {
         const uint4* b = reinterpret_cast<const uint4*>(blocks) + (size_t)id * 8;
         const uint4 pw = __ldg(b), w = __ldg(b + 1);
+        if (op_bits) *op_bits = w.w & 0xFFFFu;
         q[0] = hi(w.x); q[1] = lo(w.x); q[2] = hi(w.y); q[3] = lo(w.y);
         so[0] = hi(w.z); so[1] = lo(w.z); so[2] = hi(w.w); so[3] = lo(w.w);
         if (need_sh) {
@@ -103,7 +106,7 @@ struct Attr<true, true> {
 template <>
 struct Attr<false, false> {   // f32 planes: src/gaussian/f32.rs:53-175, planar.wgsl:334-364
     __device__ static float4 load(const float4* pos, const void* sh_p, const void* rot_p, const void* so_p, uint32_t id,
-                                  float* sh, float q[4], float so[4], bool need_sh) {
+                                  float* sh, float q[4], float so[4], bool need_sh, uint32_t* = nullptr) {
         const float4 p = __ldg(pos + id);
         const float4 r = __ldg(reinterpret_cast<const float4*>(rot_p) + id);
         const float4 s = __ldg(reinterpret_cast<const float4*>(so_p) + id);
@@ -125,9 +128,10 @@ struct Attr<true, false> {    // f16 planes: src/gaussian/f16.rs:30-56,244-263; 
     __device__ static float lo(uint32_t w) { return __half2float(__ushort_as_half((unsigned short)(w & 0xFFFFu))); }
     __device__ static float hi(uint32_t w) { return __half2float(__ushort_as_half((unsigned short)(w >> 16))); }
     __device__ static float4 load(const float4* pos, const void* sh_p, const void* rso_p, const void*, uint32_t id, float* sh,
-                                  float q[4], float so[4], bool need_sh) {
+                                  float q[4], float so[4], bool need_sh, uint32_t* op_bits = nullptr) {
         const float4 p = __ldg(pos + id);
         const uint4 w = __ldg(reinterpret_cast<const uint4*>(rso_p) + id);
+        if (op_bits) *op_bits = w.w & 0xFFFFu;
         q[0] = hi(w.x); q[1] = lo(w.x); q[2] = hi(w.y); q[3] = lo(w.y);
         so[0] = hi(w.z); so[1] = lo(w.z); so[2] = hi(w.w); so[3] = lo(w.w);
         if (need_sh) {
@@ -502,7 +506,7 @@ __global__ void __launch_bounds__(128, 6)
 project_kernel(const float4* __restrict__ pos, const void* __restrict__ sh_p, const void* __restrict__ rot_p,
                const void* __restrict__ so_p, const uint32_t* __restrict__ index_list, int by_slot,
                const FrameCounters* __restrict__ ctr, FrameConsts fc, SplatRec* __restrict__ recs,
-               float4* __restrict__ extra /* 4 x float4 per record, 2DGS + USE_AABB only */) {
+               float4* __restrict__ extra /* 4 x float4 per record, 2DGS + USE_AABB only */, const float* __restrict__ cutoff_tab) {
     const uint32_t n_vis = ctr->n_vis;
     for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n_vis; r += gridDim.x * blockDim.x) {
         // by_slot: r is a compact slot (ascending gaussian index; runs concurrently with the depth sort)
@@ -510,8 +514,11 @@ project_kernel(const float4* __restrict__ pos, const void* __restrict__ sh_p, co
         const uint32_t id = by_slot ? __ldg(index_list + r) : __ldg(index_list + (n_vis - 1u - r));
         float sh[48], q[4], so[4];
         const bool need_sh = fc.rasterize_mode == BGS_RASTERIZE_COLOR;
-        const float4 p4 = Attr<F16, BLOCKED>::load(pos, sh_p, rot_p, so_p, id, sh, q, so, need_sh);
-        project_one(fc, ctr, r, p4, q, so, __uint_as_float(0x7FC00000u),
+        uint32_t op_bits = 0u;
+        const float4 p4 = Attr<F16, BLOCKED>::load(pos, sh_p, rot_p, so_p, id, sh, q, so, need_sh, &op_bits);
+        // f16 clouds: the adaptive cutoff of this 16-bit opacity comes from the per-context table (bit-identical)
+        const float cutoff_pre = (F16 && fc.adaptive) ? __ldg(cutoff_tab + op_bits) : __uint_as_float(0x7FC00000u);
+        project_one(fc, ctr, r, p4, q, so, cutoff_pre,
                     [&](float* out) {
 #pragma unroll
                         for (int i = 0; i < 48; ++i) out[i] = sh[i];
@@ -653,7 +660,11 @@ void launch_project(bool f16, bool blocked, const float4* pos, const void* sh, c
                     const uint32_t* index_list, int by_slot, const FrameCounters* ctr, const FrameConsts& fc,
                     SplatRec* recs, float4* extra, uint32_t n_hint, int sm_count, int ctas_per_sm, const float* cutoff_tab,
                     cudaStream_t stream) {
-    if (blocked) {
+    static int use_ring = -1;
+    if (use_ring < 0) { const char* e = getenv("BGS_PROJECT_RING"); use_ring = (e && atoi(e) > 0) ? 1 : 0; }
+    if (blocked && use_ring) {
+        // (measured slower on B200 -- one UBLKCP per 128 B row sustains ~1 copy / 20 cycles / SM: 48 us vs 36 us for
+        // the per-thread gather at C3 -- kept behind BGS_PROJECT_RING=1 as the evidence, profiles/r2_experiments.md)
         // TMA ring over the gaussian-major blocks (`sh` carries the block array): a persistent grid of at most
         // ctas_per_sm CTAs per SM (2 when a depth sort shares the SMs, else the occupancy limit)
         static bool attr_set[64] = {};
@@ -674,13 +685,21 @@ void launch_project(bool f16, bool blocked, const float4* pos, const void* sh, c
         else project_ring_kernel<false><<<blocks, PR_THREADS, Ring<false>::SMEM, stream>>>(sh, index_list, by_slot, ctr, fc, recs, extra, cutoff_tab);
         return;
     }
-    // planar planes (BGS_LAYOUT=planar): per-thread gather.  Grid sized from a hint (last frame's visible count +
+    // per-thread gather (gaussian-major blocks by default, the reference's planes with BGS_LAYOUT=planar).  Grid sized from a hint (last frame's visible count +
     // head-room); the grid-stride loop keeps any n_vis correct.
     uint32_t blocks = (n_hint + 127) / 128;
     if (blocks > 65535u * 8u) blocks = 65535u * 8u;
     if (blocks < 148u) blocks = 148u;
-    if (f16) project_kernel<true, false><<<blocks, 128, 0, stream>>>(pos, sh, rot, so, index_list, by_slot, ctr, fc, recs, extra);
-    else project_kernel<false, false><<<blocks, 128, 0, stream>>>(pos, sh, rot, so, index_list, by_slot, ctr, fc, recs, extra);
+    {   // tuning knob: cap the grid at BGS_PROJECT_CTAS CTAs per SM (grid-stride loop; smaller footprint beside other frames)
+        static int cap = -1;
+        if (cap < 0) { const char* e = getenv("BGS_PROJECT_CTAS"); cap = e ? atoi(e) : 0; }
+        if (cap > 0 && blocks > (uint32_t)(cap * sm_count)) blocks = (uint32_t)(cap * sm_count);
+    }
+    // blocked layout: `sh` carries the block array
+    if (f16 && blocked) project_kernel<true, true><<<blocks, 128, 0, stream>>>(pos, sh, rot, so, index_list, by_slot, ctr, fc, recs, extra, cutoff_tab);
+    else if (f16) project_kernel<true, false><<<blocks, 128, 0, stream>>>(pos, sh, rot, so, index_list, by_slot, ctr, fc, recs, extra, cutoff_tab);
+    else if (blocked) project_kernel<false, true><<<blocks, 128, 0, stream>>>(pos, sh, rot, so, index_list, by_slot, ctr, fc, recs, extra, cutoff_tab);
+    else project_kernel<false, false><<<blocks, 128, 0, stream>>>(pos, sh, rot, so, index_list, by_slot, ctr, fc, recs, extra, cutoff_tab);
 }
 
 }  // namespace bgs

@@ -18,6 +18,8 @@
 //   pass over the sorted keys.
 //
 // HBM/L2-bound: per pass 8 B read + 8 B written per entry; histogram phase reads 4 B per entry.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace bgs {
@@ -55,13 +57,14 @@ struct SortParams {
     int shift0;                     // pass p sorts on bits [shift0 + 8p, shift0 + 8p + 8)
     int compute_hist;
     uint2* ranges;                  // non-null: the keys are tile ids; the last pass emits ranges[id] = (~start, end)
-    unsigned long long* tl;         // debug timeline (BGS_TIMELINE_SORT): per tile of pass 1, 8 clock64 stamps
+    unsigned long long* tl;         // debug timeline (BGS_TIMELINE_SORT): per tile of pass tl_pass, 8 clock64 stamps
+    int tl_pass;
 };
 
 constexpr size_t radix_smem_bytes(int items) {
     const size_t tile = (size_t)RS_THREADS * items;
     const size_t kv = tile > (size_t)RS_TABLE_WORDS ? tile : (size_t)RS_TABLE_WORDS;
-    return (2 * kv + (size_t)RS_WARPS * 256 + 256 + 256 + RS_WARPS) * 4;
+    return (2 * kv + (size_t)RS_WARPS * 256 + 256 + 256 + 1024 + RS_WARPS) * 4;
 }
 
 template <int RS_ITEMS, bool MASK_TABLE>
@@ -75,7 +78,7 @@ radix_coop_kernel(SortParams P) {
     uint32_t (*s_whist)[256] = reinterpret_cast<uint32_t (*)[256]>(s_vals + KV_WORDS);   // per-warp digit counts -> offsets
     uint32_t* s_binstart = &s_whist[0][0] + RS_WARPS * 256;     // [256] tile-local exclusive digit offsets
     uint32_t* s_gbase = s_binstart + 256;                       // [256] global destination of digit d's run, minus s_binstart[d]
-    uint32_t* s_wtot = s_gbase + 256;                           // [RS_WARPS]
+    uint32_t* s_wtot = s_gbase + 256 + 1024;                    // [RS_WARPS] (the 1024 words between: look-back window sums / flags)
 
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const uint32_t G = gridDim.x;
@@ -136,7 +139,7 @@ radix_coop_kernel(SortParams P) {
 
         for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += G) {
             const uint32_t tile_base = tile * RS_TILE;
-            unsigned long long* tlt = (P.tl && p == 1) ? P.tl + (size_t)(tile < 4096u ? tile : 4095u) * 8 : nullptr;
+            unsigned long long* tlt = (P.tl && p == P.tl_pass) ? P.tl + (size_t)(tile < 4096u ? tile : 4095u) * 8 : nullptr;
             stamp_clk(tlt, 0);
             // warp-striped load: warp w owns [w*32*ITEMS, (w+1)*32*ITEMS) of the tile; item j = 32 consecutive entries
             uint32_t k[RS_ITEMS];
@@ -246,33 +249,49 @@ radix_coop_kernel(SortParams P) {
             }
             stamp_clk(tlt, 3);
 
-            // decoupled look-back, one digit per thread
-            if (t < 256) {
-                if (tile != 0) {
-                    const unsigned long long* ps = my_status;
-                    uint32_t back = tile;
+            // decoupled look-back: digit d = t & 255 is walked by TWO threads (halves h = t >> 8) that take alternate
+            // 16-tile windows of predecessors; the windows of a round are combined in distance order through shared
+            // memory.  In a single-wave sort every tile publishes its aggregate at about the same time and nobody but
+            // tile 0 holds an inclusive prefix yet, so a tile walks all the way back: two windows per round halve that
+            // latency (a round ~0.45 us: C3 depth sort, tile 117 of 118: 5.0 -> ~2.5 us per pass).
+            if (tile != 0) {
+                uint32_t* s_part = s_binstart + 512;            // [2][256] window sums (after s_binstart, s_gbase)
+                uint32_t* s_fnd = s_part + 512;                 // [2][256] window ended at an inclusive prefix
+                const int d = t & 255, h = t >> 8;
+                const unsigned long long* ps = status + (size_t)tile * 256 + d;
+                bool done = false;
+                for (uint32_t round = 0;; ++round) {
+                    const uint32_t w0 = (2u * round + (uint32_t)h) * LB_BATCH;   // this half's window: distances w0 + 1 .. w0 + 16
+                    uint32_t sum = 0u;
                     bool found = false;
-                    while (!found) {
+                    if (!done) {
                         unsigned long long w[LB_BATCH];
 #pragma unroll
                         for (int q = 0; q < LB_BATCH; ++q)
-                            w[q] = ((uint32_t)q < back) ? ld_status(ps - 256 * (q + 1)) : (ep | ST_INC);
+                            w[q] = (w0 + (uint32_t)q < tile) ? ld_status(ps - (size_t)256 * (w0 + q + 1)) : (ep | ST_INC);   // (before tile 0: prefix 0)
 #pragma unroll
                         for (int q = 0; q < LB_BATCH; ++q) {
                             if (!found) {
                                 unsigned long long x = w[q];
-                                while ((x >> 34) != (ep >> 34) || ((x >> 32) & 3ull) == 0ull) x = ld_status(ps - 256 * (q + 1));
-                                excl += (uint32_t)x;
+                                while ((x >> 34) != (ep >> 34) || ((x >> 32) & 3ull) == 0ull) x = ld_status(ps - (size_t)256 * (w0 + q + 1));
+                                sum += (uint32_t)x;
                                 found = ((x >> 32) & 3ull) == 2ull;
                             }
                         }
-                        ps -= 256 * LB_BATCH;
-                        back = back > (uint32_t)LB_BATCH ? back - LB_BATCH : 0u;
                     }
-                    st_status(my_status, ep | ST_INC | (excl + cnt_valid));
+                    s_part[h * 256 + d] = sum;
+                    s_fnd[h * 256 + d] = found ? 1u : 0u;
+                    __syncthreads();
+                    if (!done) {
+                        excl += s_part[d];
+                        if (s_fnd[d]) done = true;
+                        else { excl += s_part[256 + d]; done = s_fnd[256 + d] != 0u; }
+                    }
+                    if (__syncthreads_and(done ? 1 : 0)) break;     // (also fences the reuse of s_part / s_fnd)
                 }
-                s_gbase[t] = excl - binstart;
+                if (t < 256) st_status(my_status, ep | ST_INC | (excl + cnt_valid));
             }
+            if (t < 256) s_gbase[t] = excl - binstart;
             __syncthreads();
             stamp_clk(tlt, 4);
 
@@ -348,6 +367,7 @@ cudaError_t launch_radix_sort(uint32_t* keys0, uint32_t* vals0, uint32_t* keys1,
     P.n_ptr = n_ptr; P.hist = hist; P.status = reinterpret_cast<unsigned long long*>(status); P.status_stride = status_stride;
     P.epoch = epoch; P.barrier = barrier; P.passes = passes; P.shift0 = shift0; P.compute_hist = compute_hist;
     P.ranges = ranges; P.tl = tl;
+    { const char* e = getenv("BGS_TIMELINE_SORT_PASS"); P.tl_pass = e ? atoi(e) : 1; }
     if (n_hint > capacity) n_hint = capacity;
     // items per thread so that one wave of tiles covers the expected count with ~6 % head-room
     const uint64_t want = (uint64_t)n_hint + n_hint / 16 + 1024;

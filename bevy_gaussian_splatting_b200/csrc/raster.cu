@@ -73,6 +73,54 @@ __device__ __forceinline__ float linear_to_srgb(float c) {
     return c <= 0.0031308f ? 12.92f * c : 1.055f * __powf(c, 1.0f / 2.4f) - 0.055f;
 }
 
+// ---- frame output.  `format` = BGS_FORMAT_* | output mode << 8:
+//   mode 0: the splat layer over an opaque black clear (examples/headless.rs:70): (C, 1)
+//   mode 1 (BGS_FLAG_PREMULTIPLIED_OUT): the layer alone, premultiplied: (C, 1 - T)
+//   mode 2 (BGS_FLAG_BLEND_OVER_TARGET): blended over what the target holds, dst = src + (1 - src.a) dst on all four
+//           channels (PREMULTIPLIED_ALPHA_BLENDING, render/mod.rs:944-948): (C + T dst.rgb, (1 - T) + T dst.a)
+constexpr uint32_t OUT_PREMUL = 1u, OUT_OVER = 2u;
+__device__ __forceinline__ float srgb_decode(float c) {
+    return c <= 0.04045f ? c * (1.0f / 12.92f) : __powf((c + 0.055f) * (1.0f / 1.055f), 2.4f);
+}
+__device__ __forceinline__ float4 read_pixel(const void* out, uint32_t fmt, size_t pix) {
+    if (fmt == BGS_FORMAT_RGBA32F) return reinterpret_cast<const float4*>(out)[pix];
+    if (fmt == BGS_FORMAT_RGBA16F) {
+        const uint2 v = reinterpret_cast<const uint2*>(out)[pix];
+        const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&v.x)), hi = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
+        return make_float4(lo.x, lo.y, hi.x, hi.y);
+    }
+    const uint32_t v = reinterpret_cast<const uint32_t*>(out)[pix];
+    return make_float4(srgb_decode((float)(v & 255u) * (1.0f / 255.0f)), srgb_decode((float)((v >> 8) & 255u) * (1.0f / 255.0f)),
+                       srgb_decode((float)((v >> 16) & 255u) * (1.0f / 255.0f)), (float)(v >> 24) * (1.0f / 255.0f));
+}
+// one pixel's accumulated premultiplied colour (r, g, b) and remaining transmittance T -> the frame
+__device__ __forceinline__ void write_pixel(void* out, uint32_t format, size_t pix, float r, float g, float b, float T) {
+    const uint32_t fmt = format & 0xFFu, mode = format >> 8;
+    float a = 1.0f;
+    if (mode & OUT_OVER) {
+        const float4 d = read_pixel(out, fmt, pix);
+        r = fmaf(T, d.x, r); g = fmaf(T, d.y, g); b = fmaf(T, d.z, b);
+        a = fmaf(T, d.w, 1.0f - T);
+    } else if (mode & OUT_PREMUL) {
+        a = 1.0f - T;
+    }
+    if (fmt == BGS_FORMAT_RGBA32F) {
+        reinterpret_cast<float4*>(out)[pix] = make_float4(r, g, b, a);
+    } else if (fmt == BGS_FORMAT_RGBA16F) {
+        const __half2 lo = __floats2half2_rn(r, g), hi = __floats2half2_rn(b, a);
+        uint2 o;
+        o.x = *reinterpret_cast<const uint32_t*>(&lo);
+        o.y = *reinterpret_cast<const uint32_t*>(&hi);
+        reinterpret_cast<uint2*>(out)[pix] = o;
+    } else {
+        const uint32_t r8 = (uint32_t)(linear_to_srgb(r) * 255.0f + 0.5f);
+        const uint32_t g8 = (uint32_t)(linear_to_srgb(g) * 255.0f + 0.5f);
+        const uint32_t b8 = (uint32_t)(linear_to_srgb(b) * 255.0f + 0.5f);
+        const uint32_t a8 = mode ? (uint32_t)(fminf(fmaxf(a, 0.0f), 1.0f) * 255.0f + 0.5f) : 255u;
+        reinterpret_cast<uint32_t*>(out)[pix] = r8 | (g8 << 8) | (b8 << 16) | (a8 << 24);
+    }
+}
+
 // shared-memory layout (byte offsets from one base so the hot loop needs a single address register)
 constexpr uint32_t SM_Q0 = 0;                         // float4 [256]: cx, cy, ux, uy
 constexpr uint32_t SM_UV = SM_Q0 + RT_CHUNK * 16;     // float4 [256]: vx, vy, bbox x, bbox y
@@ -116,12 +164,8 @@ raster_kernel(const SplatRec* __restrict__ recs, const float4* __restrict__ extr
     const uint32_t a_ent = (uint32_t)__cvta_generic_to_shared(&s_ent[0][0]);
     const uint32_t a_bar = (uint32_t)__cvta_generic_to_shared(&s_bar[0]);
     if (range.x >= range.y) {            // empty tile: nothing to stage (uniform across the CTA)
-        if (inside) {
-            const size_t pix0 = (size_t)py * W + px;
-            if (format == BGS_FORMAT_RGBA32F) reinterpret_cast<float4*>(out)[pix0] = make_float4(0.f, 0.f, 0.f, 1.0f);
-            else if (format == BGS_FORMAT_RGBA16F) reinterpret_cast<uint2*>(out)[pix0] = make_uint2(0u, 0x3C000000u);
-            else reinterpret_cast<uint32_t*>(out)[pix0] = 0xFF000000u;
-        }
+        // (blend-over mode leaves the target's pixels as they are)
+        if (inside && !((format >> 8) & OUT_OVER)) write_pixel(out, format, (size_t)py * W + px, 0.f, 0.f, 0.f, 1.0f);
         return;
     }
     // tiles with more than one chunk stream their pair list through the TMA double buffer (the next chunk's
@@ -324,21 +368,7 @@ raster_kernel(const SplatRec* __restrict__ recs, const float4* __restrict__ extr
     if (t == 0 && issued > chunk)             // chunks [0, chunk) were waited for inside the loop
         mbar_wait(a_bar + 8u * (chunk & 1u), (chunk >> 1) & 1u);
     if (!inside) return;
-    const size_t pix = (size_t)py * W + px;
-    if (format == BGS_FORMAT_RGBA32F) {
-        reinterpret_cast<float4*>(out)[pix] = make_float4(cr, cg, cb, 1.0f);
-    } else if (format == BGS_FORMAT_RGBA16F) {
-        const __half2 lo = __floats2half2_rn(cr, cg), hi = __floats2half2_rn(cb, 1.0f);
-        uint2 o;
-        o.x = *reinterpret_cast<const uint32_t*>(&lo);
-        o.y = *reinterpret_cast<const uint32_t*>(&hi);
-        reinterpret_cast<uint2*>(out)[pix] = o;
-    } else {
-        const uint32_t r8 = (uint32_t)(linear_to_srgb(cr) * 255.0f + 0.5f);
-        const uint32_t g8 = (uint32_t)(linear_to_srgb(cg) * 255.0f + 0.5f);
-        const uint32_t b8 = (uint32_t)(linear_to_srgb(cb) * 255.0f + 0.5f);
-        reinterpret_cast<uint32_t*>(out)[pix] = r8 | (g8 << 8) | (b8 << 16) | 0xFF000000u;
-    }
+    write_pixel(out, format, (size_t)py * W + px, cr, cg, cb, T);
 }
 
 // ---- MODE 0 fast path: 2 horizontally adjacent pixels per thread -----------------------------------------
@@ -350,7 +380,12 @@ constexpr uint32_t R2_LIST = SM_Q2 + RT_CHUNK * 16;                      // u16 
 constexpr uint32_t R2_BYTES = R2_LIST + (R2_THREADS / 32) * RT_CHUNK * 2;
 
 __device__ __forceinline__ void store_pixel2(void* out, uint32_t format, size_t pix, bool in0, bool in1, float r0, float g0,
-                                             float b0, float r1, float g1, float b1) {
+                                             float b0, float r1, float g1, float b1, float T0, float T1) {
+    if (format >> 8) {            // premultiplied / blend-over output: the generic per-pixel path
+        if (in0) write_pixel(out, format, pix, r0, g0, b0, T0);
+        if (in1) write_pixel(out, format, pix + 1, r1, g1, b1, T1);
+        return;
+    }
     if (format == BGS_FORMAT_RGBA32F) {
         float4* o = reinterpret_cast<float4*>(out) + pix;
         if (in0) o[0] = make_float4(r0, g0, b0, 1.0f);
@@ -497,7 +532,7 @@ raster2_kernel(const SplatRec* __restrict__ recs, const uint32_t* __restrict__ t
         return;
     }
     if (!(in0 || in1)) return;
-    store_pixel2(out, format, (size_t)py * W + px0, in0, in1, r0, g0, b0, r1, g1, b1);
+    store_pixel2(out, format, (size_t)py * W + px0, in0, in1, r0, g0, b0, r1, g1, b1, T0, T1);
 }
 
 void launch_raster(int mode, bool large_footprints, const SplatRec* recs, const float4* extra, const uint32_t* tile_entries,

@@ -110,18 +110,26 @@ class GaussianSplattingPlugin:
     def render_view(self, handle: PlanarGaussian3dHandle, settings: CloudSettings, view: View,
                     camera: GaussianCamera | None = None, transform: CloudTransform | None = None,
                     fmt: str = "rgba32f", out: np.ndarray | None = None, to_host: bool = True,
-                    asynchronous: bool = False):
+                    asynchronous: bool = False, premultiplied: bool = False, blend_over: bool = False):
         """Returns the (H, W, 4) frame (host) or None when `to_host` is False / the camera is warming up.
-        `asynchronous`: only enqueue the frame (BGS_FLAG_ASYNC); call `sync()` before reading anything."""
+        `asynchronous`: only enqueue the frame (BGS_FLAG_ASYNC); call `sync()` before reading anything.
+        `premultiplied`: the splat layer alone, (C, 1 - T) (BGS_FLAG_PREMULTIPLIED_OUT).  `blend_over`: blend over what
+        the context's frame already holds -- the previous call's result (BGS_FLAG_BLEND_OVER_TARGET): one call per
+        cloud, far cloud first, like the reference's Transparent3d items (render/mod.rs:398-452, :944-948)."""
         if camera is not None and camera.warmup:   # queue_gaussians skips warm-up cameras (render/mod.rs:361-371)
             return None
         code, dtype, ch = self.FORMATS[fmt]
         v = view.to_abi()
-        key = (dataclasses.astuple(settings), None if transform is None else transform.matrix.tobytes(), asynchronous, handle.serial)
+        key = (dataclasses.astuple(settings), None if transform is None else transform.matrix.tobytes(), asynchronous, handle.serial,
+               premultiplied, blend_over)
         if getattr(self, "_us_cache", (None,))[0] != key:
             s_ = settings.to_abi()
             if asynchronous:
                 s_.flags |= abi.BGS_FLAG_ASYNC
+            if premultiplied:
+                s_.flags |= abi.BGS_FLAG_PREMULTIPLIED_OUT
+            if blend_over:
+                s_.flags |= abi.BGS_FLAG_BLEND_OVER_TARGET
             self._us_cache = (key, self.cloud_uniform(settings, transform, handle.aabb), s_)
         _, u, s = self._us_cache
         if to_host:

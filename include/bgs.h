@@ -68,6 +68,14 @@ enum {
                                reference's command-buffer submission: radix.rs / mod.rs never read back) */
     BGS_FLAG_NO_CHUNKS = 4u,/* never split the frame into front-to-back binning rounds (see BGS_FLAG_CHUNKS);
                                the tile debug hooks need a one-round frame */
+    BGS_FLAG_PREMULTIPLIED_OUT = 16u, /* frame = the splat layer alone, premultiplied: (C, 1 - T) -- no implicit black clear,
+                               alpha = coverage.  What a compositor needs to put the layer over anything later. */
+    BGS_FLAG_BLEND_OVER_TARGET = 32u, /* blend over what the target already holds, dst = src + (1 - src.a) * dst on all four
+                               channels -- the reference's PREMULTIPLIED_ALPHA_BLENDING on the view target
+                               (render/mod.rs:944-948): several clouds per view (one bgs_render each, far cloud first,
+                               mod.rs:398-452) and a scene behind the splats.  Target = out_rgba when it is a device
+                               pointer, else the context's frame (which keeps the previous call's result; frames
+                               delivered to host memory are copied out after blending). */
     BGS_FLAG_CHUNKS = 8u    /* always bin / tile-sort / blend in front-to-back rank rounds that stop emitting
                                (splat, tile) pairs once every tile has saturated.  Same pixels, bit for bit.
                                Without either flag the library picks rounds when the previous frame had

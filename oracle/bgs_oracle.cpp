@@ -641,6 +641,15 @@ int orc_project(uint32_t n, const float* pos_vis, const float* sh, const float* 
 
 int orc_render_ref(uint32_t n, const float* pos_vis, const float* sh, const float* rot, const float* so,
                    const orc_view* view, const orc_uniform* u, const orc_settings* s, float* out, int threads) {
+    return orc_render_ref_over(n, pos_vis, sh, rot, so, view, u, s, nullptr, out, threads);
+}
+
+// The same back-to-front pass over an arbitrary initial target (premultiplied linear RGBA): what the reference's
+// Transparent3d item does to the view target it is drawn into (render/mod.rs:398-452, :944-948).  dst_init == NULL is
+// the opaque black clear of examples/headless.rs:70; all-zero dst_init yields the layer alone, (C, 1 - T).
+int orc_render_ref_over(uint32_t n, const float* pos_vis, const float* sh, const float* rot, const float* so,
+                        const orc_view* view, const orc_uniform* u, const orc_settings* s, const float* dst_init,
+                        float* out, int threads) {
     Ctx C;
     if (!make_ctx(C, view, u, s)) return 2;
 #ifdef _OPENMP
@@ -658,7 +667,12 @@ int orc_render_ref(uint32_t n, const float* pos_vis, const float* sh, const floa
         const int y0 = b * band, y1 = std::min(H, y0 + band) - 1;
         for (int y = y0; y <= y1; ++y) for (int x = 0; x < W; ++x) {
             float* px = out + 4 * ((size_t)y * W + x);
-            px[0] = 0.0f; px[1] = 0.0f; px[2] = 0.0f; px[3] = 1.0f;
+            if (dst_init) {
+                const float* d = dst_init + 4 * ((size_t)y * W + x);
+                px[0] = d[0]; px[1] = d[1]; px[2] = d[2]; px[3] = d[3];
+            } else {
+                px[0] = 0.0f; px[1] = 0.0f; px[2] = 0.0f; px[3] = 1.0f;
+            }
         }
         for (int64_t r = (int64_t)F.n_vis - 1; r >= 0; --r) {   // far -> near
             const orc_splat& sp = F.splats[r];

@@ -85,6 +85,12 @@ int orc_render_ref(uint32_t n, const float* pos_vis, const float* sh, const floa
                    const float* scale_opacity, const orc_view* view, const orc_uniform* u,
                    const orc_settings* s, float* out_rgba, int threads);
 
+/* a6 ref_mode over an initial target (premultiplied linear RGBA, W*H*4; NULL = opaque black clear): the
+ * reference's PREMULTIPLIED_ALPHA_BLENDING onto the view target, render/mod.rs:944-948. */
+int orc_render_ref_over(uint32_t n, const float* pos_vis, const float* sh, const float* rot,
+                        const float* scale_opacity, const orc_view* view, const orc_uniform* u,
+                        const orc_settings* s, const float* dst_init, float* out_rgba, int threads);
+
 /* a6+a7 tile_mode: 16x16 tile ranges over the global order, front-to-back, pixel stops at
  * T < 1e-4.  tile_ranges = tiles*2 (start,end into tile_entries); tile_entries holds the
  * front-to-back rank r (0 = nearest visible splat) of each (tile,splat) pair, capacity cap.

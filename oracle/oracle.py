@@ -122,13 +122,17 @@ def project(cloud, view, uniform, settings, ids: np.ndarray) -> np.ndarray:
     return out
 
 
-def render_ref(cloud, view, uniform, settings, threads: int = 0) -> np.ndarray:
+def render_ref(cloud, view, uniform, settings, threads: int = 0, dst: np.ndarray | None = None) -> np.ndarray:
+    """ref_mode frame.  `dst`: (H, W, 4) f32 premultiplied target to blend over (None = opaque black clear)."""
     v, u, s = _conv(view, orc_view), _conv(uniform, orc_uniform), _conv(settings, orc_settings)
     W, H = int(v.viewport[2]), int(v.viewport[3])
     out = np.empty((H, W, 4), np.float32)
-    rc = load().orc_render_ref(C.c_uint32(len(cloud)), _p(cloud.position_visibility), _p(cloud.spherical_harmonic),
-                               _p(cloud.rotation), _p(cloud.scale_opacity), C.byref(v), C.byref(u), C.byref(s), _p(out),
-                               C.c_int(threads))
+    if dst is not None:
+        dst = np.ascontiguousarray(dst, np.float32)
+        assert dst.shape == (H, W, 4)
+    rc = load().orc_render_ref_over(C.c_uint32(len(cloud)), _p(cloud.position_visibility), _p(cloud.spherical_harmonic),
+                                    _p(cloud.rotation), _p(cloud.scale_opacity), C.byref(v), C.byref(u), C.byref(s), _p(dst), _p(out),
+                                    C.c_int(threads))
     assert rc == 0
     return out
 

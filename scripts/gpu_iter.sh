@@ -3,14 +3,14 @@
 TAG=${1:-it}
 mkdir -p gpurun_out
 if [ -n "$2" ]; then
-  timeout 900 python -m pytest tests -x -q -m gpu -k "$2" > gpurun_out/pytest_gpu_$TAG.log 2>&1
+  timeout 400 python -m pytest tests -x -q -m gpu -k "$2" > gpurun_out/pytest_gpu_$TAG.log 2>&1
 else
-  timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/pytest_gpu_$TAG.log 2>&1
+  timeout 400 python -m pytest tests -x -q -m gpu > gpurun_out/pytest_gpu_$TAG.log 2>&1
 fi
 tail -6 gpurun_out/pytest_gpu_$TAG.log
 timeout 300 python scripts/timeline_sort.py > gpurun_out/tl_sort_$TAG.log 2>&1
 timeout 300 python scripts/timeline.py > gpurun_out/tl_bin_$TAG.log 2>&1
-timeout 600 python bench.py --steps 100 --warmup 10 --no-cpu-baseline > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err
+timeout 300 python bench.py --steps 100 --warmup 10 --no-cpu-baseline > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err
 python - <<PY
 import json
 try:

@@ -545,3 +545,63 @@ def test_full_size_vs_oracle(plugin, oracle, name, n, f16, kw):
     sort tiles, key-gen ranges that do not fit shared memory, > 65535-row grids, the footprint queues of the binning."""
     cloud = B.random_gaussians_3d_seeded(n, 4 if name.startswith("C4") else 0)
     check_against_oracle(plugin, oracle, cloud, B.CloudSettings(**kw), B.headless_view(1920, 1080), f16=f16, ref_mode_too=True)
+
+
+def test_compositing_over_target_and_premultiplied(plugin, oracle):
+    """Row (b): the reference blends every visible cloud over whatever the view target holds, PREMULTIPLIED_ALPHA_BLENDING,
+    one Transparent3d item per cloud (render/mod.rs:398-452, :944-948).  BGS_FLAG_BLEND_OVER_TARGET / _PREMULTIPLIED_OUT
+    against the oracle's ref_mode run over the same initial target."""
+    view = B.orbit_view(1, 8, 384, 216)
+    far = B.random_gaussians_3d_seeded(9000, 31)
+    near = B.random_gaussians_3d_seeded(7000, 32)
+    near.position_visibility[:, :3] *= np.float32(0.5)          # a smaller cloud in front of / inside the first one
+    s_far, s_near = B.CloudSettings(global_scale=0.3), B.CloudSettings(global_scale=0.2, global_opacity=0.8)
+    h_far, h_near = plugin.add_cloud(far), plugin.add_cloud(near, f16=True)
+    try:
+        u_far, u_near = plugin.cloud_uniform(s_far, None, h_far.aabb), plugin.cloud_uniform(s_near, None, h_near.aabb)
+        near16 = near.rounded_to_f16()
+        # two clouds in one target, far cloud first
+        base = plugin.render_view(h_far, s_far, view, fmt="rgba32f")
+        both = plugin.render_view(h_near, s_near, view, fmt="rgba32f", blend_over=True)
+        want_base = oracle.render_ref(far, view.to_abi(), u_far, s_far.to_abi())
+        want_both = oracle.render_ref(near16, view.to_abi(), u_near, s_near.to_abi(), dst=want_base)
+        assert np.abs(base - want_base).max() <= PIXEL_TOL
+        assert np.abs(both - want_both).max() <= PIXEL_TOL
+        assert np.abs(both - base).max() > 0.05 and np.all(both[..., 3] == 1.0)       # it did blend, alpha stays opaque
+        # the layer alone, premultiplied: (C, 1 - T)
+        layer = plugin.render_view(h_near, s_near, view, fmt="rgba32f", premultiplied=True)
+        want_layer = oracle.render_ref(near16, view.to_abi(), u_near, s_near.to_abi(), dst=np.zeros_like(want_base))
+        assert np.abs(layer - want_layer).max() <= PIXEL_TOL
+        assert layer[..., 3].min() >= 0.0 and layer[..., 3].max() > 0.5 and layer[..., 3].max() <= 1.0
+        # compositing the layer by hand over the first frame == the blend-over frame
+        assert np.abs(layer[..., :3] + (1.0 - layer[..., 3:4]) * base[..., :3] - both[..., :3]).max() <= 2e-5
+        # a scene behind the splats: blend over an arbitrary (non-black, translucent) target held by the context
+        far_layer = oracle.render_ref(far, view.to_abi(), u_far, s_far.to_abi(), dst=np.zeros_like(want_base))
+
+        def srgb_enc(c):
+            c = np.clip(c, 0, 1)
+            return np.where(c <= 0.0031308, 12.92 * c, 1.055 * np.power(c, 1 / 2.4) - 0.055)
+
+        def srgb_dec(c):
+            return np.where(c <= 0.04045, c / 12.92, np.power((c + 0.055) / 1.055, 2.4))
+
+        for fmt in ("rgba16f", "rgba8_srgb"):
+            held = plugin.render_view(h_far, s_far, view, fmt=fmt, premultiplied=True)       # target <- far layer (C, 1 - T)
+            got = plugin.render_view(h_near, s_near, view, fmt=fmt, blend_over=True).astype(np.float32)
+            if fmt == "rgba8_srgb":
+                # an 8-bit sRGB target clamps and quantises what it holds: blend over exactly what it held
+                assert np.abs(held[..., :3] / 255.0 - srgb_enc(far_layer[..., :3])).max() <= 1.01 / 255.0
+                h8 = held.astype(np.float32) / 255.0
+                dst = np.concatenate([srgb_dec(h8[..., :3]), h8[..., 3:4]], axis=2).astype(np.float32)
+                want = oracle.render_ref(near16, view.to_abi(), u_near, s_near.to_abi(), dst=dst)
+                want = np.concatenate([srgb_enc(want[..., :3]), np.clip(want[..., 3:4], 0, 1)], axis=2)
+                assert np.abs(got / 255.0 - want).max() <= 1.01 / 255.0
+            else:
+                want = oracle.render_ref(near16, view.to_abi(), u_near, s_near.to_abi(), dst=held.astype(np.float32))
+                assert np.abs(got - want).max() <= 4e-3 * max(1.0, np.abs(want).max())
+        # binning rounds take the same output path
+        rounds = plugin.render_view(h_near, B.CloudSettings(global_scale=0.2, global_opacity=0.8, binning_rounds=True), view,
+                                    fmt="rgba32f", premultiplied=True)
+        assert plugin.frame_stats().rounds > 1 and np.array_equal(rounds, layer)
+    finally:
+        h_far.destroy(); h_near.destroy()
