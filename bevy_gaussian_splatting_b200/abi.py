@@ -83,6 +83,8 @@ SYMBOLS = [
     ("bgs_cloud_destroy", None, [_P]),
     ("bgs_render", C.c_int, [_P, _P, C.POINTER(bgs_view), C.POINTER(bgs_cloud_uniform), C.POINTER(bgs_settings), _P,
                              C.c_uint32, C.c_int]),
+    ("bgs_render_aux", C.c_int, [_P, _P, C.POINTER(bgs_view), C.POINTER(bgs_cloud_uniform), C.POINTER(bgs_settings), _P, _P, _P,
+                                 C.c_uint32, C.c_int]),
     ("bgs_sync", C.c_int, [_P]),
     ("bgs_debug_sorted_entries", C.c_int, [_P, _P]),
     ("bgs_debug_tile_ranges", C.c_int, [_P, _P]),

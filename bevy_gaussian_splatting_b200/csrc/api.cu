@@ -38,7 +38,7 @@ void launch_repack(bool f16, const void* pos, const void* sh, const void* rot, c
 void launch_project(bool f16, bool blocked, const float4* pos, const void* sh, const void* rot, const void* so,
                     const uint32_t* index_list, int by_slot, const FrameCounters* ctr, const FrameConsts& fc,
                     SplatRec* recs, float4* extra, uint32_t n_hint, int sm_count, int ctas_per_sm, const float* cutoff_tab,
-                    cudaStream_t stream);
+                    float4* aux, cudaStream_t stream);
 void launch_cutoff_table(float* tab, cudaStream_t stream);
 // bin.cu
 void launch_bin_emit(const SplatRec* recs, const uint32_t* perm, FrameCounters* ctr, ChunkCounters* cc, uint32_t* status, int tiles_x,
@@ -54,7 +54,7 @@ cudaError_t launch_bin_emit_coop(const SplatRec* recs, const uint32_t* perm, Fra
 // raster.cu
 void launch_raster(int mode, bool large_footprints, const SplatRec* recs, const float4* extra, const uint32_t* tile_entries,
                    const uint2* ranges, int W, int H, int tiles_x, int tiles_y, void* out, uint32_t format,
-                   cudaStream_t stream);
+                   const float4* aux, void* out_depth, void* out_normal, cudaStream_t stream);
 void launch_raster_round(const SplatRec* recs, const uint32_t* tile_entries, const uint2* ranges, int W, int H, int tiles_x,
                          int tiles_y, void* out, uint32_t format, float4* state, unsigned char* tile_done,
                          uint32_t* tiles_done, int first, int last, cudaStream_t stream);
@@ -119,6 +119,10 @@ struct bgs_context {
     SplatRec* recs = nullptr;
     float4* extra = nullptr;          // 4 x float4 per record: 2DGS + USE_AABB only (allocated on first use)
     uint32_t cap_extra = 0;
+    float4* aux = nullptr;            // 2 x float4 per record: depth / normal colour sources (bgs_render_aux only)
+    uint32_t cap_aux = 0;
+    void* frame_aux[2] = {nullptr, nullptr};   // depth / normal frames when bgs_render_aux delivers to host memory
+    size_t frame_aux_bytes = 0;
     // scratch sized by the pair capacity (grow-only)
     uint32_t cap_pairs = 0;
     uint32_t* pkeys[2] = {nullptr, nullptr};
@@ -418,6 +422,7 @@ void bgs_context_destroy(bgs_context* c) {
         cudaFree(c->keys[i]); cudaFree(c->vals[i]); cudaFree(c->pkeys[i]); cudaFree(c->pvals[i]);
     }
     cudaFree(c->state);
+    cudaFree(c->aux); cudaFree(c->frame_aux[0]); cudaFree(c->frame_aux[1]);
     cudaFree(c->recs); cudaFree(c->extra); cudaFree(c->slot_ids); cudaFree(c->arena); cudaFree(c->frame);
     if (c->h_ctr) cudaFreeHost(c->h_ctr);
     if (c->h_sticky) cudaFreeHost(c->h_sticky);
@@ -589,8 +594,26 @@ bgs_status bgs_sync(bgs_context* c) {
     return s;
 }
 
+static bgs_status render_impl(bgs_context* c, const bgs_cloud* cloud, const bgs_view* view, const bgs_cloud_uniform* uni,
+                              const bgs_settings* st, void* out_rgba, uint32_t out_format, int out_is_device_ptr,
+                              bool want_aux, void* out_depth, void* out_normal);
+
 bgs_status bgs_render(bgs_context* c, const bgs_cloud* cloud, const bgs_view* view, const bgs_cloud_uniform* uni,
                       const bgs_settings* st, void* out_rgba, uint32_t out_format, int out_is_device_ptr) {
+    return render_impl(c, cloud, view, uni, st, out_rgba, out_format, out_is_device_ptr, false, nullptr, nullptr);
+}
+
+bgs_status bgs_render_aux(bgs_context* c, const bgs_cloud* cloud, const bgs_view* view, const bgs_cloud_uniform* uni,
+                          const bgs_settings* st, void* out_rgba, void* out_depth, void* out_normal, uint32_t out_format,
+                          int out_is_device_ptr) {
+    if (c && (!out_rgba || !out_depth || !out_normal)) return fail(c, BGS_EINVAL, "render_aux: the three output frames are required");
+    if (c && st && (st->flags & BGS_FLAG_ASYNC)) return fail(c, BGS_EINVAL, "render_aux: BGS_FLAG_ASYNC is not supported");
+    return render_impl(c, cloud, view, uni, st, out_rgba, out_format, out_is_device_ptr, true, out_depth, out_normal);
+}
+
+static bgs_status render_impl(bgs_context* c, const bgs_cloud* cloud, const bgs_view* view, const bgs_cloud_uniform* uni,
+                              const bgs_settings* st, void* out_rgba, uint32_t out_format, int out_is_device_ptr,
+                              bool want_aux, void* out_depth, void* out_normal) {
     if (!c) return BGS_EINVAL;
     // not-ready inputs map to the reference's silent skip-frame (radix.rs:645-658, mod.rs:1533-1539)
     if (!cloud || !view || !uni || !st) return fail(c, BGS_NOT_READY, "render: cloud/view/uniform/settings not ready");
@@ -635,6 +658,7 @@ bgs_status bgs_render(bgs_context* c, const bgs_cloud* cloud, const bgs_view* vi
     fc.adaptive = st->opacity_adaptive_radius; fc.draw_mode = st->draw_mode;
     fc.Wi = W; fc.Hi = H; fc.tiles_x = tiles_x; fc.tiles_y = tiles_y;
     fc.n_cloud = n;
+    fc.aux = want_aux ? 1u : 0u;
     memcpy(fc.aabb_min, uni->aabb_min, 12); memcpy(fc.aabb_max, uni->aabb_max, 12);
     static const float kIdentity[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
     fc.model_identity = memcmp(uni->transform, kIdentity, 64) == 0 ? 1u : 0u;   // (-0.0 entries take the general path)
@@ -647,6 +671,27 @@ bgs_status bgs_render(bgs_context* c, const bgs_cloud* cloud, const bgs_view* vi
         cudaFree(c->extra); c->extra = nullptr; c->cap_extra = 0;
         CU(c, cudaMalloc(&c->extra, (size_t)c->cap_n * 64));
         c->cap_extra = c->cap_n;
+    }
+    void* tgt_depth = nullptr; void* tgt_normal = nullptr;
+    if (want_aux) {
+        if (c->cap_aux < c->cap_n) {
+            cudaFree(c->aux); c->aux = nullptr; c->cap_aux = 0;
+            CU(c, cudaMalloc(&c->aux, (size_t)c->cap_n * 32));
+            c->cap_aux = c->cap_n;
+        }
+        if (out_is_device_ptr) { tgt_depth = out_depth; tgt_normal = out_normal; }
+        else {
+            const size_t fb = (size_t)W * H * format_bpp(out_format);
+            if (fb > c->frame_aux_bytes) {
+                cudaFree(c->frame_aux[0]); cudaFree(c->frame_aux[1]); c->frame_aux[0] = c->frame_aux[1] = nullptr; c->frame_aux_bytes = 0;
+                CU(c, cudaMalloc(&c->frame_aux[0], fb));
+                CU(c, cudaMalloc(&c->frame_aux[1], fb));
+                CU(c, cudaMemsetAsync(c->frame_aux[0], 0, fb, c->stream));
+                CU(c, cudaMemsetAsync(c->frame_aux[1], 0, fb, c->stream));
+                c->frame_aux_bytes = fb;
+            }
+            tgt_depth = c->frame_aux[0]; tgt_normal = c->frame_aux[1];
+        }
     }
     if (c->cap_pairs == 0) {
         uint32_t init = n < (1u << 20) ? (1u << 20) : n;   // first guess; grows on demand
@@ -679,7 +724,7 @@ bgs_status bgs_render(bgs_context* c, const bgs_cloud* cloud, const bgs_view* vi
     // and >= 2^24 pairs; measured crossover on B200: ~15-30 M pairs, profiles/r1_rounds.md) run binning / tile sort /
     // blend in front-to-back rank rounds; the rounds after every tile has saturated emit nothing.
     // Quad-uv records + cooperative binning only; BGS_FLAG_CHUNKS / _NO_CHUNKS force it.
-    bool chunked = raster_mode == 0 && c->coop && num_tiles <= CHUNK_MAX_TILES && !(st->flags & BGS_FLAG_NO_CHUNKS) && c->chunk_count > 1;
+    bool chunked = raster_mode == 0 && !want_aux && c->coop && num_tiles <= CHUNK_MAX_TILES && !(st->flags & BGS_FLAG_NO_CHUNKS) && c->chunk_count > 1;
     if (chunked && !(st->flags & BGS_FLAG_CHUNKS))
         chunked = c->n_vis_hint > 0 && c->n_pairs_hint >= (c->last_chunks > 1 ? 3u << 22 : 1u << 24) &&
                   (uint64_t)c->n_pairs_hint >= (c->last_chunks > 1 ? 24ull : 32ull) * c->n_vis_hint;   // (hysteresis)
@@ -721,7 +766,7 @@ bgs_status bgs_render(bgs_context* c, const bgs_cloud* cloud, const bgs_view* vi
         //      with the depth sort (it only needs slot_ids); records land at recs[slot]
         const uint32_t n_hint = c->n_vis_hint ? c->n_vis_hint + c->n_vis_hint / 4 + 1024 : n;
         // Depth colouring needs sorted[1] / sorted[N-1]: the projection then waits for the sort
-        const bool overlap = by_slot && st->rasterize_mode != BGS_RASTERIZE_DEPTH;
+        const bool overlap = by_slot && st->rasterize_mode != BGS_RASTERIZE_DEPTH && !want_aux;
         if (overlap) CU(c, cudaEventRecord(c->ev_fork, q));
         // ---- stage 2: depth radix sort: all P = depth_bits / 8 digit places in ONE cooperative launch (enqueued before
         //      the projection so its one-CTA-per-SM grid becomes resident first; the projection fills the other half)
@@ -735,7 +780,7 @@ bgs_status bgs_render(bgs_context* c, const bgs_cloud* cloud, const bgs_view* vi
             CU(c, cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
             CU(c, cudaEventRecord(c->ev_p0, c->stream2));
             launch_project(cloud->f16, cloud->blocks != nullptr, cloud->pos, cloud->blocks ? cloud->blocks : cloud->sh, cloud->rot, cloud->so, c->slot_ids, 1, c->ctr, fc, c->recs,
-                           raster_mode == 2 ? c->extra : nullptr, n_hint < n ? n_hint : n, c->sm_count, 2, c->cutoff_tab, c->stream2);
+                           raster_mode == 2 ? c->extra : nullptr, n_hint < n ? n_hint : n, c->sm_count, 2, c->cutoff_tab, nullptr, c->stream2);
             ++launches;
             CU(c, cudaEventRecord(c->ev_p1, c->stream2));
             CU(c, cudaEventRecord(c->ev_join, c->stream2));
@@ -747,14 +792,15 @@ bgs_status bgs_render(bgs_context* c, const bgs_cloud* cloud, const bgs_view* vi
             CU(c, cudaStreamWaitEvent(q, c->ev_join, 0));
         } else {
             // ---- stage 3 after the sort: SORT_ALL (records by front-to-back rank) or Depth colouring (by slot)
-            if (st->rasterize_mode == BGS_RASTERIZE_DEPTH) {
+            if (st->rasterize_mode == BGS_RASTERIZE_DEPTH || want_aux) {
                 launch_depth_range(cloud->pos, n, c->vals[cur], by_slot ? c->slot_ids : nullptr, c->ctr, fc, q);
                 ++launches;
             }
             CU(c, cudaEventRecord(c->ev_p0, q));
             launch_project(cloud->f16, cloud->blocks != nullptr, cloud->pos, cloud->blocks ? cloud->blocks : cloud->sh, cloud->rot, cloud->so, by_slot ? c->slot_ids : c->vals[cur],
                            by_slot ? 1 : 0, c->ctr, fc, c->recs,
-                           raster_mode == 2 ? c->extra : nullptr, n_hint < n ? n_hint : n, c->sm_count, 0, c->cutoff_tab, q);
+                           raster_mode == 2 ? c->extra : nullptr, n_hint < n ? n_hint : n, c->sm_count, 0, c->cutoff_tab,
+                           want_aux ? c->aux : nullptr, q);
             ++launches;
             CU(c, cudaEventRecord(c->ev_p1, q));
         }
@@ -802,7 +848,8 @@ bgs_status bgs_render(bgs_context* c, const bgs_cloud* cloud, const bgs_view* vi
                 if (split < 0) { const char* e = getenv("BGS_RASTER_PRIO"); split = (e && atoi(e) == 0) ? 0 : 1; }
                 cudaStream_t qr = split ? c->stream_r : q;
                 if (split) { CU(c, cudaEventRecord(c->ev_front, q)); CU(c, cudaStreamWaitEvent(qr, c->ev_front, 0)); }
-                launch_raster(raster_mode, large_fp, c->recs, c->extra, c->pvals[pcur], rng, W, H, tiles_x, tiles_y, target, raster_format, qr);
+                launch_raster(raster_mode, large_fp, c->recs, c->extra, c->pvals[pcur], rng, W, H, tiles_x, tiles_y, target, raster_format,
+                              want_aux ? c->aux : nullptr, tgt_depth, tgt_normal, qr);
                 if (split) { CU(c, cudaEventRecord(c->ev_rdone, qr)); CU(c, cudaStreamWaitEvent(q, c->ev_rdone, 0)); }
             } else
                 launch_raster_round(c->recs, c->pvals[pcur], rng, W, H, tiles_x, tiles_y, target, raster_format, c->state,
@@ -822,6 +869,10 @@ bgs_status bgs_render(bgs_context* c, const bgs_cloud* cloud, const bgs_view* vi
             c->copy_pending[fslot] = true;
         } else if (out_rgba && !out_is_device_ptr) {
             CU(c, cudaMemcpyAsync(out_rgba, target, frame_bytes, cudaMemcpyDeviceToHost, q));
+            if (want_aux) {
+                CU(c, cudaMemcpyAsync(out_depth, tgt_depth, frame_bytes, cudaMemcpyDeviceToHost, q));
+                CU(c, cudaMemcpyAsync(out_normal, tgt_normal, frame_bytes, cudaMemcpyDeviceToHost, q));
+            }
         }
         c->pend_cloud = cloud; c->pend_n = n; c->pend_fc = fc; c->pend_sort_all = sort_all; c->pend_by_slot = by_slot;
         c->pend_chunks = rounds;

@@ -48,7 +48,7 @@ keygen_compact_kernel(const float4* __restrict__ pos, uint32_t n, FrameConsts fc
         const uint32_t kkey = key_of_fast(fc, p[j].x, p[j].y, p[j].z, kvis);
         const bool v = (i < n) && kvis;
         key[j] = kkey;
-        if (fc.rasterize_mode == BGS_RASTERIZE_DEPTH && i < n && !kvis) {
+        if ((fc.rasterize_mode == BGS_RASTERIZE_DEPTH || fc.aux) && i < n && !kvis) {
             atomicMax(&ctr->culled_min_inv, 0xFFFFFFFFu - i);
             atomicMax(&ctr->culled_max_p1, i + 1u);
         }
@@ -159,12 +159,12 @@ keygen_coop_kernel(const float4* __restrict__ pos, uint32_t n, FrameConsts fc, u
             const uint32_t bal = __ballot_sync(0xffffffffu, v);
             mine += __popc(bal);
             if (lane == j) myword = bal;
-            if (fc.rasterize_mode == BGS_RASTERIZE_DEPTH && i < n && !v) { cmin_inv = max(cmin_inv, 0xFFFFFFFFu - i); cmax_p1 = max(cmax_p1, i + 1u); }
+            if ((fc.rasterize_mode == BGS_RASTERIZE_DEPTH || fc.aux) && i < n && !v) { cmin_inv = max(cmin_inv, 0xFFFFFFFFu - i); cmax_p1 = max(cmax_p1, i + 1u); }
         }
         if (lane < KG_ITEMS) __stcg(masks + (size_t)tile * KG_WORDS_PER_TILE + warp * KG_ITEMS + lane, myword);
     }
     if (lane == 0) s_red[warp] = mine;
-    if (fc.rasterize_mode == BGS_RASTERIZE_DEPTH) {
+    if ((fc.rasterize_mode == BGS_RASTERIZE_DEPTH || fc.aux)) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             cmin_inv = max(cmin_inv, __shfl_xor_sync(0xffffffffu, cmin_inv, o));

@@ -221,7 +221,7 @@ void launch_cutoff_table(float* tab, cudaStream_t stream) { cutoff_table_kernel<
 template <class ShLoader>
 __device__ __forceinline__ void project_one(const FrameConsts& fc, const FrameCounters* __restrict__ ctr, uint32_t r, float4 p4,
                                             const float q[4], const float so[4], float cutoff_pre, ShLoader load_sh,
-                                            SplatRec* __restrict__ recs, float4* __restrict__ extra) {
+                                            SplatRec* __restrict__ recs, float4* __restrict__ extra, float4* __restrict__ aux) {
     SplatRec rec;
     rec.ux = 0.f; rec.uy = 0.f; rec.vx = 0.f; rec.vy = 0.f;
     rec.bx = BBOX_EMPTY; rec.by = BBOX_EMPTY;
@@ -459,7 +459,12 @@ __device__ __forceinline__ void project_one(const FrameConsts& fc, const FrameCo
 #pragma unroll
                 for (int cc = 0; cc < 3; ++cc) rgb[cc] = srgb_to_linear(rgb[cc]);
             }
-        } else if (fc.rasterize_mode == BGS_RASTERIZE_DEPTH) {
+        }
+        // aux outputs (bgs_render_aux, config C4): the Depth and Normal colour sources ride along with the main one, so one
+        // pass yields what three single-mode frames would (the geometry and alpha of a splat do not depend on the mode)
+        float drgb[3] = {0.f, 0.f, 0.f}, nrgb[3] = {0.f, 0.f, 0.f};
+        if (fc.rasterize_mode == BGS_RASTERIZE_DEPTH || fc.aux) {
+            float* rgb = drgb;
             // material/depth.wgsl:3-11
             const float dlt[3] = {k.pw[0] - fc.cam[0], k.pw[1] - fc.cam[1], k.pw[2] - fc.cam[2]};
             const float depth = sqrtf(dot3(dlt, dlt));
@@ -473,11 +478,14 @@ __device__ __forceinline__ void project_one(const FrameConsts& fc, const FrameCo
             rgb[1] = 1.0f - fabsf(nd - 0.5f) * 2.0f;
             rgb[2] = 1.0f - t2 * t2 * (3.0f - 2.0f * t2);
             }
-        } else if (fc.rasterize_mode == BGS_RASTERIZE_POSITION) {
+        }
+        if (fc.rasterize_mode == BGS_RASTERIZE_POSITION) {
             // gaussian.wgsl:375-376: (transformed_position - min) / (max - min)
 #pragma unroll
             for (int cc = 0; cc < 3; ++cc) rgb[cc] = (k.pw[cc] - fc.aabb_min[cc]) / (fc.aabb_max[cc] - fc.aabb_min[cc]);
-        } else if (fc.rasterize_mode == BGS_RASTERIZE_NORMAL) {
+        }
+        if (fc.rasterize_mode == BGS_RASTERIZE_NORMAL || fc.aux) {
+            float* rgb = nrgb;
             // gaussian.wgsl:350-368
             float SR[3], Ln[3], wn[4];
 #pragma unroll
@@ -489,9 +497,16 @@ __device__ __forceinline__ void project_one(const FrameConsts& fc, const FrameCo
 #pragma unroll
             for (int cc = 0; cc < 3; ++cc) rgb[cc] = 0.5f * (wn[cc] / l + 1.0f);
         }
+        if (fc.rasterize_mode == BGS_RASTERIZE_DEPTH) { rgb[0] = drgb[0]; rgb[1] = drgb[1]; rgb[2] = drgb[2]; }
+        if (fc.rasterize_mode == BGS_RASTERIZE_NORMAL) { rgb[0] = nrgb[0]; rgb[1] = nrgb[1]; rgb[2] = nrgb[2]; }
         rec.r = rgb[0]; rec.g = rgb[1]; rec.b = rgb[2];
         if (fc.draw_mode == BGS_DRAW_HIGHLIGHT_SELECTED && p4.w > 0.5f) {   // gaussian.wgsl:423-427
             rec.r = 0.3f; rec.g = 1.0f; rec.b = 0.1f; rec.op = 1.0f;
+            drgb[0] = nrgb[0] = 0.3f; drgb[1] = nrgb[1] = 1.0f; drgb[2] = nrgb[2] = 0.1f;
+        }
+        if (fc.aux && aux != nullptr) {
+            aux[(size_t)r * 2] = make_float4(drgb[0], drgb[1], drgb[2], 0.0f);
+            aux[(size_t)r * 2 + 1] = make_float4(nrgb[0], nrgb[1], nrgb[2], 0.0f);
         }
     }
     // 48 B record, three 16 B stores
@@ -506,7 +521,8 @@ __global__ void __launch_bounds__(128, 6)
 project_kernel(const float4* __restrict__ pos, const void* __restrict__ sh_p, const void* __restrict__ rot_p,
                const void* __restrict__ so_p, const uint32_t* __restrict__ index_list, int by_slot,
                const FrameCounters* __restrict__ ctr, FrameConsts fc, SplatRec* __restrict__ recs,
-               float4* __restrict__ extra /* 4 x float4 per record, 2DGS + USE_AABB only */, const float* __restrict__ cutoff_tab) {
+               float4* __restrict__ extra /* 4 x float4 per record, 2DGS + USE_AABB only */, const float* __restrict__ cutoff_tab,
+               float4* __restrict__ aux /* 2 x float4 per record (depth rgb, normal rgb), bgs_render_aux only */) {
     const uint32_t n_vis = ctr->n_vis;
     for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n_vis; r += gridDim.x * blockDim.x) {
         // by_slot: r is a compact slot (ascending gaussian index; runs concurrently with the depth sort)
@@ -523,7 +539,7 @@ project_kernel(const float4* __restrict__ pos, const void* __restrict__ sh_p, co
 #pragma unroll
                         for (int i = 0; i < 48; ++i) out[i] = sh[i];
                     },
-                    recs, extra);
+                    recs, extra, aux);
     }
 }
 
@@ -644,7 +660,7 @@ project_ring_kernel(const void* __restrict__ blocks, const uint32_t* __restrict_
                                 }
                             }
                         },
-                        recs, extra);
+                        recs, extra, nullptr);
         }
         __syncwarp();                                  // every lane is done with the stage before it is refilled
         issue(k + (uint32_t)R::STAGES);
@@ -659,10 +675,10 @@ void launch_depth_range(const float4* pos, uint32_t n, const uint32_t* sorted_pa
 void launch_project(bool f16, bool blocked, const float4* pos, const void* sh, const void* rot, const void* so,
                     const uint32_t* index_list, int by_slot, const FrameCounters* ctr, const FrameConsts& fc,
                     SplatRec* recs, float4* extra, uint32_t n_hint, int sm_count, int ctas_per_sm, const float* cutoff_tab,
-                    cudaStream_t stream) {
+                    float4* aux, cudaStream_t stream) {
     static int use_ring = -1;
     if (use_ring < 0) { const char* e = getenv("BGS_PROJECT_RING"); use_ring = (e && atoi(e) > 0) ? 1 : 0; }
-    if (blocked && use_ring) {
+    if (blocked && use_ring && aux == nullptr) {
         // (measured slower on B200 -- one UBLKCP per 128 B row sustains ~1 copy / 20 cycles / SM: 48 us vs 36 us for
         // the per-thread gather at C3 -- kept behind BGS_PROJECT_RING=1 as the evidence, profiles/r2_experiments.md)
         // TMA ring over the gaussian-major blocks (`sh` carries the block array): a persistent grid of at most
@@ -696,10 +712,10 @@ void launch_project(bool f16, bool blocked, const float4* pos, const void* sh, c
         if (cap > 0 && blocks > (uint32_t)(cap * sm_count)) blocks = (uint32_t)(cap * sm_count);
     }
     // blocked layout: `sh` carries the block array
-    if (f16 && blocked) project_kernel<true, true><<<blocks, 128, 0, stream>>>(pos, sh, rot, so, index_list, by_slot, ctr, fc, recs, extra, cutoff_tab);
-    else if (f16) project_kernel<true, false><<<blocks, 128, 0, stream>>>(pos, sh, rot, so, index_list, by_slot, ctr, fc, recs, extra, cutoff_tab);
-    else if (blocked) project_kernel<false, true><<<blocks, 128, 0, stream>>>(pos, sh, rot, so, index_list, by_slot, ctr, fc, recs, extra, cutoff_tab);
-    else project_kernel<false, false><<<blocks, 128, 0, stream>>>(pos, sh, rot, so, index_list, by_slot, ctr, fc, recs, extra, cutoff_tab);
+    if (f16 && blocked) project_kernel<true, true><<<blocks, 128, 0, stream>>>(pos, sh, rot, so, index_list, by_slot, ctr, fc, recs, extra, cutoff_tab, aux);
+    else if (f16) project_kernel<true, false><<<blocks, 128, 0, stream>>>(pos, sh, rot, so, index_list, by_slot, ctr, fc, recs, extra, cutoff_tab, aux);
+    else if (blocked) project_kernel<false, true><<<blocks, 128, 0, stream>>>(pos, sh, rot, so, index_list, by_slot, ctr, fc, recs, extra, cutoff_tab, aux);
+    else project_kernel<false, false><<<blocks, 128, 0, stream>>>(pos, sh, rot, so, index_list, by_slot, ctr, fc, recs, extra, cutoff_tab, aux);
 }
 
 }  // namespace bgs

@@ -129,15 +129,21 @@ constexpr uint32_t SM_LIST = SM_Q2 + RT_CHUNK * 16;   // u16 [8][256]: per-warp 
 constexpr uint32_t SM_EXTRA = SM_LIST + (RT_THREADS / 32) * RT_CHUNK * 2;   // MODE 2 only: 4 x float4 [256]
 constexpr uint32_t SM_BYTES = SM_EXTRA;
 constexpr uint32_t SM_BYTES_2D = SM_EXTRA + 4 * RT_CHUNK * 16;
+// AUX (bgs_render_aux): 2 x float4 [256] after the mode's own arrays: depth rgb, normal rgb of the staged splats
+
 
 // MODE 0: USE_OBB quad-uv falloff (3DGS, and 2DGS without aabb)   gaussian.wgsl:474-504
 // MODE 1: 3DGS USE_AABB conic falloff                              gaussian.wgsl:459-471
 // MODE 2: 2DGS USE_AABB ray-splat intersection                     gaussian.wgsl:441-458, gaussian_2d.wgsl:134-156
-template <int MODE>
-__global__ void __launch_bounds__(RT_THREADS, MODE == 0 ? 6 : 5)
+// AUX: the same pass also blends the splats' Depth and Normal colour sources (aux records, 2 x float4 per splat) into two
+// more frames with the very same alphas: config C4's colour + depth + normal outputs cost one pass, not three.
+template <int MODE, bool AUX>
+__global__ void __launch_bounds__(RT_THREADS, (MODE == 0 && !AUX) ? 6 : 5)
 raster_kernel(const SplatRec* __restrict__ recs, const float4* __restrict__ extra, const uint32_t* __restrict__ tile_entries,
-              const uint2* __restrict__ ranges, int W, int H, int tiles_x, void* __restrict__ out, uint32_t format) {
-    __shared__ __align__(16) unsigned char s_mem[MODE == 2 ? SM_BYTES_2D : SM_BYTES];
+              const uint2* __restrict__ ranges, int W, int H, int tiles_x, void* __restrict__ out, uint32_t format,
+              const float4* __restrict__ aux, void* __restrict__ out_depth, void* __restrict__ out_normal) {
+    __shared__ __align__(16) unsigned char s_mem[(MODE == 2 ? SM_BYTES_2D : SM_BYTES) + (AUX ? 2 * RT_CHUNK * 16 : 0)];
+    constexpr uint32_t SM_AUX = MODE == 2 ? SM_BYTES_2D : SM_BYTES;
     __shared__ __align__(16) uint32_t s_ent[2][ENT_WORDS];    // TMA destination: the tile's pair-list chunks
     __shared__ __align__(8) unsigned long long s_bar[2];
     __shared__ __align__(8) float2 s_thr[MODE == 0 ? RT_CHUNK : 1];   // MODE 0: per staged splat cull thresholds (u, v)
@@ -165,7 +171,13 @@ raster_kernel(const SplatRec* __restrict__ recs, const float4* __restrict__ extr
     const uint32_t a_bar = (uint32_t)__cvta_generic_to_shared(&s_bar[0]);
     if (range.x >= range.y) {            // empty tile: nothing to stage (uniform across the CTA)
         // (blend-over mode leaves the target's pixels as they are)
-        if (inside && !((format >> 8) & OUT_OVER)) write_pixel(out, format, (size_t)py * W + px, 0.f, 0.f, 0.f, 1.0f);
+        if (inside && !((format >> 8) & OUT_OVER)) {
+            write_pixel(out, format, (size_t)py * W + px, 0.f, 0.f, 0.f, 1.0f);
+            if (AUX) {
+                write_pixel(out_depth, format, (size_t)py * W + px, 0.f, 0.f, 0.f, 1.0f);
+                write_pixel(out_normal, format, (size_t)py * W + px, 0.f, 0.f, 0.f, 1.0f);
+            }
+        }
         return;
     }
     // tiles with more than one chunk stream their pair list through the TMA double buffer (the next chunk's
@@ -183,6 +195,7 @@ raster_kernel(const SplatRec* __restrict__ recs, const float4* __restrict__ extr
     }
 
     float T = inside ? 1.0f : 0.0f, cr = 0.0f, cg = 0.0f, cb = 0.0f;   // T < T_STOP <=> this pixel is done
+    float dr = 0.0f, dg = 0.0f, db = 0.0f, nr = 0.0f, ng = 0.0f, nb = 0.0f;   // AUX: depth / normal frames
     for (uint32_t base = range.x; base < range.y; base += RT_CHUNK, ++chunk) {
         if (__syncthreads_count(T < T_STOP ? 0 : 1) == 0) break;   // also fences reuse of the staging buffers
         const uint32_t cnt = min((uint32_t)RT_CHUNK, range.y - base);
@@ -218,6 +231,11 @@ raster_kernel(const SplatRec* __restrict__ recs, const float4* __restrict__ extr
 #pragma unroll
                 for (int q = 0; q < 4; ++q) s_ex[q * RT_CHUNK + t] = __ldg(ep + q);
             }
+            if (AUX) {
+                float4* s_ax = reinterpret_cast<float4*>(s_mem + SM_AUX);
+                s_ax[t] = __ldg(aux + (size_t)r * 2);
+                s_ax[RT_CHUNK + t] = __ldg(aux + (size_t)r * 2 + 1);
+            }
         }
         __syncthreads();
         // each warp compacts the chunk to the splats whose bbox touches its 8x4 pixels (order kept)
@@ -247,7 +265,7 @@ raster_kernel(const SplatRec* __restrict__ recs, const float4* __restrict__ extr
             }
             __syncwarp();
         }
-        if (MODE == 0) {
+        if (MODE == 0 && !AUX) {
             // two candidates per iteration: one 32-bit load brings both list entries, the four record loads and both
             // coverage tests are independent (ILP), loop control is paid once; blending stays strictly in list order
             if (!(T < T_STOP)) {
@@ -359,6 +377,13 @@ raster_kernel(const SplatRec* __restrict__ recs, const float4* __restrict__ extr
                 const float a = fminf(e * opac, 0.999f);
                 const float w = a * T;
                 cr = fmaf(w, q2.x, cr); cg = fmaf(w, q2.y, cg); cb = fmaf(w, q2.z, cb);
+                if (AUX) {
+                    float4 ad, an;
+                    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(ad.x), "=f"(ad.y), "=f"(ad.z), "=f"(ad.w) : "r"(a_rec + SM_AUX));
+                    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(an.x), "=f"(an.y), "=f"(an.z), "=f"(an.w) : "r"(a_rec + SM_AUX + RT_CHUNK * 16));
+                    dr = fmaf(w, ad.x, dr); dg = fmaf(w, ad.y, dg); db = fmaf(w, ad.z, db);
+                    nr = fmaf(w, an.x, nr); ng = fmaf(w, an.y, ng); nb = fmaf(w, an.z, nb);
+                }
                 T = fmaf(-a, T, T);
                 if (T < T_STOP) break;
             }
@@ -369,6 +394,10 @@ raster_kernel(const SplatRec* __restrict__ recs, const float4* __restrict__ extr
         mbar_wait(a_bar + 8u * (chunk & 1u), (chunk >> 1) & 1u);
     if (!inside) return;
     write_pixel(out, format, (size_t)py * W + px, cr, cg, cb, T);
+    if (AUX) {
+        write_pixel(out_depth, format, (size_t)py * W + px, dr, dg, db, T);
+        write_pixel(out_normal, format, (size_t)py * W + px, nr, ng, nb, T);
+    }
 }
 
 // ---- MODE 0 fast path: 2 horizontally adjacent pixels per thread -----------------------------------------
@@ -537,23 +566,30 @@ raster2_kernel(const SplatRec* __restrict__ recs, const uint32_t* __restrict__ t
 
 void launch_raster(int mode, bool large_footprints, const SplatRec* recs, const float4* extra, const uint32_t* tile_entries,
                    const uint2* ranges, int W, int H, int tiles_x, int tiles_y, void* out, uint32_t format,
-                   cudaStream_t stream) {
+                   const float4* aux, void* out_depth, void* out_normal, cudaStream_t stream) {
+    const int grid = tiles_x * tiles_y;
+    if (aux != nullptr) {          // colour + depth + normal in one pass (bgs_render_aux)
+        if (mode == 0) raster_kernel<0, true><<<grid, RT_THREADS, 0, stream>>>(recs, extra, tile_entries, ranges, W, H, tiles_x, out, format, aux, out_depth, out_normal);
+        else if (mode == 1) raster_kernel<1, true><<<grid, RT_THREADS, 0, stream>>>(recs, extra, tile_entries, ranges, W, H, tiles_x, out, format, aux, out_depth, out_normal);
+        else raster_kernel<2, true><<<grid, RT_THREADS, 0, stream>>>(recs, extra, tile_entries, ranges, W, H, tiles_x, out, format, aux, out_depth, out_normal);
+        return;
+    }
     // measured on B200: the 2-pixels-per-thread variant wins when splats cover many tiles (C2 raw, scale 1:
     // 131 -> 117 us) and loses when most splats are a few pixels (C3, scale 0.02: 178 -> 217 us)
     if (mode == 0 && large_footprints)
-        raster2_kernel<false><<<tiles_x * tiles_y, R2_THREADS, 0, stream>>>(recs, tile_entries, ranges, W, H, tiles_x, out, format,
-                                                                            nullptr, nullptr, nullptr, 1, 1);
+        raster2_kernel<false><<<grid, R2_THREADS, 0, stream>>>(recs, tile_entries, ranges, W, H, tiles_x, out, format,
+                                                               nullptr, nullptr, nullptr, 1, 1);
     else if (mode == 0) {
         // experiment knob: pad the CTA's shared memory so fewer raster CTAs fit per SM and kernels of another
         // in-flight frame can co-run (BGS_RASTER_PAD = bytes of dynamic shared memory, default 0)
         static int pad = -1;
         if (pad < 0) { const char* e = getenv("BGS_RASTER_PAD"); pad = e ? atoi(e) : 0; }
-        raster_kernel<0><<<tiles_x * tiles_y, RT_THREADS, pad, stream>>>(recs, extra, tile_entries, ranges, W, H, tiles_x, out, format);
+        raster_kernel<0, false><<<grid, RT_THREADS, pad, stream>>>(recs, extra, tile_entries, ranges, W, H, tiles_x, out, format, nullptr, nullptr, nullptr);
     }
     else if (mode == 1)
-        raster_kernel<1><<<tiles_x * tiles_y, RT_THREADS, 0, stream>>>(recs, extra, tile_entries, ranges, W, H, tiles_x, out, format);
+        raster_kernel<1, false><<<grid, RT_THREADS, 0, stream>>>(recs, extra, tile_entries, ranges, W, H, tiles_x, out, format, nullptr, nullptr, nullptr);
     else
-        raster_kernel<2><<<tiles_x * tiles_y, RT_THREADS, 0, stream>>>(recs, extra, tile_entries, ranges, W, H, tiles_x, out, format);
+        raster_kernel<2, false><<<grid, RT_THREADS, 0, stream>>>(recs, extra, tile_entries, ranges, W, H, tiles_x, out, format, nullptr, nullptr, nullptr);
 }
 
 // One front-to-back round of a chunked frame (quad-uv records only); see raster2_kernel.

@@ -142,6 +142,19 @@ class GaussianSplattingPlugin:
         self._check(st)
         return out if to_host else None
 
+    def render_view_aux(self, handle: PlanarGaussian3dHandle, settings: CloudSettings, view: View,
+                        transform: CloudTransform | None = None, fmt: str = "rgba32f"):
+        """Colour, depth and normal frames of one view in ONE pass (`bgs_render_aux`, BASELINE.json config 4)."""
+        code, dtype, ch = self.FORMATS[fmt]
+        v = view.to_abi()
+        u = self.cloud_uniform(settings, transform, handle.aabb)
+        s = settings.to_abi()
+        outs = [np.empty((view.height, view.width, ch), dtype) for _ in range(3)]
+        st = self._lib.bgs_render_aux(self._ctx, handle._h, C.byref(v), C.byref(u), C.byref(s), _ptr(outs[0]), _ptr(outs[1]),
+                                      _ptr(outs[2]), code, 0)
+        self._check(st)
+        return outs
+
     def sync(self) -> bool:
         """Complete the frames enqueued with `asynchronous=True`.  False = the last frame must be rendered again
         (its pair list outgrew the buffer, which has been grown)."""

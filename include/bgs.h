@@ -129,6 +129,16 @@ bgs_status bgs_render(bgs_context* ctx, const bgs_cloud* cloud, const bgs_view* 
                       const bgs_cloud_uniform* uniform, const bgs_settings* settings, void* out_rgba,
                       uint32_t out_format, int out_is_device_ptr);
 
+/* Colour + depth + normal frames of one view in ONE pass (BASELINE.json config 4: "2M-surfel 2dgs cloud with depth+normal
+ * outputs").  out_rgba gets the frame bgs_render would produce with `settings` as given; out_depth / out_normal get, bit
+ * for bit, the frames bgs_render would produce with rasterize_mode = Depth / Normal (gaussian.wgsl:329-368,
+ * material/depth.wgsl:3-11): the splats' geometry, order and alpha do not depend on the colour source, so the extra
+ * colours ride along (two more float3 per projected record, six more FMAs per blend).  All three frames share
+ * out_format and the host/device kind of the pointers.  Synchronous only. */
+bgs_status bgs_render_aux(bgs_context* ctx, const bgs_cloud* cloud, const bgs_view* view,
+                          const bgs_cloud_uniform* uniform, const bgs_settings* settings, void* out_rgba,
+                          void* out_depth, void* out_normal, uint32_t out_format, int out_is_device_ptr);
+
 /* Wait for every frame enqueued with BGS_FLAG_ASYNC.  BGS_OK: the last frame is complete and valid.
  * BGS_NOT_READY: the last frame's (splat, tile) pair list outgrew its buffer (scene/camera changed a
  * lot); the buffer has been grown -- render that frame again.  A no-op after a synchronous render. */

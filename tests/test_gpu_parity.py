@@ -605,3 +605,31 @@ def test_compositing_over_target_and_premultiplied(plugin, oracle):
         assert plugin.frame_stats().rounds > 1 and np.array_equal(rounds, layer)
     finally:
         h_far.destroy(); h_near.destroy()
+
+
+@pytest.mark.parametrize("gm,aabb,n,scale", [(B.GaussianMode.Gaussian2d, True, 40000, 0.12), (B.GaussianMode.Gaussian3d, False, 30000, 0.2),
+                                             (B.GaussianMode.Gaussian3d, True, 20000, 0.25)])
+def test_aux_depth_normal_frames_in_one_pass(plugin, oracle, gm, aabb, n, scale):
+    """Row f2 / config C4: bgs_render_aux delivers colour + depth + normal frames from ONE pass; each must be the frame the
+    corresponding single-mode bgs_render produces (gaussian.wgsl:329-368, material/depth.wgsl:3-11) -- bit for bit -- and so
+    match the oracle's three single-mode frames within the pixel tolerance."""
+    import dataclasses
+
+    cloud = B.random_gaussians_3d_seeded(n, 41)
+    view = B.orbit_view(3, 8, 480, 270)
+    s = B.CloudSettings(global_scale=scale, gaussian_mode=gm, aabb=aabb)
+    h = plugin.add_cloud(cloud)
+    try:
+        colour, depth, normal = plugin.render_view_aux(h, s, view, fmt="rgba32f")
+        for got, mode in ((colour, B.RasterizeMode.Color), (depth, B.RasterizeMode.Depth), (normal, B.RasterizeMode.Normal)):
+            sm = dataclasses.replace(s, rasterize_mode=mode)
+            single = plugin.render_view(h, sm, view, fmt="rgba32f")
+            assert np.array_equal(got, single), mode
+            want = oracle.render_tiles(cloud, view.to_abi(), plugin.cloud_uniform(sm, None, h.aabb), sm.to_abi())["image"]
+            assert np.abs(got - want).max() <= PIXEL_TOL, mode
+        assert np.abs(depth - colour).max() > 0.05 and np.abs(normal - colour).max() > 0.05
+        c8, d8, n8 = plugin.render_view_aux(h, s, view, fmt="rgba8_srgb")
+        assert np.array_equal(c8, plugin.render_view(h, s, view, fmt="rgba8_srgb"))
+        assert np.array_equal(n8, plugin.render_view(h, dataclasses.replace(s, rasterize_mode=B.RasterizeMode.Normal), view, fmt="rgba8_srgb"))
+    finally:
+        h.destroy()
