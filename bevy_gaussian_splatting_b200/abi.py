@@ -80,6 +80,7 @@ SYMBOLS = [
     ("bgs_context_destroy", None, [_P]),
     ("bgs_cloud_upload_f32", C.c_int, [_P, C.c_uint32, _P, _P, _P, _P, C.POINTER(_P)]),
     ("bgs_cloud_upload_f16", C.c_int, [_P, C.c_uint32, _P, _P, _P, C.POINTER(_P)]),
+    ("bgs_cloud_upload_f16_cov", C.c_int, [_P, C.c_uint32, _P, _P, _P, C.POINTER(_P)]),
     ("bgs_cloud_destroy", None, [_P]),
     ("bgs_render", C.c_int, [_P, _P, C.POINTER(bgs_view), C.POINTER(bgs_cloud_uniform), C.POINTER(bgs_settings), _P,
                              C.c_uint32, C.c_int]),

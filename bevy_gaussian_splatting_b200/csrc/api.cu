@@ -67,6 +67,7 @@ struct bgs_cloud {
     int device;             // the CUDA device the planes live on
     uint32_t n;
     bool f16;
+    bool cov;         // f16 layout whose second plane holds Covariance3dOpacityPacked128 records (precomputed Sigma3D)
     float4* pos;      // n * 16 B
     void* sh;         // f32: n * 192 B; f16: n * 96 B
     void* rot;        // f32: n * 16 B (w,x,y,z); f16: n * 16 B packed rotation+scale+opacity
@@ -446,7 +447,7 @@ static bgs_status upload_common(bgs_context* ctx, uint32_t n, bool f16, const fl
     CU(ctx, cudaSetDevice(ctx->device));
     bgs_cloud* cl = new (std::nothrow) bgs_cloud();
     if (!cl) return BGS_ENOMEM;
-    cl->ctx = ctx; cl->device = ctx->device; cl->n = n; cl->f16 = f16;
+    cl->ctx = ctx; cl->device = ctx->device; cl->n = n; cl->f16 = f16; cl->cov = false;
     cl->pos = nullptr; cl->sh = nullptr; cl->rot = nullptr; cl->so = nullptr; cl->blocks = nullptr;
     const size_t sh_bytes = (size_t)n * (f16 ? 96 : 192);
     cudaError_t e = cudaMalloc(&cl->pos, (size_t)n * 16);
@@ -491,6 +492,13 @@ bgs_status bgs_cloud_upload_f32(bgs_context* ctx, uint32_t n, const float* pos_v
 bgs_status bgs_cloud_upload_f16(bgs_context* ctx, uint32_t n, const float* pos_vis, const uint32_t* sh_packed,
                                 const uint32_t* rot_scale_opacity, bgs_cloud** out) {
     return upload_common(ctx, n, true, pos_vis, sh_packed, rot_scale_opacity, nullptr, out);
+}
+
+bgs_status bgs_cloud_upload_f16_cov(bgs_context* ctx, uint32_t n, const float* pos_vis, const uint32_t* sh_packed,
+                                    const uint32_t* cov3d_opacity, bgs_cloud** out) {
+    const bgs_status s = upload_common(ctx, n, true, pos_vis, sh_packed, cov3d_opacity, nullptr, out);
+    if (s == BGS_OK) (*out)->cov = true;
+    return s;
 }
 
 void bgs_cloud_destroy(bgs_cloud* cl) {
@@ -627,6 +635,8 @@ static bgs_status render_impl(bgs_context* c, const bgs_cloud* cloud, const bgs_
     if (st->rasterize_mode > BGS_RASTERIZE_POSITION)
         return fail(c, BGS_EINVAL, "render: rasterize_mode %u not supported (Color, Depth, Normal, Position are)", st->rasterize_mode);
     if (st->draw_mode > BGS_DRAW_HIGHLIGHT_SELECTED) return fail(c, BGS_EINVAL, "render: bad draw_mode");
+    if (cloud->cov && (st->gaussian_mode != BGS_GAUSSIAN_3D || st->rasterize_mode == BGS_RASTERIZE_NORMAL || want_aux))
+        return fail(c, BGS_EINVAL, "render: a precomputed-covariance cloud has no rotation / scale: Gaussian3d with Color, Depth or Position only");
     const int W = (int)view->viewport[2], H = (int)view->viewport[3];
     if (W <= 0 || H <= 0 || W > 65535 || H > 65535) return fail(c, BGS_EINVAL, "render: viewport %dx%d out of range", W, H);
     CU(c, cudaSetDevice(c->device));
@@ -659,6 +669,7 @@ static bgs_status render_impl(bgs_context* c, const bgs_cloud* cloud, const bgs_
     fc.Wi = W; fc.Hi = H; fc.tiles_x = tiles_x; fc.tiles_y = tiles_y;
     fc.n_cloud = n;
     fc.aux = want_aux ? 1u : 0u;
+    fc.cov_pre = cloud->cov ? 1u : 0u;
     memcpy(fc.aabb_min, uni->aabb_min, 12); memcpy(fc.aabb_max, uni->aabb_max, 12);
     static const float kIdentity[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
     fc.model_identity = memcmp(uni->transform, kIdentity, 64) == 0 ? 1u : 0u;   // (-0.0 entries take the general path)

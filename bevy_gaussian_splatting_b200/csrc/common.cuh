@@ -29,6 +29,7 @@ struct FrameConsts {
     uint32_t n_cloud;           // gaussians in the cloud
     uint32_t model_identity;    // CloudUniform.transform is exactly the identity (key-gen skips the multiply)
     float aabb_min[3], aabb_max[3];   // CloudUniform.min / .max (RasterizeMode::Position)
+    uint32_t cov_pre;           // the cloud carries Covariance3dOpacityPacked128 records (f16.rs:131-170) instead of rotation + scale
     uint32_t aux;               // bgs_render_aux: the projection also emits the Depth and Normal colour sources
 };
 

@@ -297,7 +297,13 @@ __device__ __forceinline__ void project_one(const FrameConsts& fc, const FrameCo
 #pragma unroll
             for (int j = 0; j < 3; ++j) TS[i][j] = (X[i][0] * A[j][0] + X[i][1] * A[j][1]) + X[i][2] * A[j][2];
         }
-        const float c3[6] = {TS[0][0], TS[1][0], TS[2][0], TS[1][1], TS[2][1], TS[2][2]};
+        float c3[6] = {TS[0][0], TS[1][0], TS[2][0], TS[1][1], TS[2][1], TS[2][2]};
+        if (fc.cov_pre) {
+            // PRECOMPUTE_COVARIANCE_3D (gaussian_3d.wgsl:78-79, planar.wgsl:133-152): the decoded record goes straight into
+            // cov2d -- no global_scale, no model 3x3.  It arrives in the plane slots it occupies: q = c0..c3, so = c4, c5,
+            // opacity, opacity
+            c3[0] = q[0]; c3[1] = q[1]; c3[2] = q[2]; c3[3] = q[3]; c3[4] = so[0]; c3[5] = so[1];
+        }
         const float Vrk[3][3] = {{c3[0], c3[1], c3[2]}, {c3[1], c3[3], c3[4]}, {c3[2], c3[4], c3[5]}};
         // helpers.wgsl:8-47
         float tv[4];

@@ -71,6 +71,26 @@ class PlanarGaussian3d:
                         (s[:, 2] << 16) | s[:, 3]], axis=1)
         return np.ascontiguousarray(sh_packed, dtype=np.uint32), np.ascontiguousarray(rso, dtype=np.uint32)
 
+    def precomputed_covariance(self) -> "PlanarGaussian3d":
+        """`Covariance3dOpacity` per gaussian (src/gaussian/f32.rs:238-251 <- covariance.rs:4-41, every product in f32, glam's
+        accumulation order), laid out in the plane slots `Covariance3dOpacityPacked128` occupies (f16.rs:131-170): rotation
+        = (c0, c1, c2, c3), scale_opacity = (c4, c5, opacity, opacity).  `pack_f16()` of the result is the record the
+        reference's PRECOMPUTE_COVARIANCE_3D layout uploads; `rounded_to_f16()` is what its shader decodes."""
+        f = np.float32
+        q, so = self.rotation.astype(f), self.scale_opacity.astype(f)
+        r, x, y, z = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
+        two, one = f(2.0), f(1.0)
+        R = np.empty((len(q), 3, 3), f)     # R[:, i, j]: row i, column j (columns = the triplets covariance.rs writes)
+        R[:, 0, 0] = one - two * (y * y + z * z); R[:, 1, 0] = two * (x * y - r * z); R[:, 2, 0] = two * (x * z + r * y)
+        R[:, 0, 1] = two * (x * y + r * z); R[:, 1, 1] = one - two * (x * x + z * z); R[:, 2, 1] = two * (y * z - r * x)
+        R[:, 0, 2] = two * (x * z - r * y); R[:, 1, 2] = two * (y * z + r * x); R[:, 2, 2] = one - two * (x * x + y * y)
+        M = (so[:, :3, None] * R).astype(f)                      # M = S R: row i scaled by s_i
+        def sg(i, j):
+            return ((M[:, 0, i] * M[:, 0, j] + M[:, 1, i] * M[:, 1, j]).astype(f) + M[:, 2, i] * M[:, 2, j]).astype(f)
+        cov_rot = np.stack([sg(0, 0), sg(0, 1), sg(0, 2), sg(1, 1)], axis=1)
+        cov_so = np.stack([sg(1, 2), sg(2, 2), so[:, 3], so[:, 3]], axis=1)
+        return PlanarGaussian3d(self.position_visibility, self.spherical_harmonic, cov_rot, cov_so)
+
     def rounded_to_f16(self) -> "PlanarGaussian3d":
         """The f32 cloud the f16 layout decodes to (position stays f32: bindings.wgsl:104-106)."""
         def rt(a):

@@ -38,7 +38,8 @@ class PlanarGaussian3dHandle:
 
     _next_serial = 0
 
-    def __init__(self, plugin: "GaussianSplattingPlugin", cloud: PlanarGaussian3d, f16: bool = False):
+    def __init__(self, plugin: "GaussianSplattingPlugin", cloud: PlanarGaussian3d, f16: bool = False,
+                 precompute_covariance: bool = False):
         PlanarGaussian3dHandle._next_serial += 1
         self.serial = PlanarGaussian3dHandle._next_serial   # never reused (id() is, once a handle is collected)
         self._plugin = plugin
@@ -47,7 +48,13 @@ class PlanarGaussian3dHandle:
         self.f16 = f16
         self.aabb = cloud.compute_aabb()        # the entity's Aabb (calculate_bounds, src/gaussian/cloud.rs:45-62)
         self._h = C.c_void_p()
-        if f16:
+        self.precompute_covariance = precompute_covariance
+        if precompute_covariance:
+            # the reference's `precompute_covariance_3d` feature: Covariance3dOpacityPacked128 in the second plane
+            sh_p, cov_op = cloud.precomputed_covariance().pack_f16()
+            st = self._lib.bgs_cloud_upload_f16_cov(plugin._ctx, self.n, _ptr(cloud.position_visibility), _ptr(sh_p),
+                                                    _ptr(cov_op), C.byref(self._h))
+        elif f16:
             sh_p, rso = cloud.pack_f16()
             st = self._lib.bgs_cloud_upload_f16(plugin._ctx, self.n, _ptr(cloud.position_visibility), _ptr(sh_p),
                                                 _ptr(rso), C.byref(self._h))
@@ -84,8 +91,8 @@ class GaussianSplattingPlugin:
         self.device = cuda_device
 
     # -- resources
-    def add_cloud(self, cloud: PlanarGaussian3d, f16: bool = False) -> PlanarGaussian3dHandle:
-        return PlanarGaussian3dHandle(self, cloud, f16)
+    def add_cloud(self, cloud: PlanarGaussian3d, f16: bool = False, precompute_covariance: bool = False) -> PlanarGaussian3dHandle:
+        return PlanarGaussian3dHandle(self, cloud, f16, precompute_covariance)
 
     def _check(self, st: int):
         if st != abi.BGS_OK:

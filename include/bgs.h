@@ -120,6 +120,13 @@ bgs_status bgs_cloud_upload_f32(bgs_context* ctx, uint32_t n, const float* pos_v
  * sh_packed n*24 words (even coefficient in the low half); rot_scale_opacity n*4 words. */
 bgs_status bgs_cloud_upload_f16(bgs_context* ctx, uint32_t n, const float* pos_vis, const uint32_t* sh_packed,
                                 const uint32_t* rot_scale_opacity, bgs_cloud** out);
+/* f16 planar layout with PRECOMPUTED 3D covariance (the reference's `precompute_covariance_3d` feature): the second plane
+ * holds Covariance3dOpacityPacked128 {cov3d: [u32; 3], opacity: u32} (f16.rs:131-170; decode planar.wgsl:133-152)
+ * instead of rotation + scale.  Projection then skips quat/scale -> Sigma3D; as in the reference shader
+ * (gaussian_3d.wgsl:78-79) neither global_scale nor the model 3x3 touch the stored covariance.  Gaussian3d with
+ * RasterizeMode Color / Depth / Position only (Normal and 2DGS need the rotation). */
+bgs_status bgs_cloud_upload_f16_cov(bgs_context* ctx, uint32_t n, const float* pos_vis, const uint32_t* sh_packed,
+                                    const uint32_t* cov3d_opacity, bgs_cloud** out);
 void bgs_cloud_destroy(bgs_cloud* cloud);
 
 /* One view of one cloud: key-gen -> depth radix sort -> projection + SH colour -> tile

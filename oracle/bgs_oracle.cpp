@@ -267,7 +267,13 @@ void project_one(const Ctx& C, const float* p4, const float* sh, const float* q,
         for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j)
             TS[i][j] = (X[i][0] * A[j][0] + X[i][1] * A[j][1]) + X[i][2] * A[j][2];
         // cov3d = (TS[0][0], TS[0][1], TS[0][2], TS[1][1], TS[1][2], TS[2][2]) in WGSL [col][row]
-        const float c3[6] = {TS[0][0], TS[1][0], TS[2][0], TS[1][1], TS[2][1], TS[2][2]};
+        float c3[6] = {TS[0][0], TS[1][0], TS[2][0], TS[1][1], TS[2][1], TS[2][2]};
+        if (s.reserved & 1u) {
+            // PRECOMPUTE_COVARIANCE_3D (gaussian_3d.wgsl:78-79, planar.wgsl:133-152): get_cov3d(index) goes straight into
+            // cov2d -- no global_scale, no model transform.  The caller hands the decoded Covariance3dOpacityPacked128 in
+            // the plane slots it occupies: rotation = (c0, c1, c2, c3), scale_opacity = (c4, c5, opacity, opacity).
+            c3[0] = q[0]; c3[1] = q[1]; c3[2] = q[2]; c3[3] = q[3]; c3[4] = so[0]; c3[5] = so[1];
+        }
         float Vrk[3][3] = {{c3[0], c3[1], c3[2]}, {c3[1], c3[3], c3[4]}, {c3[2], c3[4], c3[5]}};
         // ---- helpers.wgsl:8-47
         float t[4];
@@ -622,6 +628,24 @@ void orc_decode_f16(uint32_t n, const uint32_t* sh_packed, const uint32_t* rso, 
         rot[4 * i + 2] = hi(rso[4 * i + 1]); rot[4 * i + 3] = lo(rso[4 * i + 1]);
         so[4 * i + 0] = hi(rso[4 * i + 2]); so[4 * i + 1] = lo(rso[4 * i + 2]);
         so[4 * i + 2] = hi(rso[4 * i + 3]); so[4 * i + 3] = lo(rso[4 * i + 3]);
+    }
+}
+
+// src/gaussian/covariance.rs:4-41 (compute_covariance_3d, the source of Covariance3dOpacity, f32.rs:238-251): Sigma = M^T M,
+// M = S R, R's columns as written there, upper triangle (xx, xy, xz, yy, yz, zz).  glam's Mat3 products accumulate
+// column by column: ((a0 b0 + a1 b1) + a2 b2).
+void orc_covariance_3d(uint32_t n, const float* rot, const float* so, float* cov6) {
+    for (uint32_t g = 0; g < n; ++g) {
+        const float* q = rot + 4 * (size_t)g; const float* s3 = so + 4 * (size_t)g;
+        float Rm[3][3];
+        rotation_rows(q, Rm);                       // Rm[i][j]: row i, column j of R (columns = the written triplets)
+        float M[3][3];
+        for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) M[i][j] = s3[i] * Rm[i][j];
+        float Sg[3][3];
+        for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j)
+            Sg[i][j] = (M[0][i] * M[0][j] + M[1][i] * M[1][j]) + M[2][i] * M[2][j];
+        float* o = cov6 + 6 * (size_t)g;
+        o[0] = Sg[0][0]; o[1] = Sg[0][1]; o[2] = Sg[0][2]; o[3] = Sg[1][1]; o[4] = Sg[1][2]; o[5] = Sg[2][2];
     }
 }
 

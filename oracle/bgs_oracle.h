@@ -74,6 +74,12 @@ void orc_pack_f16(uint32_t n, const float* sh, const float* rot, const float* sc
 void orc_decode_f16(uint32_t n, const uint32_t* sh_packed, const uint32_t* rso_packed,
                     float* sh, float* rot, float* scale_opacity);
 
+/* f3: src/gaussian/covariance.rs:4-41 -- the f32 upper triangle that Covariance3dOpacityPacked128 stores as f16
+ * (f16.rs:131-170).  With orc_settings.reserved bit 0 set, projection / rendering read the decoded record from the
+ * plane slots it occupies (rotation = c0..c3, scale_opacity = c4, c5, opacity, opacity) and skip Sigma = M^T M,
+ * global_scale and the model 3x3, as PRECOMPUTE_COVARIANCE_3D does (gaussian_3d.wgsl:78-79). */
+void orc_covariance_3d(uint32_t n, const float* rot, const float* scale_opacity, float* cov6);
+
 /* a4+a5: per-gaussian projection + colour for the listed ids (gaussian.wgsl:185-436) */
 int orc_project(uint32_t n, const float* pos_vis, const float* sh, const float* rot,
                 const float* scale_opacity, const orc_view* view, const orc_uniform* u,

@@ -111,6 +111,13 @@ def decode_f16(shp, rso):
     return sh, rot, so
 
 
+def covariance_3d(rot: np.ndarray, so: np.ndarray) -> np.ndarray:
+    n = len(rot)
+    out = np.empty((n, 6), np.float32)
+    load().orc_covariance_3d(C.c_uint32(n), _p(np.ascontiguousarray(rot, np.float32)), _p(np.ascontiguousarray(so, np.float32)), _p(out))
+    return out
+
+
 def project(cloud, view, uniform, settings, ids: np.ndarray) -> np.ndarray:
     ids = np.ascontiguousarray(ids, np.uint32)
     out = np.zeros(len(ids), SPLAT_DTYPE)

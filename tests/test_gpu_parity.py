@@ -24,11 +24,15 @@ def _uniform(s):
     return B.GaussianSplattingPlugin.cloud_uniform(s)
 
 
-def check_against_oracle(plugin, oracle, cloud, settings, view, f16=False, pixel_tol=PIXEL_TOL, ref_mode_too=False):
-    h = plugin.add_cloud(cloud, f16=f16)
+def check_against_oracle(plugin, oracle, cloud, settings, view, f16=False, pixel_tol=PIXEL_TOL, ref_mode_too=False, cov=False):
+    h = plugin.add_cloud(cloud, f16=f16, precompute_covariance=cov)
     try:
         img = plugin.render_view(h, settings, view, fmt="rgba32f")
         oc = cloud.rounded_to_f16() if f16 else cloud
+        if cov:      # row f3: the oracle reads the decoded Covariance3dOpacityPacked128 from the plane slots it occupies
+            oc = cloud.precomputed_covariance().rounded_to_f16()
+        s_abi = settings.to_abi()
+        s_abi.reserved = 1 if cov else 0
         u = plugin.cloud_uniform(settings, None, h.aabb)
         bits = int(settings.radix_sort_depth_bits)
         keys = oracle.keygen(oc.position_visibility, view.to_abi(), u, bits)
@@ -36,14 +40,14 @@ def check_against_oracle(plugin, oracle, cloud, settings, view, f16=False, pixel
         got = plugin.sorted_entries()
         assert np.array_equal(got[:, 0], sk), "sorted keys differ (must be bit-exact)"
         assert np.array_equal(got[:, 1], si), "sort permutation differs (must be bit-exact)"
-        til = oracle.render_tiles(oc, view.to_abi(), u, settings.to_abi())
+        til = oracle.render_tiles(oc, view.to_abi(), u, s_abi)
         fs = plugin.frame_stats()
         assert fs.n_visible == til["n_vis"] and fs.n_pairs == til["n_pairs"]
         assert np.array_equal(plugin.tile_ranges(), til["tile_ranges"]), "tile ranges differ (must be bit-exact)"
         assert np.array_equal(plugin.tile_entries(), til["tile_entries"]), "per-tile slices differ"
         rec, ids = plugin.projected()
         assert np.array_equal(ids, til["rank_to_id"])
-        orec = oracle.project(oc, view.to_abi(), u, settings.to_abi(), til["rank_to_id"])
+        orec = oracle.project(oc, view.to_abi(), u, s_abi, til["rank_to_id"])
         drawn = orec["xlo"] <= orec["xhi"]
         if settings.aabb and settings.gaussian_mode == B.GaussianMode.Gaussian3d:
             # USE_AABB record: centre, conic x/y/z, quad half-side
@@ -63,7 +67,7 @@ def check_against_oracle(plugin, oracle, cloud, settings, view, f16=False, pixel
         assert err <= pixel_tol, f"pixel L-inf {err}"
         if ref_mode_too:
             # the reference's own semantics (instanced quads blended back-to-front, no tiles, no early-out), directly
-            ref = oracle.render_ref(oc, view.to_abi(), u, settings.to_abi())
+            ref = oracle.render_ref(oc, view.to_abi(), u, s_abi)
             err_ref = float(np.abs(img - ref).max())
             assert err_ref <= pixel_tol, f"pixel L-inf {err_ref} vs the oracle's ref_mode"
         # the second frame picks kernel variants from the first frame's counts (sort tile size, raster variant)
@@ -631,5 +635,25 @@ def test_aux_depth_normal_frames_in_one_pass(plugin, oracle, gm, aabb, n, scale)
         c8, d8, n8 = plugin.render_view_aux(h, s, view, fmt="rgba8_srgb")
         assert np.array_equal(c8, plugin.render_view(h, s, view, fmt="rgba8_srgb"))
         assert np.array_equal(n8, plugin.render_view(h, dataclasses.replace(s, rasterize_mode=B.RasterizeMode.Normal), view, fmt="rgba8_srgb"))
+    finally:
+        h.destroy()
+
+
+def test_parity_precomputed_covariance_plane(plugin, oracle):
+    """Row f3: `Covariance3dOpacityPacked128` clouds (the reference's precompute_covariance_3d layout, f16.rs:131-170,
+    planar.wgsl:133-152, gaussian_3d.wgsl:78-79): same bit-exact / 1e-3 bars as the other layouts."""
+    cloud = B.random_gaussians_3d_seeded(30000, 19)
+    cloud.scale_opacity[:, :3] *= np.float32(0.15)          # (the stored covariance ignores global_scale: scale the cloud itself)
+    for view, kw in ((B.headless_view(480, 270), {}), (B.orbit_view(5, 8, 417, 233), dict(rasterize_mode=B.RasterizeMode.Depth)),
+                     (B.orbit_view(2, 8, 320, 200), dict(aabb=True, global_scale=7.0))):      # global_scale must NOT matter
+        check_against_oracle(plugin, oracle, cloud, B.CloudSettings(**kw), view, f16=True, cov=True)
+    h = plugin.add_cloud(cloud, precompute_covariance=True)
+    try:
+        a = plugin.render_view(h, B.CloudSettings(), B.headless_view(320, 200))
+        b = plugin.render_view(h, B.CloudSettings(global_scale=3.0), B.headless_view(320, 200))
+        assert np.array_equal(a, b)
+        for bad in (dict(rasterize_mode=B.RasterizeMode.Normal), dict(gaussian_mode=B.GaussianMode.Gaussian2d)):
+            with pytest.raises(B.BgsError):
+                plugin.render_view(h, B.CloudSettings(**bad), B.headless_view(320, 200))
     finally:
         h.destroy()

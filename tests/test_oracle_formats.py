@@ -54,3 +54,33 @@ def test_fixed_series_ln(oracle):
     assert lib.orc_ln(float("inf")) == np.inf
     sub = np.float32(1e-42)
     assert abs(lib.orc_ln(float(sub)) - np.log(np.float64(sub))) < 1e-4
+
+
+def test_precomputed_covariance_form_matches_covariance_rs(oracle):
+    """Row f3: the host's `Covariance3dOpacity` (PlanarGaussian3d.precomputed_covariance, numpy f32) against the oracle's
+    restatement of src/gaussian/covariance.rs:4-41, bit for bit, and its f16 packing (Covariance3dOpacityPacked128,
+    f16.rs:131-170: pack(upper, lower) words, opacity in both halves)."""
+    import numpy as np
+    import bevy_gaussian_splatting_b200 as B
+
+    cloud = B.random_gaussians_3d_seeded(5000, 3)
+    cov = cloud.precomputed_covariance()
+    want = oracle.covariance_3d(cloud.rotation, cloud.scale_opacity)
+    got = np.concatenate([cov.rotation, cov.scale_opacity[:, :2]], axis=1)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    assert np.array_equal(cov.scale_opacity[:, 2], cloud.scale_opacity[:, 3]) and np.array_equal(cov.scale_opacity[:, 3], cloud.scale_opacity[:, 3])
+    # symmetric positive semi-definite, and equal to an independent float64 evaluation
+    q, s = cloud.rotation.astype(np.float64), cloud.scale_opacity[:, :3].astype(np.float64)
+    r, x, y, z = q.T
+    R = np.stack([np.stack([1 - 2 * (y * y + z * z), 2 * (x * y + r * z), 2 * (x * z - r * y)], 1),
+                  np.stack([2 * (x * y - r * z), 1 - 2 * (x * x + z * z), 2 * (y * z + r * x)], 1),
+                  np.stack([2 * (x * z + r * y), 2 * (y * z - r * x), 1 - 2 * (x * x + y * y)], 1)], 1)   # R[:, row, col]
+    M = s[:, :, None] * R
+    S64 = np.einsum("nki,nkj->nij", M, M)
+    ref = np.stack([S64[:, 0, 0], S64[:, 0, 1], S64[:, 0, 2], S64[:, 1, 1], S64[:, 1, 2], S64[:, 2, 2]], 1)
+    assert np.abs(want - ref).max() <= 1e-5 * np.abs(ref).max()
+    sh_p, words = cov.pack_f16()
+    h = cov.rounded_to_f16()
+    dec = oracle.decode_f16(sh_p, words)
+    assert np.array_equal(dec[1], h.rotation) and np.array_equal(dec[2], h.scale_opacity)
+    assert np.array_equal(words[:, 3] >> 16, words[:, 3] & 0xFFFF)        # opacity packed in both halves
