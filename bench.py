@@ -266,8 +266,9 @@ def run_cuda(args):
     settings = B.CloudSettings(global_scale=GLOBAL_SCALE)
     sessions = []
     for i, p in enumerate(plugins):
+        share = os.environ.get("BGS_SHARED_COMM", "1") != "0"        # (tuning knob: one communicator per context instead)
         sessions.append(MultiViewSession(rank, world, 0, plugin=p if world > 1 else None,
-                                         share_comm_of=sessions[0] if (world > 1 and i > 0) else None))
+                                         share_comm_of=sessions[0] if (world > 1 and i > 0 and share) else None))
     sess = sessions[0]
     view = sess.view(WIDTH, HEIGHT) if world > 1 else B.headless_view(WIDTH, HEIGHT)
     frame_bytes = WIDTH * HEIGHT * 4

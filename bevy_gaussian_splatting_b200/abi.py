@@ -98,6 +98,9 @@ SYMBOLS = [
     ("bgs_context_copy_stream", _P, [_P]),
     ("bgs_frame_device_ptr", _P, [_P]),
     ("bgs_last_launch_count", C.c_uint32, [_P]),
+    ("bgs_frame_export_create", C.c_int, [C.c_int, C.c_size_t, C.POINTER(_P), C.POINTER(C.c_int), C.POINTER(C.c_size_t)]),
+    ("bgs_frame_export_import", C.c_int, [C.c_int, C.c_int, C.c_size_t, C.POINTER(_P)]),
+    ("bgs_frame_export_destroy", None, [_P]),
     ("bgs_nccl_unique_id", C.c_int, [_P]),
     ("bgs_nccl_comm_init", C.c_int, [_P, C.c_int, C.c_int, _P, C.POINTER(_P)]),
     ("bgs_nccl_comm_destroy", None, [_P]),

@@ -480,14 +480,41 @@ raster2_kernel(const SplatRec* __restrict__ recs, const uint32_t* __restrict__ t
             if (done) range.y = range.x;
         }
     }
-    for (uint32_t base = range.x; base < range.y; base += RT_CHUNK) {
+    // multi-chunk tiles (the norm on this path: heavy footprints put thousands of entries in a tile) stream their slice of
+    // the sorted pair list through the TMA double buffer, like raster_kernel: chunk k + 1's bulk copy (UBLKCP, mbarrier
+    // complete_tx) is in flight while chunk k is blended
+    __shared__ __align__(16) uint32_t s_ent[2][ENT_WORDS];
+    __shared__ __align__(8) unsigned long long s_bar[2];
+    const uint32_t a_ent = (uint32_t)__cvta_generic_to_shared(&s_ent[0][0]);
+    const uint32_t a_bar = (uint32_t)__cvta_generic_to_shared(&s_bar[0]);
+    const bool use_tma = range.y > range.x && range.y - range.x > (uint32_t)RT_CHUNK;
+    uint32_t issued = 0u, chunk = 0u;
+    if (use_tma) {
+        if (t == 0) {
+            mbar_init(a_bar, 1u); mbar_init(a_bar + 8u, 1u);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (t == 0) issue_entries(tile_entries, range.x, (uint32_t)RT_CHUNK, a_ent, a_bar, 0);
+        issued = 1u;
+    }
+    for (uint32_t base = range.x; base < range.y; base += RT_CHUNK, ++chunk) {
         if (__syncthreads_count((lim0 > 0.f || lim1 > 0.f) ? 1 : 0) == 0) break;   // also fences smem reuse
         const uint32_t cnt = min((uint32_t)RT_CHUNK, range.y - base);
+        const int buf = (int)(chunk & 1u);
+        if (use_tma) {
+            // prefetch the NEXT chunk's entries (its buffer was last read two iterations ago: the vote above fenced it)
+            if (base + RT_CHUNK < range.y) {
+                if (t == 0) issue_entries(tile_entries, base + RT_CHUNK, min((uint32_t)RT_CHUNK, range.y - base - RT_CHUNK), a_ent, a_bar, buf ^ 1);
+                ++issued;
+            }
+            mbar_wait(a_bar + 8u * buf, (chunk >> 1) & 1u);
+        }
 #pragma unroll
         for (int k = 0; k < RT_CHUNK / R2_THREADS; ++k) {
             const uint32_t j = t + k * R2_THREADS;
             if (j < cnt) {
-                const uint32_t r = __ldg(tile_entries + base + j);
+                const uint32_t r = use_tma ? s_ent[buf][(base & 3u) + j] : __ldg(tile_entries + base + j);
                 const float4* rp = reinterpret_cast<const float4*>(recs + r);
                 s_q0[j] = __ldg(rp);
                 s_uv[j] = __ldg(rp + 1);
@@ -551,6 +578,8 @@ raster2_kernel(const SplatRec* __restrict__ recs, const uint32_t* __restrict__ t
             }
         }
     }
+    // an early exit (all pixels saturated) may leave one prefetch in flight: keep the CTA alive until it lands
+    if (t == 0 && issued > chunk) mbar_wait(a_bar + 8u * (chunk & 1u), (chunk >> 1) & 1u);
     if (CHUNKED && !last) {
         st[0] = make_float4(r0, g0, b0, T0);
         st[1] = make_float4(r1, g1, b1, T1);

@@ -162,6 +162,15 @@ class GaussianSplattingPlugin:
         self._check(st)
         return outs
 
+    def render_view_to_device(self, handle: PlanarGaussian3dHandle, settings: CloudSettings, view: View, device_ptr: int,
+                              transform: CloudTransform | None = None, fmt: str = "rgba8_srgb") -> None:
+        """Render straight into caller-owned device memory (e.g. an exported frame target: `bgs_frame_export_create`)."""
+        code, _, _ = self.FORMATS[fmt]
+        v = view.to_abi()
+        u = self.cloud_uniform(settings, transform, handle.aabb)
+        s = settings.to_abi()
+        self._check(self._lib.bgs_render(self._ctx, handle._h, C.byref(v), C.byref(u), C.byref(s), C.c_void_p(device_ptr), code, 1))
+
     def sync(self) -> bool:
         """Complete the frames enqueued with `asynchronous=True`.  False = the last frame must be rendered again
         (its pair list outgrew the buffer, which has been grown)."""

@@ -180,6 +180,18 @@ const void* bgs_frame_device_ptr(bgs_context* ctx);
 /* Kernel launches issued by the last bgs_render. */
 uint32_t bgs_last_launch_count(const bgs_context* ctx);
 
+/* Frame hand-back without a copy.  bgs_frame_export_create allocates a frame target in memory that is
+ * exportable as a POSIX file descriptor: pass *out_device_ptr to bgs_render as out_rgba with out_is_device_ptr = 1, and
+ * hand *out_fd (+ *out_alloc_bytes) to the graphics API -- Vulkan / wgpu-hal import it with VK_KHR_external_memory_fd
+ * (VkImportMemoryFdInfoKHR, handle type OPAQUE_FD) as the memory behind the view-target image or a staging buffer
+ * (INTEGRATION.md §6).  The fd is owned by the caller (importing into Vulkan transfers that ownership).
+ * bgs_frame_export_import is the consumer side in CUDA terms (another process / library maps the same allocation); the
+ * tests use it to prove the exported handle carries the rendered frame.  bgs_frame_export_destroy unmaps and releases a
+ * pointer returned by either call. */
+bgs_status bgs_frame_export_create(int cuda_device, size_t bytes, void** out_device_ptr, int* out_fd, size_t* out_alloc_bytes);
+bgs_status bgs_frame_export_import(int cuda_device, int fd, size_t alloc_bytes, void** out_device_ptr);
+void bgs_frame_export_destroy(void* device_ptr);
+
 /* Multi-GPU (one view per GPU, replicated cloud): gather every rank's frame to `root`.
  * nccl_comm is an ncclComm_t.  Enqueued on the context's streams (a frame produced by an async
  * bgs_render is gathered on the copy/comm stream so the next frame overlaps the transfer);

@@ -705,3 +705,41 @@ def test_cloud_files_through_the_cuda_path(plugin, oracle, tmp_path):
             assert np.array_equal(img, frames[name])
         else:       # (libm exp / sigmoid of the two hosts may differ in the last ulp)
             assert np.abs(img - frames[name]).max() <= 1e-3
+
+
+def test_exported_frame_target_round_trip(plugin):
+    """Row f4 (hand-back): the frame is rendered into an allocation exported as a POSIX fd (what Vulkan / wgpu-hal import with
+    VK_KHR_external_memory_fd); importing that fd again -- the consumer's side, here in CUDA terms -- must show the rendered
+    frame, byte for byte, with no copy in between."""
+    import ctypes as C
+    import os
+
+    from bevy_gaussian_splatting_b200 import abi
+
+    lib = abi.load()
+    w, h = 512, 288
+    nbytes = w * h * 4
+    ptr, fd, alloc = C.c_void_p(), C.c_int(-1), C.c_size_t(0)
+    assert lib.bgs_frame_export_create(0, nbytes, C.byref(ptr), C.byref(fd), C.byref(alloc)) == abi.BGS_OK
+    assert ptr.value and fd.value >= 0 and alloc.value >= nbytes
+    cloud = B.random_gaussians_3d_seeded(30000, 61)
+    hd = plugin.add_cloud(cloud)
+    view, s = B.headless_view(w, h), B.CloudSettings(global_scale=0.3)
+    other = C.c_void_p()
+    try:
+        want = plugin.render_view(hd, s, view, fmt="rgba8_srgb")
+        plugin.render_view_to_device(hd, s, view, ptr.value, fmt="rgba8_srgb")
+        assert lib.bgs_frame_export_import(0, fd.value, alloc.value, C.byref(other)) == abi.BGS_OK
+        assert other.value and other.value != ptr.value          # a second mapping of the same physical allocation
+        got = np.empty(nbytes, np.uint8)
+        cu = C.CDLL("libcuda.so.1")                                      # read the consumer's mapping with the driver API
+        cu.cuMemcpyDtoH_v2.argtypes = [C.c_void_p, C.c_uint64, C.c_size_t]
+        assert cu.cuMemcpyDtoH_v2(got.ctypes.data_as(C.c_void_p), C.c_uint64(other.value), nbytes) == 0
+        assert np.array_equal(got.reshape(h, w, 4), want)
+        assert want[..., :3].max() > 16
+    finally:
+        hd.destroy()
+        if other.value:
+            lib.bgs_frame_export_destroy(other)
+        lib.bgs_frame_export_destroy(ptr)
+        os.close(fd.value)
