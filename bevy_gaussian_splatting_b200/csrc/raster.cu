@@ -268,21 +268,45 @@ raster_kernel(const SplatRec* __restrict__ recs, const float4* __restrict__ extr
         if (MODE == 0 && !AUX) {
             // two candidates per iteration: one 32-bit load brings both list entries, the four record loads and both
             // coverage tests are independent (ILP), loop control is paid once; blending stays strictly in list order
-            if (!(T < T_STOP)) {
+            // The blend is PREDICATED, not branched: 14 predicated instructions per candidate instead of a divergent block
+            // with its BSSY / BRA / BREAK / BSYNC bookkeeping (~23 issue slots; 98 % of the candidates cover some pixel of
+            // the warp anyway).  `lim` = 1 while the pixel is alive, -1 once it has stopped (T < T_STOP) or lies outside the
+            // frame, so "covered" and "alive" are one comparison and a stopped pixel skips every later splat exactly as an
+            // early exit would.
+            {
                 const uint32_t a_end = a_list + nl * 2u;
                 uint32_t a_it = a_list;
-                auto blend = [&](uint32_t a_rec, float u, float v) {
-                    float4 q2; float e;
-                    const float qd = __fmaf_rn(v, v, __fmul_rn(u, u));
-                    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4+8192];" : "=f"(q2.x), "=f"(q2.y), "=f"(q2.z), "=f"(q2.w) : "r"(a_rec));
-                    // exp(-4.5 qd) = 2^(qd * -4.5 log2 e); qd <= 2 so the argument stays >= -13 (no range fix-up)
-                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(qd * -6.492127684f));
-                    const float a = fminf(e * q2.w, 0.999f);
-                    const float w = a * T;
-                    cr = fmaf(w, q2.x, cr); cg = fmaf(w, q2.y, cg); cb = fmaf(w, q2.z, cb);
-                    T = fmaf(-a, T, T);
+                float lim = (T < T_STOP) ? -1.0f : 1.0f;
+                auto blend_if_covered = [&](uint32_t a_rec, float u, float v) {
+                    asm volatile(
+                        "{\n\t"
+                        ".reg .pred p, q;\n\t"
+                        ".reg .f32 au, av, x, y, z, o, qd, e, a, w, na;\n\t"
+                        "abs.f32 au, %5;\n\t"
+                        "abs.f32 av, %6;\n\t"
+                        "setp.le.f32 p, au, %4;\n\t"
+                        "setp.le.and.f32 p, av, %4, p;\n\t"
+                        // (the temporaries are computed unconditionally -- a predicated definition would keep their old values
+                        // alive across iterations -- only the four accumulations are predicated)
+                        "ld.shared.v4.f32 {x, y, z, o}, [%7+8192];\n\t"
+                        "mul.rn.f32 qd, %5, %5;\n\t"
+                        "fma.rn.f32 qd, %6, %6, qd;\n\t"
+                        "mul.rn.f32 qd, qd, 0fC0CFBF83;\n\t"             // -6.492127684f: exp(-4.5 qd) = 2^(qd * -4.5 log2 e)
+                        "ex2.approx.ftz.f32 e, qd;\n\t"
+                        "mul.rn.f32 a, e, o;\n\t"
+                        "min.f32 a, a, 0f3F7FBE77;\n\t"                 // 0.999f
+                        "mul.rn.f32 w, a, %0;\n\t"
+                        "neg.f32 na, a;\n\t"
+                        "@p fma.rn.f32 %1, w, x, %1;\n\t"
+                        "@p fma.rn.f32 %2, w, y, %2;\n\t"
+                        "@p fma.rn.f32 %3, w, z, %3;\n\t"
+                        "@p fma.rn.f32 %0, na, %0, %0;\n\t"
+                        "setp.lt.and.f32 q, %0, 0f38D1B717, p;\n\t"     // T < T_STOP (1e-4f) after a blend: the pixel stops
+                        "@q mov.f32 %4, 0fBF800000;\n\t"
+                        "}"
+                        : "+f"(T), "+f"(cr), "+f"(cg), "+f"(cb), "+f"(lim)
+                        : "f"(u), "f"(v), "r"(a_rec));
                 };
-                bool alive = true;
                 for (; a_it + 2u < a_end; a_it += 4u) {
                     uint32_t two;
                     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(two) : "r"(a_it));
@@ -296,16 +320,10 @@ raster_kernel(const SplatRec* __restrict__ recs, const float4* __restrict__ extr
                     const float dxb = __fsub_rn(fx, pb.x), dyb = __fsub_rn(fy, pb.y);
                     const float ua = __fmaf_rn(pa.w, dya, __fmul_rn(pa.z, dxa)), va = __fmaf_rn(sa.y, dya, __fmul_rn(sa.x, dxa));
                     const float ub = __fmaf_rn(pb.w, dyb, __fmul_rn(pb.z, dxb)), vb = __fmaf_rn(sb.y, dyb, __fmul_rn(sb.x, dxb));
-                    if (fabsf(ua) <= 1.0f && fabsf(va) <= 1.0f) {
-                        blend(ra, ua, va);
-                        if (T < T_STOP) { alive = false; break; }
-                    }
-                    if (fabsf(ub) <= 1.0f && fabsf(vb) <= 1.0f) {
-                        blend(rb, ub, vb);
-                        if (T < T_STOP) { alive = false; break; }
-                    }
+                    blend_if_covered(ra, ua, va);
+                    blend_if_covered(rb, ub, vb);
                 }
-                if (alive && a_it != a_end) {   // odd tail
+                if (a_it != a_end) {   // odd tail
                     uint32_t ra;
                     asm volatile("ld.shared.u16 %0, [%1];" : "=r"(ra) : "r"(a_it));
                     float4 pa; float2 sa;
@@ -313,7 +331,7 @@ raster_kernel(const SplatRec* __restrict__ recs, const float4* __restrict__ extr
                     asm volatile("ld.shared.v2.f32 {%0,%1}, [%2+4096];" : "=f"(sa.x), "=f"(sa.y) : "r"(ra));
                     const float dxa = __fsub_rn(fx, pa.x), dya = __fsub_rn(fy, pa.y);
                     const float ua = __fmaf_rn(pa.w, dya, __fmul_rn(pa.z, dxa)), va = __fmaf_rn(sa.y, dya, __fmul_rn(sa.x, dxa));
-                    if (fabsf(ua) <= 1.0f && fabsf(va) <= 1.0f) blend(ra, ua, va);
+                    blend_if_covered(ra, ua, va);
                 }
             }
         } else if (!(T < T_STOP)) {
