@@ -80,11 +80,13 @@ struct bgs_context {
     int sm_count = 148;
     int coop = 0;                 // device supports cooperative launch
     uint32_t kg_grid = 0, bin_grid = 0;   // co-resident grid sizes of the cooperative kernels (synchronous frames: latency)
-    uint32_t kg_grid_async = 0, bin_grid_async = 0;   // ... of queued (BGS_FLAG_ASYNC) frames: 2 CTAs per SM.  A latency-bound
+    uint32_t kg_grid_async = 0, bin_grid_async = 0;   // ... of queued (BGS_FLAG_ASYNC) frames: 1 CTA per SM.  A latency-bound
                                           // cooperative grid holds its registers while it waits; with several frames in flight
                                           // a smaller grid leaves that room to the other frames' issue-bound blend
-                                          // (measured at C3, 3 contexts: 0.333 -> 0.309 ms per frame, profiles/r2_experiments.md)
+                                          // (measured at C3, 3 contexts, 4 / 2 / 1 CTAs per SM: 0.346 / 0.319 / 0.311 ms per
+                                          // frame before, 0.283 -> 0.268 after the other changes, profiles/r2_experiments.md)
     int rs_per_sm = 0;                    // co-resident radix-sort CTAs per SM (radix.cu)
+    int rs_per_sm_async = 1;              // ... the pair sort of queued frames may use (1: half an SM, two waves)
     uint32_t sort_epoch = 0;              // look-back status epoch: +1 per sort launch (status words never need clearing)
     cudaStream_t stream = nullptr;    // render stream (high priority): everything but the projection
     cudaStream_t stream2 = nullptr;   // projection runs here, beside the depth sort
@@ -363,12 +365,14 @@ bgs_status bgs_context_create(int cuda_device, bgs_context** out) {
         if (const char* e = getenv("BGS_COOP_BLOCKS")) lim = atoi(e) > 0 ? atoi(e) : 4;   // second context's kernels)
         c->kg_grid = (uint32_t)(c->sm_count * (kb > lim ? lim : kb));
         c->bin_grid = (uint32_t)(c->sm_count * (bb > lim ? lim : bb));
-        int lim_a = 2;
-        if (const char* e = getenv("BGS_COOP_BLOCKS_ASYNC")) lim_a = atoi(e) > 0 ? atoi(e) : 2;
+        int lim_a = 1;
+        if (const char* e = getenv("BGS_COOP_BLOCKS_ASYNC")) lim_a = atoi(e) > 0 ? atoi(e) : 1;
         if (lim_a > lim) lim_a = lim;
         c->kg_grid_async = (uint32_t)(c->sm_count * (kb > lim_a ? lim_a : kb));
         c->bin_grid_async = (uint32_t)(c->sm_count * (bb > lim_a ? lim_a : bb));
         c->rs_per_sm = radix_coop_blocks_per_sm(16);
+        if (const char* e = getenv("BGS_SORT_CTAS_ASYNC")) c->rs_per_sm_async = atoi(e) > 0 ? atoi(e) : 1;
+        if (c->rs_per_sm_async > c->rs_per_sm) c->rs_per_sm_async = c->rs_per_sm;
         if (c->kg_grid == 0 || c->bin_grid == 0 || c->kg_grid > 4096 || c->bin_grid > 4096 || c->rs_per_sm == 0) c->coop = 0;
     }
     if (const char* fr = getenv("BGS_CHUNK_FRACS")) {
@@ -845,7 +849,7 @@ static bgs_status render_impl(bgs_context* c, const bgs_cloud* cloud, const bgs_
             if (p_hint > c->cap_pairs) p_hint = c->cap_pairs;
             CU(c, launch_radix_sort(c->pkeys[0], c->pvals[0], c->pkeys[1], c->pvals[1], &cc->n_pairs, c->cap_pairs, p_hint, hist_r, 1,
                                     c->status_pairs, (size_t)radix_num_tiles(c->status_np) * 256, next_epoch(c), &cc->tile_ctr_sort[0],
-                                    tile_passes, 0, rng, c->sm_count, c->rs_per_sm, q, nullptr));
+                                    tile_passes, 0, rng, c->sm_count, (st->flags & BGS_FLAG_ASYNC) ? c->rs_per_sm_async : c->rs_per_sm, q, nullptr));
             ++launches;
             pcur = tile_passes & 1;
             if (r + 1 == rounds) {

@@ -522,8 +522,11 @@ __device__ __forceinline__ void project_one(const FrameConsts& fc, const FrameCo
     out[2] = make_float4(rec.r, rec.g, rec.b, rec.op);
 }
 
+#ifndef PROJ_MIN_CTAS
+#define PROJ_MIN_CTAS 6
+#endif
 template <bool F16, bool BLOCKED>
-__global__ void __launch_bounds__(128, 6)
+__global__ void __launch_bounds__(128, PROJ_MIN_CTAS)
 project_kernel(const float4* __restrict__ pos, const void* __restrict__ sh_p, const void* __restrict__ rot_p,
                const void* __restrict__ so_p, const uint32_t* __restrict__ index_list, int by_slot,
                const FrameCounters* __restrict__ ctr, FrameConsts fc, SplatRec* __restrict__ recs,

@@ -28,6 +28,9 @@ constexpr int RS_THREADS = 512;                   // fat CTAs, one (two for > 1.
 constexpr int RS_WARPS = RS_THREADS / 32;         // <= 148 (296) tiles, so the look-back walks (traffic ~ tiles^2 x 2 KB)
                                                   // stay short; 512 x 64 registers leave half an SM to a concurrent kernel
 constexpr int RS_TABLE_WORDS = RS_WARPS * 256;    // one peer-mask table (all warps)
+#ifndef RS_MIN_CTAS
+#define RS_MIN_CTAS 2
+#endif
 constexpr int LB_BATCH = 16;                      // look-back loads in flight per thread
 
 // status word: [63:34] epoch, [33:32] flag (1 = tile aggregate, 2 = inclusive prefix), [31:0] value
@@ -68,7 +71,7 @@ constexpr size_t radix_smem_bytes(int items) {
 }
 
 template <int RS_ITEMS, bool MASK_TABLE>
-__global__ void __launch_bounds__(RS_THREADS, 2)
+__global__ void __launch_bounds__(RS_THREADS, RS_MIN_CTAS)
 radix_coop_kernel(SortParams P) {
     constexpr int RS_TILE = RS_THREADS * RS_ITEMS;
     constexpr int KV_WORDS = RS_TILE > RS_TABLE_WORDS ? RS_TILE : RS_TABLE_WORDS;
@@ -369,14 +372,24 @@ cudaError_t launch_radix_sort(uint32_t* keys0, uint32_t* vals0, uint32_t* keys1,
     P.ranges = ranges; P.tl = tl;
     { const char* e = getenv("BGS_TIMELINE_SORT_PASS"); P.tl_pass = e ? atoi(e) : 1; }
     if (n_hint > capacity) n_hint = capacity;
-    // items per thread so that one wave of tiles covers the expected count with ~6 % head-room
-    const uint64_t want = (uint64_t)n_hint + n_hint / 16 + 1024;
+    // items per thread so that `waves` waves of tiles cover the expected count with ~3 % head-room (a frame that outgrows
+    // it gives some CTAs one more tile: slower, never wrong).  One CTA per SM when the count allows, else two -- unless
+    // the caller caps it (coop_per_sm = 1: queued frames keep the sort's footprint at half an SM and run two waves).
+    const uint64_t want = (uint64_t)n_hint + n_hint / 32 + 1024;
     uint32_t grid = (uint32_t)sm_count;
-    uint32_t items = (uint32_t)((want + (uint64_t)grid * RS_THREADS - 1) / ((uint64_t)grid * RS_THREADS));
-    if (items > 16 && coop_per_sm >= 2) {
+    auto items_for = [&](uint32_t g, uint32_t& waves) {
+        const uint64_t per_wave = (uint64_t)g * RS_THREADS * 16u;
+        waves = (uint32_t)((want + per_wave - 1) / per_wave);
+        const uint64_t per_item = (uint64_t)g * RS_THREADS * waves;
+        return (uint32_t)((want + per_item - 1) / per_item);
+    };
+    uint32_t waves = 1;
+    uint32_t items = items_for(grid, waves);
+    if (waves > 1 && coop_per_sm >= 2) {
         grid = 2u * (uint32_t)sm_count;
-        items = (uint32_t)((want + (uint64_t)grid * RS_THREADS - 1) / ((uint64_t)grid * RS_THREADS));
+        items = items_for(grid, waves);
     }
+    if (waves > 3) items = 17;      // many waves: the throughput variant (16 items, MATCH.ANY ranking)
     // never more tiles than status rows, whatever the actual count turns out to be
     const uint32_t rows = (uint32_t)(status_stride / 256);
     const uint32_t min_items = (uint32_t)(((uint64_t)capacity + (uint64_t)rows * RS_THREADS - 1) / ((uint64_t)rows * RS_THREADS));

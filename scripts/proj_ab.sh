@@ -1,0 +1,9 @@
+#!/bin/bash
+# A/B the projection kernel's register budget (min CTAs per SM) on the GPU box: rebuild project.o, time C3.
+for m in 6 8; do
+  touch bevy_gaussian_splatting_b200/csrc/project.cu
+  make -C bevy_gaussian_splatting_b200/csrc -j8 EXTRA=-DPROJ_MIN_CTAS=$m > /dev/null 2>&1
+  echo "== PROJ_MIN_CTAS=$m"
+  timeout 240 python bench.py --steps 100 --warmup 10 --no-cpu-baseline 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], 'p50', d['frame_ms_p50'], 'e2e', d['e2e']['value'], [s['us'] for s in d['stages']])"
+  timeout 100 python scripts/timeline_sort.py 2>&1 | tail -1
+done
