@@ -743,3 +743,36 @@ def test_exported_frame_target_round_trip(plugin):
             lib.bgs_frame_export_destroy(other)
         lib.bgs_frame_export_destroy(ptr)
         os.close(fd.value)
+
+
+def test_overflow_of_an_earlier_queued_frame_is_reported(plugin):
+    """with BGS_FLAG_ASYNC a pair-list overflow used to be noticed only on the LAST queued frame.  The library now
+    keeps a sticky device-side maximum over every frame queued since the last sync: a heavy frame followed by a light one
+    must still make `bgs_sync` report BGS_NOT_READY (and grow the buffer), after which the same sequence succeeds."""
+    cloud = B.random_gaussians_3d_seeded(40000, 3)
+    view = B.headless_view(640, 360)
+    light, heavy = B.CloudSettings(global_scale=0.05), B.CloudSettings(global_scale=3.0)
+    p2 = B.GaussianSplattingPlugin(0)
+    try:
+        h2 = p2.add_cloud(cloud)
+        p2.render_view(h2, light, view, fmt="rgba32f", to_host=False)                       # sizes the pair buffer small
+        small_pairs = p2.frame_stats().n_pairs
+        out_heavy, out_light = np.empty((360, 640, 4), np.float32), np.empty((360, 640, 4), np.float32)
+        p2.render_view(h2, heavy, view, fmt="rgba32f", out=out_heavy, asynchronous=True)    # overflows ...
+        p2.render_view(h2, light, view, fmt="rgba32f", out=out_light, asynchronous=True)    # ... but is not the last frame
+        ok = p2.sync()
+        ref_heavy = plugin.add_cloud(cloud)
+        try:
+            want_heavy = plugin.render_view(ref_heavy, heavy, view, fmt="rgba32f")
+            needs_more = plugin.frame_stats().n_pairs > max(small_pairs, 1 << 20)
+        finally:
+            ref_heavy.destroy()
+        assert needs_more, "the construction must overflow the first buffer"
+        assert not ok, "an overflow of the earlier frame went unreported"
+        p2.render_view(h2, heavy, view, fmt="rgba32f", out=out_heavy, asynchronous=True)
+        p2.render_view(h2, light, view, fmt="rgba32f", out=out_light, asynchronous=True)
+        assert p2.sync()
+        assert np.array_equal(out_heavy, want_heavy)
+        h2.destroy()
+    finally:
+        p2.destroy()
