@@ -206,13 +206,27 @@ public:
     }
     // One view of one cloud.  Returns false when the frame is skipped (warm-up camera / not ready), like the
     // reference's silent skip (src/render/mod.rs:361-371, src/sort/radix.rs:645-658).
+    // `extra_flags`: BGS_FLAG_BLEND_OVER_TARGET (blend over what the target holds: one call per cloud, far cloud first, as
+    // the reference's Transparent3d items do, render/mod.rs:398-452, :944-948), BGS_FLAG_PREMULTIPLIED_OUT (the layer alone).
     bool render_view(const PlanarGaussian3dHandle& cloud, const CloudSettings& settings, const bgs_view& view, void* out_rgba,
-                     uint32_t format = BGS_FORMAT_RGBA8_SRGB, const GaussianCamera& camera = {}, bool out_is_device = false) {
+                     uint32_t format = BGS_FORMAT_RGBA8_SRGB, const GaussianCamera& camera = {}, bool out_is_device = false,
+                     uint32_t extra_flags = 0) {
         if (camera.warmup) return false;
         bgs_cloud_uniform u = cloud_uniform(settings);
         std::memcpy(u.aabb_min, cloud.aabb_min(), 12); std::memcpy(u.aabb_max, cloud.aabb_max(), 12);
-        const bgs_settings s = settings.to_abi();
+        const bgs_settings s = settings.to_abi(extra_flags);
         const bgs_status st = bgs_render(ctx_, cloud.get(), &view, &u, &s, out_rgba, format, out_is_device ? 1 : 0);
+        if (st == BGS_NOT_READY) return false;
+        check(st);
+        return true;
+    }
+    // Colour + depth + normal frames of one view in one pass (BASELINE.json config 4; bgs_render_aux).
+    bool render_view_aux(const PlanarGaussian3dHandle& cloud, const CloudSettings& settings, const bgs_view& view, void* out_rgba,
+                         void* out_depth, void* out_normal, uint32_t format = BGS_FORMAT_RGBA8_SRGB, bool out_is_device = false) {
+        bgs_cloud_uniform u = cloud_uniform(settings);
+        std::memcpy(u.aabb_min, cloud.aabb_min(), 12); std::memcpy(u.aabb_max, cloud.aabb_max(), 12);
+        const bgs_settings s = settings.to_abi();
+        const bgs_status st = bgs_render_aux(ctx_, cloud.get(), &view, &u, &s, out_rgba, out_depth, out_normal, format, out_is_device ? 1 : 0);
         if (st == BGS_NOT_READY) return false;
         check(st);
         return true;
