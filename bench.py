@@ -235,6 +235,33 @@ def parity_block(plugin, handle, settings, view, cloud, ref_img):
             "tolerance": 1e-3}
 
 
+def bind_to_gpu_numa_node(gpu_index: int):
+    """Multi-GPU runs: keep this rank's threads (and so its pinned frame buffers: first touch) on the NUMA node its GPU
+    hangs off, so eight ranks' device->host frame copies do not cross the socket interconnect.  Best effort."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(gpu_index)).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:
+            bus = bus[4:]                                   # "00000000:1b:00.0" -> "0000:1b:00.0"
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 def run_cuda(args):
     import torch
 
@@ -249,6 +276,7 @@ def run_cuda(args):
         raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     dist = None
+    numa_node = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     if world > 1:
         import torch.distributed as dist
 
@@ -446,7 +474,7 @@ def run_cuda(args):
         "warmup": args.warmup, "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32 (f16-packed inputs)", "data": "synthetic",
         "config": bench_config(views, world, {"n_visible": nv, "n_pairs": I, "l2": "inputs larger than L2 (768 MB cloud vs 126 MB)",
-                                              "frames_in_flight": frames_in_flight,
+                                              "frames_in_flight": frames_in_flight, "rank0_numa_node": numa_node,
                                               "timing": "value: 3 frames in flight, CUDA events over render + copy/comm streams; "
                                                         "stages[] / frame_ms_*: one frame at a time on an idle GPU"}),
         "frame_ms_p50": round(float(np.percentile(frame_us, 50)) / 1000.0, 4),
