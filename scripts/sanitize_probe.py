@@ -21,9 +21,20 @@ for f16 in (False, True):
             img = pl.render_view(hd, s, view, fmt=fmt)
             img = pl.render_view(hd, s, view, fmt=fmt)      # hinted frame (other kernel variants)
             n += 2
+    # round-2 paths: compositing output modes, aux frames
+    s = B.CloudSettings(global_scale=0.3)
+    pl.render_view(hd, s, view, fmt="rgba32f")
+    pl.render_view(hd, s, view, fmt="rgba32f", blend_over=True)
+    pl.render_view(hd, s, view, fmt="rgba8_srgb", premultiplied=True)
+    pl.render_view_aux(hd, s, view, fmt="rgba32f")
+    pl.render_view_aux(hd, B.CloudSettings(global_scale=0.3, gaussian_mode=B.GaussianMode.Gaussian2d, aabb=True), view, fmt="rgba8_srgb")
+    n += 5
     out = np.empty((120, 208, 4), np.float32)
     for _ in range(3):
         pl.render_view(hd, B.CloudSettings(global_scale=0.3), view, fmt="rgba32f", out=out, asynchronous=True)
     pl.sync()
     hd.destroy()
+hc = pl.add_cloud(cloud, precompute_covariance=True)
+pl.render_view(hc, B.CloudSettings(), view, fmt="rgba32f"); n += 1
+hc.destroy()
 print("sanitize probe ok:", n, "frames")
