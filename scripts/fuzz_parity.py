@@ -11,9 +11,10 @@ pl = B.GaussianSplattingPlugin(0)
 t0 = time.time(); it = 0; worst = 0.0
 while time.time() - t0 < budget:
     it += 1
-    n = int(rng.choice([1, 2, 31, 33, 1000, 4096, 4097, 20000, 50000]))
+    # (the larger counts reach the sort's bigger tile variants: ITEMS 2..16 per thread, one and two CTAs per SM)
+    n = int(rng.choice([1, 2, 31, 33, 1000, 4096, 4097, 20000, 50000, 300000, 1200000, 2500000], p=[.08, .05, .05, .05, .12, .1, .1, .15, .12, .08, .06, .04]))
     w, h = int(rng.integers(8, 700)), int(rng.integers(8, 400))
-    scale = float(10 ** rng.uniform(-2, 0.5))
+    scale = float(10 ** rng.uniform(-2, 0.5)) if n <= 50000 else float(10 ** rng.uniform(-2.2, -1.3))
     gm = B.GaussianMode(int(rng.integers(0, 2))); aabb = bool(rng.integers(0, 2))
     rm = B.RasterizeMode(int(rng.integers(0, 4))); dm = B.DrawMode(int(rng.integers(0, 3)))
     bits = B.RadixSortDepthBits(int(rng.choice([16, 24, 32])))
