@@ -629,7 +629,7 @@ static bgs_status render_impl(bgs_context* c, const bgs_cloud* cloud, const bgs_
     if (!c) return BGS_EINVAL;
     // not-ready inputs map to the reference's silent skip-frame (radix.rs:645-658, mod.rs:1533-1539)
     if (!cloud || !view || !uni || !st) return fail(c, BGS_NOT_READY, "render: cloud/view/uniform/settings not ready");
-    if (cloud->ctx != c && cloud->ctx->device != c->device)
+    if (cloud->device != c->device)     // (cloud->ctx may be gone: clouds outlive the context that uploaded them)
         return fail(c, BGS_EINVAL, "render: cloud lives on another device");   // contexts of one GPU may share clouds
     if (out_format > BGS_FORMAT_RGBA32F) return fail(c, BGS_EINVAL, "render: unknown out_format %u", out_format);
     if (st->radix_sort_depth_bits != 16 && st->radix_sort_depth_bits != 24 && st->radix_sort_depth_bits != 32)
