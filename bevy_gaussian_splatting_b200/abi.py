@@ -105,6 +105,10 @@ SYMBOLS = [
     ("bgs_nccl_comm_init", C.c_int, [_P, C.c_int, C.c_int, _P, C.POINTER(_P)]),
     ("bgs_nccl_comm_destroy", None, [_P]),
     ("bgs_gather_frames", C.c_int, [_P, _P, C.c_int, _P, _P, C.c_size_t]),
+    ("bgs_peer_buffer_create", C.c_int, [C.c_int, C.c_size_t, C.POINTER(_P), _P]),
+    ("bgs_peer_buffer_open", C.c_int, [C.c_int, _P, C.POINTER(_P)]),
+    ("bgs_peer_buffer_release", None, [_P, C.c_int]),
+    ("bgs_push_frame", C.c_int, [_P, _P, _P, C.c_int, C.c_size_t]),
 ]
 
 _lib = None

@@ -123,4 +123,47 @@ bgs_status bgs_gather_frames(bgs_context* ctx, void* nccl_comm, int root, const 
     return BGS_OK;
 }
 
+// ---- copy-engine variant of the gather (measured beside the NCCL one, bench.py `gather_ce`): the root's frame array is a
+// cudaMalloc allocation exported with CUDA IPC; every other rank (a separate process) opens it and PUSHES its finished
+// frame with a peer-to-peer cudaMemcpyAsync on its own copy/comm stream -- NVLink through the sender's copy engine, no SM
+// on either side, nothing queued on the root.  The root learns about completion from the host (barrier / its own
+// protocol); a per-frame device-side signal would be an IPC event (not built).  NCCL stays the default path (north_star).
+bgs_status bgs_peer_buffer_create(int cuda_device, size_t bytes, void** out_ptr, void* out_handle64) {
+    if (!out_ptr || !out_handle64 || bytes == 0) return BGS_EINVAL;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    if (cudaSetDevice(cuda_device) != cudaSuccess) return BGS_ECUDA;
+    void* p = nullptr;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) return BGS_ENOMEM;
+    cudaIpcMemHandle_t h;
+    if (cudaMemset(p, 0, bytes) != cudaSuccess || cudaIpcGetMemHandle(&h, p) != cudaSuccess) { cudaFree(p); return BGS_ECUDA; }
+    memcpy(out_handle64, &h, 64);
+    *out_ptr = p;
+    return BGS_OK;
+}
+
+bgs_status bgs_peer_buffer_open(int cuda_device, const void* handle64, void** out_ptr) {
+    if (!out_ptr || !handle64) return BGS_EINVAL;
+    if (cudaSetDevice(cuda_device) != cudaSuccess) return BGS_ECUDA;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    void* p = nullptr;
+    if (cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); return BGS_ECUDA; }
+    *out_ptr = p;
+    return BGS_OK;
+}
+
+void bgs_peer_buffer_release(void* ptr, int opened) {
+    if (!ptr) return;
+    if (opened) cudaIpcCloseMemHandle(ptr); else cudaFree(ptr);
+}
+
+bgs_status bgs_push_frame(bgs_context* ctx, const void* local_frame, void* remote_frames, int index, size_t bytes) {
+    if (!ctx || !local_frame || !remote_frames || index < 0 || bytes == 0) return BGS_EINVAL;
+    int slot = -1;
+    cudaStream_t q = bgs_internal_gather_begin_(ctx, local_frame, &slot);   // copy/comm stream for async library frames
+    const cudaError_t e = cudaMemcpyAsync((char*)remote_frames + (size_t)index * bytes, local_frame, bytes, cudaMemcpyDefault, q);
+    bgs_internal_gather_end_(ctx, slot);
+    return e == cudaSuccess ? BGS_OK : BGS_ECUDA;
+}
+
 }  // extern "C"

@@ -79,6 +79,39 @@ class MultiViewSession:
         if st != abi.BGS_OK:
             raise abi.BgsError(st, "bgs_gather_frames failed")
 
+    # ---- copy-engine variant (CUDA IPC + peer-to-peer copies; NCCL stays the default)
+    def setup_peer_frames(self, device: int, nbytes_per_frame: int) -> int:
+        """Root: create the exportable frame array (world x nbytes) and broadcast its IPC handle; others: open it.
+        Returns the device pointer every rank pushes into (the root's own array on the root)."""
+        import torch
+        import torch.distributed as dist
+
+        handle = (C.c_ubyte * 64)()
+        self._peer_ptr, self._peer_opened = C.c_void_p(), 0
+        if self.rank == self.root:
+            st = self._lib.bgs_peer_buffer_create(device, self.world * nbytes_per_frame, C.byref(self._peer_ptr), handle)
+            if st != abi.BGS_OK:
+                raise abi.BgsError(st, "bgs_peer_buffer_create failed")
+        t = torch.frombuffer(bytearray(bytes(handle)), dtype=torch.uint8).clone().to(torch.device("cuda", torch.cuda.current_device()))
+        dist.broadcast(t, src=self.root)
+        if self.rank != self.root:
+            raw = (C.c_ubyte * 64).from_buffer_copy(bytes(t.cpu().numpy().tobytes()))
+            st = self._lib.bgs_peer_buffer_open(device, raw, C.byref(self._peer_ptr))
+            if st != abi.BGS_OK:
+                raise abi.BgsError(st, "bgs_peer_buffer_open failed (no peer access between the GPUs?)")
+            self._peer_opened = 1
+        return int(self._peer_ptr.value)
+
+    def push_device(self, local_ptr: int, nbytes: int) -> None:
+        st = self._lib.bgs_push_frame(self.plugin._ctx, C.c_void_p(local_ptr), self._peer_ptr, self.rank, nbytes)
+        if st != abi.BGS_OK:
+            raise abi.BgsError(st, "bgs_push_frame failed")
+
+    def release_peer_frames(self) -> None:
+        if getattr(self, "_peer_ptr", None) is not None and self._peer_ptr:
+            self._lib.bgs_peer_buffer_release(self._peer_ptr, self._peer_opened)
+            self._peer_ptr = C.c_void_p()
+
     def gather_host(self, frame: np.ndarray):
         """gloo stand-in used by the CPU tests: same ordering contract (frames[r] = rank r's frame)."""
         import torch

@@ -202,6 +202,18 @@ void bgs_nccl_comm_destroy(void* nccl_comm);
 bgs_status bgs_gather_frames(bgs_context* ctx, void* nccl_comm, int root, const void* local_frame,
                              void* all_frames, size_t bytes);
 
+/* Copy-engine alternative to bgs_gather_frames (same contract: rank r's frame lands at all_frames + r * bytes on the
+ * root), reported beside the NCCL gather by bench.py (`gather_ce`).  The root creates its frame array exportable
+ * (bgs_peer_buffer_create -> 64-byte CUDA IPC handle, shipped to the other ranks by the host's own channel); every other
+ * rank -- a separate process -- opens it (bgs_peer_buffer_open) and pushes each finished frame with bgs_push_frame: a
+ * peer-to-peer copy over NVLink on the sender's copy/comm stream, no SM on either side.  The root itself pushes into its
+ * own array (index = its rank).  Completion on the root is the host's to establish (the bench: sync + barrier).
+ * bgs_peer_buffer_release(ptr, opened): opened != 0 for pointers from bgs_peer_buffer_open. */
+bgs_status bgs_peer_buffer_create(int cuda_device, size_t bytes, void** out_ptr, void* out_handle64);
+bgs_status bgs_peer_buffer_open(int cuda_device, const void* handle64, void** out_ptr);
+void bgs_peer_buffer_release(void* ptr, int opened);
+bgs_status bgs_push_frame(bgs_context* ctx, const void* local_frame, void* remote_frames, int index, size_t bytes);
+
 #ifdef __cplusplus
 }
 #endif
