@@ -374,36 +374,69 @@ def run_cuda(args):
         for k in range(frames_in_flight):
             sessions[k].setup_peer_frames(local_rank, frame_bytes)
 
+        # completion is signalled on the devices (bgs_push_frame_signal / bgs_wait_frames): proven on the warm-up frames
+        # first (every rank's words must have reached the expected sequence), else the host barrier below stands in
+        use_signal = [True]
+
         def step_ce(i):
             k = i % frames_in_flight
             p = plugins[k]
             p.render_view(handle, settings, view, fmt="rgba8_srgb", to_host=False, asynchronous=True)
+            if use_signal[0]:
+                try:
+                    sessions[k].push_device(p.frame_device_ptr, frame_bytes, signal=True)
+                    return
+                except abi.BgsError:
+                    use_signal[0] = False
             sessions[k].push_device(p.frame_device_ptr, frame_bytes)
+
+        def read_root(ptr, nbytes):
+            got = np.empty(nbytes, np.uint8)
+            cu = C.CDLL("libcuda.so.1")
+            cu.cuMemcpyDtoH_v2.argtypes = [C.c_void_p, C.c_uint64, C.c_size_t]
+            assert cu.cuMemcpyDtoH_v2(got.ctypes.data_as(C.c_void_p), C.c_uint64(ptr), got.size) == 0
+            return got
 
         for i in range(2 * frames_in_flight + args.warmup):
             step_ce(i)
         assert sync_all()
+        barrier()
+        sig_ok = 1 if use_signal[0] else 0
+        if rank == 0 and sig_ok:
+            for k in range(frames_in_flight):
+                words = read_root(sessions[k].peer_flags_ptr(), 4 * world).view(np.uint32)
+                if not np.all(words == np.uint32(sessions[k]._peer_seq)):
+                    sig_ok = 0
+        t = torch.tensor([sig_ok], device="cuda", dtype=torch.int32)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        use_signal[0] = bool(t.item())
         barrier()
         c0 = torch.cuda.Event(enable_timing=True)
         c1 = [torch.cuda.Event(enable_timing=True) for _ in range(2 * len(plugins))]
         c0.record(streams[0])
         for i in range(args.steps):
             step_ce(i)
+        if rank == 0 and use_signal[0]:
+            # the root's copy/comm streams resume when EVERY rank's last push of that context has landed
+            for k in range(frames_in_flight):
+                sessions[k].wait_frames(plugins[k].copy_stream_ptr, sessions[k]._peer_seq)
         for ev, st_ in zip(c1, streams + copy_streams):
             ev.record(st_)
         assert sync_all()
+        ce_ok = None
+        k_last = (args.steps - 1) % frames_in_flight
+        got = None
+        if rank == 0 and use_signal[0]:
+            # read BEFORE any host barrier: the device-side wait alone has established that all frames are there
+            got = read_root(sessions[k_last]._peer_ptr.value, world * frame_bytes)
         barrier()
         ce_ms = max(c0.elapsed_time(ev) for ev in c1) / args.steps
         t = torch.tensor([ce_ms], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ce_ms = float(t.item())
-        ce_ok = None
         if rank == 0:
-            k_last = (args.steps - 1) % frames_in_flight
-            got = np.empty(world * frame_bytes, np.uint8)
-            cu = C.CDLL("libcuda.so.1")
-            cu.cuMemcpyDtoH_v2.argtypes = [C.c_void_p, C.c_uint64, C.c_size_t]
-            assert cu.cuMemcpyDtoH_v2(got.ctypes.data_as(C.c_void_p), C.c_uint64(sessions[k_last]._peer_ptr.value), got.size) == 0
+            if got is None:
+                got = read_root(sessions[k_last]._peer_ptr.value, world * frame_bytes)
             got = got.reshape(world, HEIGHT, WIDTH, 4)
             ce_ok = True
             for r in range(world):
@@ -415,7 +448,9 @@ def run_cuda(args):
         gather_ce = {"transport": "CUDA IPC + cudaMemcpyAsync peer pushes on each rank's copy stream (copy engines, no SM)",
                      "value": round(N_GAUSSIANS * world / (ce_ms / 1000.0) / 1e6, 1), "unit": "Msplats/s", "ms_per_step": round(ce_ms, 4),
                      "frames_verified": ce_ok,
-                     "note": "reported beside the NCCL gather (the headline `value`, north_star); completion on the root is established by the host here"}
+                     "signalling": ("device: one 32-bit sequence word per slot stored after the copy, cuStreamWaitValue32 on the root's stream "
+                                    "(frames read back before any host barrier)") if use_signal[0] else "host barrier",
+                     "note": "reported beside the NCCL gather (the headline `value`, north_star)"}
     # per-frame / per-stage times (live CUDA events inside the library), one frame at a time on an idle GPU
     frame_us, stage_rows = [], []
     for _ in range(min(args.steps, 100)):

@@ -109,6 +109,8 @@ SYMBOLS = [
     ("bgs_peer_buffer_open", C.c_int, [C.c_int, _P, C.POINTER(_P)]),
     ("bgs_peer_buffer_release", None, [_P, C.c_int]),
     ("bgs_push_frame", C.c_int, [_P, _P, _P, C.c_int, C.c_size_t]),
+    ("bgs_push_frame_signal", C.c_int, [_P, _P, _P, C.c_int, C.c_size_t, _P, C.c_uint32]),
+    ("bgs_wait_frames", C.c_int, [_P, _P, C.c_int, C.c_uint32]),
 ]
 
 _lib = None

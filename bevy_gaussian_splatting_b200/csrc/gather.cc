@@ -5,11 +5,14 @@
 //
 // NCCL is resolved lazily with dlopen so single-GPU users of libbgs.so never need it, and so a
 // host process that already loaded an NCCL (e.g. the torch-bundled one) shares that instance.
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <cstdint>
 #include <cstdio>
+#include <mutex>
 #include <cstring>
 
 #include "../../include/bgs.h"
@@ -126,8 +129,10 @@ bgs_status bgs_gather_frames(bgs_context* ctx, void* nccl_comm, int root, const 
 // ---- copy-engine variant of the gather (measured beside the NCCL one, bench.py `gather_ce`): the root's frame array is a
 // cudaMalloc allocation exported with CUDA IPC; every other rank (a separate process) opens it and PUSHES its finished
 // frame with a peer-to-peer cudaMemcpyAsync on its own copy/comm stream -- NVLink through the sender's copy engine, no SM
-// on either side, nothing queued on the root.  The root learns about completion from the host (barrier / its own
-// protocol); a per-frame device-side signal would be an IPC event (not built).  NCCL stays the default path (north_star).
+// on either side, nothing queued on the root.  Completion is signalled on the devices as well (bgs_push_frame_signal /
+// bgs_wait_frames below): a 32-bit sequence word per slot, stored by the sender's stream after its copy and awaited by a
+// stream memory operation on the root -- no cross-process event, no host round-trip.  NCCL stays the default path
+// (north_star).
 bgs_status bgs_peer_buffer_create(int cuda_device, size_t bytes, void** out_ptr, void* out_handle64) {
     if (!out_ptr || !out_handle64 || bytes == 0) return BGS_EINVAL;
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
@@ -164,6 +169,55 @@ bgs_status bgs_push_frame(bgs_context* ctx, const void* local_frame, void* remot
     const cudaError_t e = cudaMemcpyAsync((char*)remote_frames + (size_t)index * bytes, local_frame, bytes, cudaMemcpyDefault, q);
     bgs_internal_gather_end_(ctx, slot);
     return e == cudaSuccess ? BGS_OK : BGS_ECUDA;
+}
+
+// ---- per-slot completion words.  The sender stores `sequence` into remote_flags[index] with a 32-bit memset on the SAME
+// stream as the frame copy (stream order: the copy has completed, i.e. its peer writes have landed, before the store is
+// issued); the consumer queues cuStreamWaitValue32(flags[i] >= sequence, cyclic compare) on the stream that reads the
+// frames.  Both are driver-API calls, resolved with dlopen like NCCL (libbgs.so links cudart only).
+namespace {
+struct SigApi {
+    CUresult (*MemsetD32Async)(CUdeviceptr, unsigned int, size_t, CUstream) = nullptr;
+    CUresult (*StreamWaitValue32)(CUstream, CUdeviceptr, cuuint32_t, unsigned int) = nullptr;
+    bool ok = false;
+};
+SigApi& sig_api() {
+    static SigApi a;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* lib = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
+        if (!lib) return;
+        *(void**)(&a.MemsetD32Async) = dlsym(lib, "cuMemsetD32Async");
+        *(void**)(&a.StreamWaitValue32) = dlsym(lib, "cuStreamWaitValue32_v2");
+        if (!a.StreamWaitValue32) *(void**)(&a.StreamWaitValue32) = dlsym(lib, "cuStreamWaitValue32");
+        a.ok = a.MemsetD32Async && a.StreamWaitValue32;
+    });
+    return a;
+}
+}  // namespace
+
+bgs_status bgs_push_frame_signal(bgs_context* ctx, const void* local_frame, void* remote_frames, int index, size_t bytes,
+                                 void* remote_flags, uint32_t sequence) {
+    if (!ctx || !local_frame || !remote_frames || !remote_flags || index < 0 || bytes == 0) return BGS_EINVAL;
+    SigApi& a = sig_api();
+    if (!a.ok) return BGS_ECUDA;
+    int slot = -1;
+    cudaStream_t q = bgs_internal_gather_begin_(ctx, local_frame, &slot);
+    const cudaError_t e = cudaMemcpyAsync((char*)remote_frames + (size_t)index * bytes, local_frame, bytes, cudaMemcpyDefault, q);
+    CUresult r = CUDA_ERROR_UNKNOWN;
+    if (e == cudaSuccess) r = a.MemsetD32Async((CUdeviceptr)((uint32_t*)remote_flags + index), sequence, 1, (CUstream)q);
+    bgs_internal_gather_end_(ctx, slot);
+    return (e == cudaSuccess && r == CUDA_SUCCESS) ? BGS_OK : BGS_ECUDA;
+}
+
+bgs_status bgs_wait_frames(void* cuda_stream, const void* flags, int count, uint32_t sequence) {
+    if (!flags || count <= 0) return BGS_EINVAL;
+    SigApi& a = sig_api();
+    if (!a.ok) return BGS_ECUDA;
+    for (int i = 0; i < count; ++i)
+        if (a.StreamWaitValue32((CUstream)cuda_stream, (CUdeviceptr)((const uint32_t*)flags + i), sequence, CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS)
+            return BGS_ECUDA;
+    return BGS_OK;
 }
 
 }  // extern "C"

@@ -88,8 +88,11 @@ class MultiViewSession:
 
         handle = (C.c_ubyte * 64)()
         self._peer_ptr, self._peer_opened = C.c_void_p(), 0
+        # layout of the exported allocation: world frames, then (256 B-aligned) one 32-bit completion word per slot
+        self._peer_flags_off = (self.world * nbytes_per_frame + 255) & ~255
+        self._peer_seq = 0
         if self.rank == self.root:
-            st = self._lib.bgs_peer_buffer_create(device, self.world * nbytes_per_frame, C.byref(self._peer_ptr), handle)
+            st = self._lib.bgs_peer_buffer_create(device, self._peer_flags_off + 4 * self.world, C.byref(self._peer_ptr), handle)
             if st != abi.BGS_OK:
                 raise abi.BgsError(st, "bgs_peer_buffer_create failed")
         t = torch.frombuffer(bytearray(bytes(handle)), dtype=torch.uint8).clone().to(torch.device("cuda", torch.cuda.current_device()))
@@ -102,10 +105,30 @@ class MultiViewSession:
             self._peer_opened = 1
         return int(self._peer_ptr.value)
 
-    def push_device(self, local_ptr: int, nbytes: int) -> None:
-        st = self._lib.bgs_push_frame(self.plugin._ctx, C.c_void_p(local_ptr), self._peer_ptr, self.rank, nbytes)
+    def push_device(self, local_ptr: int, nbytes: int, signal: bool = False) -> int:
+        """Queue the push of this rank's finished frame into its slot of the root's array.  signal=True also stores
+        this push's sequence number (1, 2, ... per session) into the slot's completion word, ordered after the copy on
+        the same stream; the root pairs it with wait_frames(stream, sequence).  Returns the sequence."""
+        self._peer_seq += 1
+        if signal:
+            st = self._lib.bgs_push_frame_signal(self.plugin._ctx, C.c_void_p(local_ptr), self._peer_ptr, self.rank, nbytes,
+                                                 C.c_void_p(self._peer_ptr.value + self._peer_flags_off), self._peer_seq & 0xFFFFFFFF)
+        else:
+            st = self._lib.bgs_push_frame(self.plugin._ctx, C.c_void_p(local_ptr), self._peer_ptr, self.rank, nbytes)
         if st != abi.BGS_OK:
             raise abi.BgsError(st, "bgs_push_frame failed")
+        return self._peer_seq
+
+    def wait_frames(self, stream_ptr: int, sequence: int) -> None:
+        """Root: make `stream_ptr` wait (on the device, no host round-trip) until every rank's push number `sequence`
+        has landed.  Every rank must queue that push, or the stream never resumes."""
+        st = self._lib.bgs_wait_frames(C.c_void_p(stream_ptr), C.c_void_p(self._peer_ptr.value + self._peer_flags_off),
+                                       self.world, sequence & 0xFFFFFFFF)
+        if st != abi.BGS_OK:
+            raise abi.BgsError(st, "bgs_wait_frames failed")
+
+    def peer_flags_ptr(self) -> int:
+        return int(self._peer_ptr.value) + self._peer_flags_off
 
     def release_peer_frames(self) -> None:
         if getattr(self, "_peer_ptr", None) is not None and self._peer_ptr:

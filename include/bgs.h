@@ -214,6 +214,19 @@ bgs_status bgs_peer_buffer_open(int cuda_device, const void* handle64, void** ou
 void bgs_peer_buffer_release(void* ptr, int opened);
 bgs_status bgs_push_frame(bgs_context* ctx, const void* local_frame, void* remote_frames, int index, size_t bytes);
 
+/* Device-side completion for the copy-engine gather.  bgs_push_frame_signal = bgs_push_frame, then the 32-bit word
+ * remote_flags[index] is set to `sequence` by the same stream (ordered after the copy; the words live in the peer buffer,
+ * e.g. behind the frames, and start at 0 -- bgs_peer_buffer_create clears the allocation).  bgs_wait_frames makes
+ * `cuda_stream` (a CUstream / cudaStream_t of the consumer, NULL = the legacy default stream) wait until
+ * flags[0..count) have all reached `sequence` (cyclic >=, so sequences may wrap): work queued behind it sees every
+ * frame of that step.  Senders use increasing sequences (frame number + 1).  No host round-trip and no cross-process
+ * event is involved; the caller must make sure every awaited push is eventually queued, or the stream never resumes.
+ * Replaces: the queue-submission order that makes a finished view target visible to its consumer in the reference
+ * (src/render/mod.rs:1501-1569 draws inside the view's render pass; here the producer is another process / GPU). */
+bgs_status bgs_push_frame_signal(bgs_context* ctx, const void* local_frame, void* remote_frames, int index, size_t bytes,
+                                 void* remote_flags, uint32_t sequence);
+bgs_status bgs_wait_frames(void* cuda_stream, const void* flags, int count, uint32_t sequence);
+
 #ifdef __cplusplus
 }
 #endif

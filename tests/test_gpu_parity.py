@@ -776,3 +776,59 @@ def test_overflow_of_an_earlier_queued_frame_is_reported(plugin):
         h2.destroy()
     finally:
         p2.destroy()
+
+
+@pytest.mark.gpu
+def test_copy_engine_gather_with_device_side_signalling(plugin):
+    """Row e (copy-engine gather): frames pushed into a frame stack with bgs_push_frame_signal, the consumer's stream held by
+    bgs_wait_frames until every slot's sequence word has arrived.  One process and one GPU here (the slots are written by the
+    same device); the cross-process form runs in bench.py --gpus N (`gather_ce`)."""
+    import ctypes as C
+
+    import torch
+
+    from bevy_gaussian_splatting_b200 import abi
+
+    lib = abi.load()
+    w, h, slots = 320, 200, 3
+    nbytes = w * h * 4
+    flags_off = (slots * nbytes + 255) & ~255
+    base, handle = C.c_void_p(), (C.c_ubyte * 64)()
+    assert lib.bgs_peer_buffer_create(0, flags_off + 4 * slots, C.byref(base), handle) == abi.BGS_OK
+    flags = C.c_void_p(base.value + flags_off)
+    cu = C.CDLL("libcuda.so.1")
+    cu.cuMemcpyDtoH_v2.argtypes = [C.c_void_p, C.c_uint64, C.c_size_t]
+
+    def read(ptr, n):
+        got = np.empty(n, np.uint8)
+        assert cu.cuMemcpyDtoH_v2(got.ctypes.data_as(C.c_void_p), C.c_uint64(ptr), n) == 0
+        return got
+
+    hd = plugin.add_cloud(B.random_gaussians_3d_seeded(20000, 7))
+    s = B.CloudSettings(global_scale=0.3)
+    consumer = torch.cuda.Stream()
+    try:
+        assert not read(flags.value, 4 * slots).any()                     # the allocation starts cleared
+        wants = []
+        for seq in (1, 2):
+            for i in range(slots):
+                view = B.perspective_view((4.0 * np.cos(i + seq), 1.5, 4.0 * np.sin(i + seq)), (0, 0, 0), w, h)
+                wants.append(plugin.render_view(hd, s, view, fmt="rgba8_srgb"))
+                plugin.render_view(hd, s, view, fmt="rgba8_srgb", to_host=False, asynchronous=True)
+                st = lib.bgs_push_frame_signal(plugin._ctx, C.c_void_p(plugin.frame_device_ptr), base, i, nbytes, flags, seq)
+                assert st == abi.BGS_OK
+            assert lib.bgs_wait_frames(C.c_void_p(consumer.cuda_stream), flags, slots, seq) == abi.BGS_OK
+            consumer.synchronize()                                        # returns only when all three words reached seq
+            got = read(base.value, slots * nbytes).reshape(slots, h, w, 4)
+            for i in range(slots):
+                assert np.array_equal(got[i], wants[-slots + i]), (seq, i)
+            assert np.array_equal(read(flags.value, 4 * slots).view(np.uint32), np.full(slots, seq, np.uint32))
+        # the compare is a cyclic >=: waiting for an older sequence passes at once
+        assert lib.bgs_wait_frames(C.c_void_p(consumer.cuda_stream), flags, slots, 1) == abi.BGS_OK
+        consumer.synchronize()
+        assert plugin.sync()
+        assert lib.bgs_wait_frames(None, None, slots, 1) == abi.BGS_EINVAL
+        assert lib.bgs_push_frame_signal(plugin._ctx, C.c_void_p(plugin.frame_device_ptr), base, 0, nbytes, None, 1) == abi.BGS_EINVAL
+    finally:
+        hd.destroy()
+        lib.bgs_peer_buffer_release(base, 0)
