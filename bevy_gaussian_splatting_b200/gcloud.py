@@ -445,6 +445,13 @@ def decode_gcloud(data) -> PlanarGaussian3d:
     """`PlanarGaussian3d::decode` (src/io/gcloud/flexbuffers.rs:18-21): structural, like serde -- structs from maps
     (or from sequences in field order), arrays from any vector of numbers; a missing plane is an error, a missing
     FIELD takes its default (`#[serde(default)]`, planar_3d.rs:45-54)."""
+    try:
+        return _decode_gcloud(data)
+    except (KeyError, IndexError, OverflowError, MemoryError) as e:
+        raise FlexBufferError(f"malformed gcloud: {type(e).__name__}: {e}") from e
+
+
+def _decode_gcloud(data) -> PlanarGaussian3d:
     r = root(data)
     if r.type == FBT_MAP:
         top = r.as_dict()
@@ -459,6 +466,8 @@ def decode_gcloud(data) -> PlanarGaussian3d:
         if pr is None or not pr.is_vector():
             raise FlexBufferError(f"plane {key.decode()} missing")
         n = len(pr)
+        if n > len(data):
+            raise FlexBufferError("element count exceeds the buffer")     # a corrupted length must not size an allocation
         n_ref = n if n_ref is None else n_ref
         if n != n_ref:
             raise FlexBufferError("planes differ in length")

@@ -58,10 +58,18 @@ def _read_header(f):
 
 
 def parse_ply_3d(source) -> PlanarGaussian3d:
-    """`source`: path, bytes or binary file object."""
+    """`source`: path, bytes or binary file object.  A malformed file raises ValueError (ply.rs returns io::Error)."""
     if isinstance(source, (str, os.PathLike)):
         with open(source, "rb") as fh:
             return parse_ply_3d(fh.read())
+    try:
+        with np.errstate(over="ignore", invalid="ignore"):
+            return _parse_ply_3d(source)
+    except (TypeError, IndexError, KeyError, UnicodeDecodeError, OverflowError, MemoryError) as e:
+        raise ValueError(f"malformed ply: {type(e).__name__}: {e}") from e
+
+
+def _parse_ply_3d(source) -> PlanarGaussian3d:
     f = io.BytesIO(source) if isinstance(source, (bytes, bytearray)) else source
     fmt, elements = _read_header(f)
     vertex = None

@@ -333,6 +333,7 @@ inline PlanarGaussian3d decode_gcloud(const unsigned char* data, size_t len) {
         if (!vec.is_vector()) throw std::runtime_error(std::string("gcloud: ") + planes[p].name + " is not a vector");
         const size_t cnt = vec.size();
         if (p == 0) n = cnt; else if (cnt != n) throw std::runtime_error("gcloud: planes disagree on the gaussian count");
+        if (cnt > len) throw std::runtime_error("gcloud: element count exceeds the buffer");   // every element occupies >= 1 byte: a corrupted length must not size an allocation
         planes[p].dst->reserve(cnt * (planes[p].w0 + (planes[p].f1 ? 1 : 0)));
         for (size_t i = 0; i < cnt; ++i) {
             const flex::Ref e = vec.at(i);

@@ -190,3 +190,57 @@ def test_cpp_gcloud_reader_and_writer_interoperate_with_python(tmp_path):
     # malformed input: a status, not a crash
     (tmp_path / "bad.gcloud").write_bytes(open(tmp_path / "py.gcloud", "rb").read()[:-7])
     assert subprocess.run([tool, str(tmp_path / "bad.gcloud"), str(tmp_path / "o.bin")], capture_output=True).returncode == 2
+
+
+def test_damaged_files_are_errors_in_both_hosts(tmp_path):
+    """Truncated, bit-flipped and tail-corrupted `.ply` / `.gcloud` files: the Python loaders raise ValueError, the C++ loader
+    exits with its error code -- never a crash, a hang or an allocation sized by a corrupted count (the loaders of the
+    reference return io::Error, src/io/loader.rs:38-66).  A longer run of the same mutations under ASan / UBSan is logged
+    in profiles/r2_fuzz.txt."""
+    import io as pyio
+    import os
+    import subprocess
+
+    import bevy_gaussian_splatting_b200.io as IO
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.run(["make", "-C", os.path.join(root, "examples"), "-s", "cloud_tool"], check=True)
+    tool = os.path.join(root, "examples", "cloud_tool")
+    cloud = B.random_gaussians_3d_seeded(29, 3)
+    IO.write_ply_3d(tmp_path / "a.ply", cloud)
+    G.write_gcloud(tmp_path / "a.gcloud", cloud)
+    rng = np.random.default_rng(11)
+    outcomes = set()
+    for ext in ("ply", "gcloud"):
+        data = (tmp_path / f"a.{ext}").read_bytes()
+        for it in range(40):
+            b = bytearray(data)
+            mode = it % 3
+            if mode == 0:
+                b = b[: int(rng.integers(0, len(b)))]
+            elif mode == 1:
+                for _ in range(int(rng.integers(1, 8))):
+                    b[int(rng.integers(0, len(b)))] = int(rng.integers(0, 256))
+            else:   # the flexbuffer root and the plane offsets live at the END of a .gcloud; the header at the start of a .ply
+                lo = max(0, len(b) - 64) if ext == "gcloud" else 0
+                for _ in range(int(rng.integers(1, 6))):
+                    b[lo + int(rng.integers(0, 64))] = int(rng.integers(0, 256))
+            try:
+                if ext == "ply":
+                    IO.parse_ply_3d(pyio.BytesIO(bytes(b)))
+                else:
+                    G.decode_gcloud(bytes(b))
+                outcomes.add((ext, "py-ok"))
+            except ValueError:
+                outcomes.add((ext, "py-error"))
+            if it % 4 == 0:   # (a process per case: a sample is enough here)
+                fn = tmp_path / f"m.{ext}"
+                fn.write_bytes(bytes(b))
+                r = subprocess.run([tool, str(fn), str(tmp_path / "o.bin")], capture_output=True, timeout=60)
+                assert r.returncode in (0, 2), (ext, it, r.returncode, r.stderr.decode()[-300:])
+                outcomes.add((ext, "cpp-ok" if r.returncode == 0 else "cpp-error"))
+    assert {("ply", "py-error"), ("gcloud", "py-error"), ("ply", "cpp-error"), ("gcloud", "cpp-error")} <= outcomes
+    # the one the sanitizer run found: a plane whose length slot claims more elements than the buffer has bytes
+    with pytest.raises(ValueError):
+        bad = bytearray((tmp_path / "a.gcloud").read_bytes())
+        G.decode_gcloud(bytes(bad[:-3]) + b"\xff\xff\xff")
