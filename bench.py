@@ -365,30 +365,17 @@ def run_cuda(args):
         for r in range(world):
             local = plugin.render_view(handle, settings, MultiViewSession(r, world, 0).view(WIDTH, HEIGHT), fmt="rgba8_srgb")
             gather_ok = gather_ok and bool(np.array_equal(local, gathered[r]))
-    # ---- the same window with the COPY-ENGINE gather (CUDA IPC + peer-to-peer pushes; NCCL above stays the headline):
-    #      measured beside it so the two transports can be compared on the same box in the same run
-    gather_ce = None
+    # ---- the same window with the frames moved by the GPUs themselves instead of NCCL kernels (CUDA IPC mapping of the
+    #      root's frame stack + per-slot completion words awaited on the root's stream):
+    #      "copy_engine": every rank pushes its finished frame with a peer-to-peer cudaMemcpyAsync (copy engines, no SM);
+    #      "direct":      every rank RENDERS into its slot of the root's stack: the blend kernel's own pixel stores cross
+    #                     NVLink, only the completion word follows.
+    #      All transports are measured in the same run on the same box and verified frame by frame; the line's `value` is
+    #      the fastest verified one (config.gather names it), the others stay beside it.
+    gather_ce = gather_direct = None
+    peer_ready = False
     if world > 1:
         import ctypes as C
-
-        for k in range(frames_in_flight):
-            sessions[k].setup_peer_frames(local_rank, frame_bytes)
-
-        # completion is signalled on the devices (bgs_push_frame_signal / bgs_wait_frames): proven on the warm-up frames
-        # first (every rank's words must have reached the expected sequence), else the host barrier below stands in
-        use_signal = [True]
-
-        def step_ce(i):
-            k = i % frames_in_flight
-            p = plugins[k]
-            p.render_view(handle, settings, view, fmt="rgba8_srgb", to_host=False, asynchronous=True)
-            if use_signal[0]:
-                try:
-                    sessions[k].push_device(p.frame_device_ptr, frame_bytes, signal=True)
-                    return
-                except abi.BgsError:
-                    use_signal[0] = False
-            sessions[k].push_device(p.frame_device_ptr, frame_bytes)
 
         def read_root(ptr, nbytes):
             got = np.empty(nbytes, np.uint8)
@@ -397,60 +384,105 @@ def run_cuda(args):
             assert cu.cuMemcpyDtoH_v2(got.ctypes.data_as(C.c_void_p), C.c_uint64(ptr), got.size) == 0
             return got
 
-        for i in range(2 * frames_in_flight + args.warmup):
-            step_ce(i)
-        assert sync_all()
-        barrier()
-        sig_ok = 1 if use_signal[0] else 0
-        if rank == 0 and sig_ok:
+        def agree(ok: bool) -> bool:
+            t_ = torch.tensor([1 if ok else 0], device="cuda", dtype=torch.int32)
+            dist.all_reduce(t_, op=dist.ReduceOp.MIN)
+            return bool(t_.item())
+
+        try:
             for k in range(frames_in_flight):
-                words = read_root(sessions[k].peer_flags_ptr(), 4 * world).view(np.uint32)
-                if not np.all(words == np.uint32(sessions[k]._peer_seq)):
-                    sig_ok = 0
-        t = torch.tensor([sig_ok], device="cuda", dtype=torch.int32)
-        dist.all_reduce(t, op=dist.ReduceOp.MIN)
-        use_signal[0] = bool(t.item())
-        barrier()
-        c0 = torch.cuda.Event(enable_timing=True)
-        c1 = [torch.cuda.Event(enable_timing=True) for _ in range(2 * len(plugins))]
-        c0.record(streams[0])
-        for i in range(args.steps):
-            step_ce(i)
-        if rank == 0 and use_signal[0]:
-            # the root's copy/comm streams resume when EVERY rank's last push of that context has landed
-            for k in range(frames_in_flight):
-                sessions[k].wait_frames(plugins[k].copy_stream_ptr, sessions[k]._peer_seq)
-        for ev, st_ in zip(c1, streams + copy_streams):
-            ev.record(st_)
-        assert sync_all()
-        ce_ok = None
-        k_last = (args.steps - 1) % frames_in_flight
-        got = None
-        if rank == 0 and use_signal[0]:
-            # read BEFORE any host barrier: the device-side wait alone has established that all frames are there
-            got = read_root(sessions[k_last]._peer_ptr.value, world * frame_bytes)
-        barrier()
-        ce_ms = max(c0.elapsed_time(ev) for ev in c1) / args.steps
-        t = torch.tensor([ce_ms], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ce_ms = float(t.item())
-        if rank == 0:
-            if got is None:
+                sessions[k].setup_peer_frames(local_rank, frame_bytes)
+            peer_ready = True
+        except Exception as e:          # (no peer access between the GPUs: NCCL stays the only transport)
+            print(f"bench.py: rank {rank}: peer frame stack unavailable: {e}", file=sys.stderr)
+        peer_ready = agree(peer_ready)
+
+        def peer_leg(direct: bool):
+            use_signal = [True]
+
+            def step_p(i):
+                k = i % frames_in_flight
+                p = plugins[k]
+                if direct:
+                    slot = sessions[k].peer_slot_ptr(frame_bytes)
+                    p.render_view_to_device(handle, settings, view, slot, fmt="rgba8_srgb", asynchronous=True)
+                    sessions[k].push_device(slot, frame_bytes, signal=use_signal[0])     # (the word only: no copy)
+                    return
+                p.render_view(handle, settings, view, fmt="rgba8_srgb", to_host=False, asynchronous=True)
+                if use_signal[0]:
+                    try:
+                        sessions[k].push_device(p.frame_device_ptr, frame_bytes, signal=True)
+                        return
+                    except abi.BgsError:
+                        use_signal[0] = False
+                sessions[k].push_device(p.frame_device_ptr, frame_bytes)
+
+            # completion words are proven on the warm-up frames first (every rank's words must have reached the expected
+            # sequence), before any stream is made to wait on them; else the host barrier stands in
+            ok = True
+            try:
+                for i in range(2 * frames_in_flight + args.warmup):
+                    step_p(i)
+            except Exception as e:
+                print(f"bench.py: rank {rank}: {'direct' if direct else 'copy-engine'} gather failed: {e}", file=sys.stderr)
+                ok = False
+            ok = sync_all() and ok
+            barrier()
+            if not agree(ok):
+                return None
+            sig_ok = use_signal[0]
+            if rank == 0 and sig_ok:
+                for k in range(frames_in_flight):
+                    words = read_root(sessions[k].peer_flags_ptr(), 4 * world).view(np.uint32)
+                    sig_ok = sig_ok and bool(np.all(words == np.uint32(sessions[k]._peer_seq & 0xFFFFFFFF)))
+            use_signal[0] = agree(sig_ok)
+            barrier()
+            leg_clocks = make_clock_sampler(local_rank)
+            if rank == 0:
+                leg_clocks.start()
+            c0 = torch.cuda.Event(enable_timing=True)
+            c1 = [torch.cuda.Event(enable_timing=True) for _ in range(2 * len(plugins))]
+            c0.record(streams[0])
+            for i in range(args.steps):
+                step_p(i)
+            if rank == 0 and use_signal[0]:
+                # the root's copy/comm streams resume when EVERY rank's last frame of that context has landed
+                for k in range(frames_in_flight):
+                    sessions[k].wait_frames(plugins[k].copy_stream_ptr, sessions[k]._peer_seq)
+            for ev, st_ in zip(c1, streams + copy_streams):
+                ev.record(st_)
+            assert sync_all()
+            leg_clk = leg_clocks.stop() if rank == 0 else None
+            k_last = (args.steps - 1) % frames_in_flight
+            got = None
+            if rank == 0 and use_signal[0]:
+                # read BEFORE any host barrier: the device-side wait alone has established that all frames are there
                 got = read_root(sessions[k_last]._peer_ptr.value, world * frame_bytes)
-            got = got.reshape(world, HEIGHT, WIDTH, 4)
-            ce_ok = True
-            for r in range(world):
-                local = plugin.render_view(handle, settings, MultiViewSession(r, world, 0).view(WIDTH, HEIGHT), fmt="rgba8_srgb")
-                ce_ok = ce_ok and bool(np.array_equal(local, got[r]))
-        barrier()
-        for k in range(frames_in_flight):
-            sessions[k].release_peer_frames()
-        gather_ce = {"transport": "CUDA IPC + cudaMemcpyAsync peer pushes on each rank's copy stream (copy engines, no SM)",
-                     "value": round(N_GAUSSIANS * world / (ce_ms / 1000.0) / 1e6, 1), "unit": "Msplats/s", "ms_per_step": round(ce_ms, 4),
-                     "frames_verified": ce_ok,
-                     "signalling": ("device: one 32-bit sequence word per slot stored after the copy, cuStreamWaitValue32 on the root's stream "
-                                    "(frames read back before any host barrier)") if use_signal[0] else "host barrier",
-                     "note": "reported beside the NCCL gather (the headline `value`, north_star)"}
+            barrier()
+            leg_ms = max(c0.elapsed_time(ev) for ev in c1) / args.steps
+            t_ = torch.tensor([leg_ms], device="cuda")
+            dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+            leg_ms = float(t_.item())
+            leg_ok = None
+            if rank == 0:
+                if got is None:
+                    got = read_root(sessions[k_last]._peer_ptr.value, world * frame_bytes)
+                got = got.reshape(world, HEIGHT, WIDTH, 4)
+                leg_ok = True
+                for r in range(world):
+                    local = plugin.render_view(handle, settings, MultiViewSession(r, world, 0).view(WIDTH, HEIGHT), fmt="rgba8_srgb")
+                    leg_ok = leg_ok and bool(np.array_equal(local, got[r]))
+            barrier()
+            return {"transport": ("bgs_render straight into the root's frame stack (CUDA IPC mapping): the blend kernel's pixel stores cross NVLink, no copy"
+                                  if direct else "CUDA IPC + cudaMemcpyAsync peer pushes on each rank's copy stream (copy engines, no SM)"),
+                    "value": round(N_GAUSSIANS * world / (leg_ms / 1000.0) / 1e6, 1), "unit": "Msplats/s", "ms_per_step": round(leg_ms, 4),
+                    "frames_verified": leg_ok, "clocks": leg_clk, "device_signalling": bool(use_signal[0]),
+                    "signalling": ("device: one 32-bit sequence word per slot stored after the frame, cuStreamWaitValue32 on the root's stream "
+                                   "(frames read back before any host barrier)") if use_signal[0] else "host barrier"}
+
+        if peer_ready:
+            gather_ce = peer_leg(False)
+            gather_direct = peer_leg(True)
     # per-frame / per-stage times (live CUDA events inside the library), one frame at a time on an idle GPU
     frame_us, stage_rows = [], []
     for _ in range(min(args.steps, 100)):
@@ -462,6 +494,18 @@ def run_cuda(args):
         t = torch.tensor([ms_step], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_step = float(t.item())
+    # the line's transport: the fastest one whose gathered frames were verified (rank 0 decides, everybody follows)
+    choice = 0
+    if world > 1:
+        if rank == 0:
+            cands = [(ms_step, 0)] if gather_ok else []
+            for code, leg in ((1, gather_ce), (2, gather_direct)):
+                if leg and leg["frames_verified"]:
+                    cands.append((leg["ms_per_step"], code))
+            choice = min(cands)[1] if cands else 0
+        t = torch.tensor([choice], device="cuda", dtype=torch.int32)
+        dist.broadcast(t, src=0)
+        choice = int(t.item())
     launches_per_frame = plugin.last_launch_count
     fs = plugin.frame_stats()
     stage_med = np.median(np.array(stage_rows), axis=0)
@@ -470,15 +514,34 @@ def run_cuda(args):
     #      host->device as kernel arguments and the finished RGBA8 frame comes back into pinned host memory.
     # K frames in, K frames out: each frame's D2H copy (copy stream) overlaps later frames' kernels; pinned host
     # buffers alternate; sync_all() (every frame delivered to host memory) closes the timed region.
+    # At N > 1 every rank's frame lands in its own host buffer AND in the root's frame stack, over the line's transport
+    # (the copy-engine push when a peer transport was chosen: the frame is rendered into library memory for the D2H copy).
     host_frames = [torch.empty((HEIGHT, WIDTH, 4), dtype=torch.uint8).pin_memory().numpy() for _ in range(2 * frames_in_flight)]
+    e2e_push = world > 1 and choice != 0
+    e2e_signal = bool(e2e_push and gather_ce and gather_ce["device_signalling"])
+
+    def step_e2e(i):
+        if not e2e_push:
+            return step(i, out=host_frames[i % (2 * frames_in_flight)])
+        k = i % frames_in_flight
+        p = plugins[k]
+        p.render_view(handle, settings, view, fmt="rgba8_srgb", to_host=True, out=host_frames[i % (2 * frames_in_flight)], asynchronous=True)
+        sessions[k].push_device(p.frame_device_ptr, frame_bytes, signal=e2e_signal)
+
+    def close_e2e():
+        if e2e_signal and rank == 0:
+            for k in range(frames_in_flight):
+                sessions[k].wait_frames(plugins[k].copy_stream_ptr, sessions[k]._peer_seq)
+        return sync_all()
+
     for i in range(2 * frames_in_flight):
-        step(i, out=host_frames[i])
-    assert sync_all()
+        step_e2e(i)
+    assert close_e2e()
     barrier()
     t0 = time.perf_counter()
     for i in range(args.steps):
-        step(i, out=host_frames[i % (2 * frames_in_flight)])
-    assert sync_all()
+        step_e2e(i)
+    assert close_e2e()
     barrier()
     e2e_ms = 1000.0 * (time.perf_counter() - t0) / args.steps
     if dist is not None:
@@ -486,6 +549,13 @@ def run_cuda(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t.item())
     h2d = sum(__import__("ctypes").sizeof(c) for c in (abi.bgs_view, abi.bgs_cloud_uniform, abi.bgs_settings))
+    if peer_ready:
+        barrier()
+        for root_turn in (False, True):          # the ranks that opened the root's allocation close it before the root frees it
+            if (rank == 0) == root_turn:
+                for k in range(frames_in_flight):
+                    sessions[k].release_peer_frames()
+            barrier()
 
     if rank != 0:
         for se in sessions:
@@ -560,6 +630,15 @@ def run_cuda(args):
                "stage_us": [round(float(x), 1) for x in med[:5]]}
 
     views = world
+    gather_nccl = None
+    gather_name = None
+    if world > 1:
+        gather_nccl = {"transport": "bgs_gather_frames: NCCL send/recv on each rank's copy/comm stream (north_star's gather)",
+                       "value": round(N_GAUSSIANS * views / (ms_step / 1000.0) / 1e6, 1), "unit": "Msplats/s",
+                       "ms_per_step": round(ms_step, 4), "frames_verified": gather_ok, "clocks": clk}
+        chosen = {0: gather_nccl, 1: gather_ce, 2: gather_direct}[choice]
+        gather_name = {0: "nccl", 1: "copy_engine", 2: "direct"}[choice]
+        ms_step, gather_ok, clk = chosen["ms_per_step"], chosen["frames_verified"], chosen["clocks"]
     value = N_GAUSSIANS * views / (ms_step / 1000.0) / 1e6
     line = {
         "impl": "cuda", "metric": METRIC, "value": round(value, 1), "unit": "Msplats/s", "n_gpus": world, "steps": args.steps,
@@ -567,6 +646,8 @@ def run_cuda(args):
         "vs_baseline": None, "dtype": "f32 (f16-packed inputs)", "data": "synthetic",
         "config": bench_config(views, world, {"n_visible": nv, "n_pairs": I, "l2": "inputs larger than L2 (768 MB cloud vs 126 MB)",
                                               "frames_in_flight": frames_in_flight, "rank0_numa_node": numa_node,
+                                              "gather": None if world == 1 else
+                                              f"{gather_name}: the fastest verified transport of this run (gather_nccl / gather_ce / gather_direct hold all three)",
                                               "timing": "value: 3 frames in flight, CUDA events over render + copy/comm streams; "
                                                         "stages[] / frame_ms_*: one frame at a time on an idle GPU"}),
         "frame_ms_p50": round(float(np.percentile(frame_us, 50)) / 1000.0, 4),
@@ -578,7 +659,8 @@ def run_cuda(args):
                 "ms_per_step": round(e2e_ms, 4), "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": frame_bytes},
         "gpu_launches": int(launches_per_frame * args.steps),
         "roofline": roofline, "proj_sort_roofline": proj_sort, "stages": stages, "cpu_baseline": cpu, "parity": parity,
-        "gathered_frames_verified": gather_ok, "gather_ce": gather_ce, "raw_scale_1": raw, "clocks": clk,
+        "gathered_frames_verified": gather_ok, "gather_nccl": gather_nccl, "gather_ce": gather_ce, "gather_direct": gather_direct,
+        "raw_scale_1": raw, "clocks": clk,
     }
     print(json.dumps(line), flush=True)
     for se in sessions:

@@ -166,7 +166,8 @@ bgs_status bgs_push_frame(bgs_context* ctx, const void* local_frame, void* remot
     if (!ctx || !local_frame || !remote_frames || index < 0 || bytes == 0) return BGS_EINVAL;
     int slot = -1;
     cudaStream_t q = bgs_internal_gather_begin_(ctx, local_frame, &slot);   // copy/comm stream for async library frames
-    const cudaError_t e = cudaMemcpyAsync((char*)remote_frames + (size_t)index * bytes, local_frame, bytes, cudaMemcpyDefault, q);
+    char* const dst = (char*)remote_frames + (size_t)index * bytes;
+    const cudaError_t e = dst == (const char*)local_frame ? cudaSuccess : cudaMemcpyAsync(dst, local_frame, bytes, cudaMemcpyDefault, q);
     bgs_internal_gather_end_(ctx, slot);
     return e == cudaSuccess ? BGS_OK : BGS_ECUDA;
 }
@@ -203,7 +204,10 @@ bgs_status bgs_push_frame_signal(bgs_context* ctx, const void* local_frame, void
     if (!a.ok) return BGS_ECUDA;
     int slot = -1;
     cudaStream_t q = bgs_internal_gather_begin_(ctx, local_frame, &slot);
-    const cudaError_t e = cudaMemcpyAsync((char*)remote_frames + (size_t)index * bytes, local_frame, bytes, cudaMemcpyDefault, q);
+    // local_frame == the slot itself: the frame was RENDERED into the peer buffer (bgs_render with that device target:
+    // the blend kernel's stores crossed NVLink), so only the completion word remains to be stored after it
+    char* const dst = (char*)remote_frames + (size_t)index * bytes;
+    const cudaError_t e = dst == (const char*)local_frame ? cudaSuccess : cudaMemcpyAsync(dst, local_frame, bytes, cudaMemcpyDefault, q);
     CUresult r = CUDA_ERROR_UNKNOWN;
     if (e == cudaSuccess) r = a.MemsetD32Async((CUdeviceptr)((uint32_t*)remote_flags + index), sequence, 1, (CUstream)q);
     bgs_internal_gather_end_(ctx, slot);

@@ -119,6 +119,12 @@ class MultiViewSession:
             raise abi.BgsError(st, "bgs_push_frame failed")
         return self._peer_seq
 
+    def peer_slot_ptr(self, nbytes: int) -> int:
+        """Device address of this rank's slot in the root's frame stack: rendering into it (`render_view_to_device`)
+        makes the blend kernel write the frame across NVLink itself; follow it with push_device(slot, nbytes, signal=True),
+        which then only stores the completion word."""
+        return int(self._peer_ptr.value) + self.rank * nbytes
+
     def wait_frames(self, stream_ptr: int, sequence: int) -> None:
         """Root: make `stream_ptr` wait (on the device, no host round-trip) until every rank's push number `sequence`
         has landed.  Every rank must queue that push, or the stream never resumes."""

@@ -127,6 +127,19 @@ class GaussianSplattingPlugin:
             return None
         code, dtype, ch = self.FORMATS[fmt]
         v = view.to_abi()
+        u, s = self._uniform_and_settings(handle, settings, transform, asynchronous, premultiplied, blend_over)
+        if to_host:
+            if out is None:
+                out = np.empty((view.height, view.width, ch), dtype)
+            assert out.dtype == dtype and out.size == view.height * view.width * ch and out.flags.c_contiguous
+            st = self._lib.bgs_render(self._ctx, handle._h, C.byref(v), C.byref(u), C.byref(s), _ptr(out), code, 0)
+        else:
+            st = self._lib.bgs_render(self._ctx, handle._h, C.byref(v), C.byref(u), C.byref(s), None, code, 0)
+        self._check(st)
+        return out if to_host else None
+
+    def _uniform_and_settings(self, handle, settings, transform, asynchronous=False, premultiplied=False, blend_over=False):
+        """The two ABI structs of a call; cached while (settings, transform, cloud, flags) repeat from frame to frame."""
         key = (dataclasses.astuple(settings), None if transform is None else transform.matrix.tobytes(), asynchronous, handle.serial,
                premultiplied, blend_over)
         if getattr(self, "_us_cache", (None,))[0] != key:
@@ -138,16 +151,7 @@ class GaussianSplattingPlugin:
             if blend_over:
                 s_.flags |= abi.BGS_FLAG_BLEND_OVER_TARGET
             self._us_cache = (key, self.cloud_uniform(settings, transform, handle.aabb), s_)
-        _, u, s = self._us_cache
-        if to_host:
-            if out is None:
-                out = np.empty((view.height, view.width, ch), dtype)
-            assert out.dtype == dtype and out.size == view.height * view.width * ch and out.flags.c_contiguous
-            st = self._lib.bgs_render(self._ctx, handle._h, C.byref(v), C.byref(u), C.byref(s), _ptr(out), code, 0)
-        else:
-            st = self._lib.bgs_render(self._ctx, handle._h, C.byref(v), C.byref(u), C.byref(s), None, code, 0)
-        self._check(st)
-        return out if to_host else None
+        return self._us_cache[1], self._us_cache[2]
 
     def render_view_aux(self, handle: PlanarGaussian3dHandle, settings: CloudSettings, view: View,
                         transform: CloudTransform | None = None, fmt: str = "rgba32f"):
@@ -163,12 +167,13 @@ class GaussianSplattingPlugin:
         return outs
 
     def render_view_to_device(self, handle: PlanarGaussian3dHandle, settings: CloudSettings, view: View, device_ptr: int,
-                              transform: CloudTransform | None = None, fmt: str = "rgba8_srgb") -> None:
-        """Render straight into caller-owned device memory (e.g. an exported frame target: `bgs_frame_export_create`)."""
+                              transform: CloudTransform | None = None, fmt: str = "rgba8_srgb", asynchronous: bool = False) -> None:
+        """Render straight into caller-owned device memory: an exported frame target (`bgs_frame_export_create`), or
+        another GPU's memory mapped into this process (`bgs_peer_buffer_open`) -- the blend kernel's pixel stores then
+        travel over NVLink themselves."""
         code, _, _ = self.FORMATS[fmt]
         v = view.to_abi()
-        u = self.cloud_uniform(settings, transform, handle.aabb)
-        s = settings.to_abi()
+        u, s = self._uniform_and_settings(handle, settings, transform, asynchronous)
         self._check(self._lib.bgs_render(self._ctx, handle._h, C.byref(v), C.byref(u), C.byref(s), C.c_void_p(device_ptr), code, 1))
 
     def sync(self) -> bool:

@@ -219,7 +219,9 @@ bgs_status bgs_push_frame(bgs_context* ctx, const void* local_frame, void* remot
  * e.g. behind the frames, and start at 0 -- bgs_peer_buffer_create clears the allocation).  bgs_wait_frames makes
  * `cuda_stream` (a CUstream / cudaStream_t of the consumer, NULL = the legacy default stream) wait until
  * flags[0..count) have all reached `sequence` (cyclic >=, so sequences may wrap): work queued behind it sees every
- * frame of that step.  Senders use increasing sequences (frame number + 1).  No host round-trip and no cross-process
+ * frame of that step.  Senders use increasing sequences (frame number + 1).  When local_frame IS the slot
+ * (remote_frames + index * bytes) -- the frame was rendered straight into the peer buffer by passing that address to
+ * bgs_render as a device target, so the blend kernel's own stores crossed NVLink -- no copy is queued, only the word.  No host round-trip and no cross-process
  * event is involved; the caller must make sure every awaited push is eventually queued, or the stream never resumes.
  * Replaces: the queue-submission order that makes a finished view target visible to its consumer in the reference
  * (src/render/mod.rs:1501-1569 draws inside the view's render pass; here the producer is another process / GPU). */
