@@ -39,7 +39,8 @@ def _cloud(n, seed, spread=6.0):
 
 
 def _shader(view, u, s):
-    mode = {B.RasterizeMode.Color: "color", B.RasterizeMode.Normal: "normal", B.RasterizeMode.Position: "position"}[s.rasterize_mode]
+    mode = {B.RasterizeMode.Color: "color", B.RasterizeMode.Depth: "depth", B.RasterizeMode.Normal: "normal",
+            B.RasterizeMode.Position: "position"}[s.rasterize_mode]
     return Shader(ViewU(view.to_abi()), CloudU(u), use_obb=not s.aabb, gaussian_2d=s.gaussian_mode == B.GaussianMode.Gaussian2d,
                   adaptive=s.opacity_adaptive_radius, rasterize=mode)
 
@@ -153,8 +154,11 @@ def test_oracle_projection_matches_wgsl_literal(oracle, kw):
 @pytest.mark.parametrize("kw,n,scale", [(dict(), 48, 0.45), (dict(aabb=True), 40, 0.4),
                                         (dict(gaussian_mode=B.GaussianMode.Gaussian2d, aabb=True), 40, 0.5),
                                         (dict(gaussian_mode=B.GaussianMode.Gaussian2d, global_opacity=1.5), 36, 0.5),
-                                        (dict(draw_mode=B.DrawMode.HighlightSelected), 30, 0.4)],
-                         ids=["3dgs-obb", "3dgs-aabb", "2dgs-aabb", "2dgs-obb", "highlight"])
+                                        (dict(draw_mode=B.DrawMode.HighlightSelected), 30, 0.4),
+                                        (dict(rasterize_mode=B.RasterizeMode.Depth), 40, 0.45),
+                                        (dict(rasterize_mode=B.RasterizeMode.Normal), 36, 0.45),
+                                        (dict(rasterize_mode=B.RasterizeMode.Position, gaussian_mode=B.GaussianMode.Gaussian2d), 36, 0.5)],
+                         ids=["3dgs-obb", "3dgs-aabb", "2dgs-aabb", "2dgs-obb", "highlight", "depth", "normal", "2dgs-position"])
 def test_oracle_ref_mode_matches_wgsl_literal_frame(oracle, kw, n, scale):
     """Whole frames: the emulator rasterises the emitted quads (vs_points -> affine patch -> fs_main -> premultiplied
     "over", far -> near) and must reproduce the oracle's ref_mode image."""
@@ -166,11 +170,16 @@ def test_oracle_ref_mode_matches_wgsl_literal_frame(oracle, kw, n, scale):
     tr = CloudTransform(_model())
     u = GaussianSplattingPlugin.cloud_uniform(s, tr, cloud.compute_aabb())
     keys = oracle.keygen(cloud.position_visibility, view.to_abi(), u, 32)
-    _, order = oracle.radix_sort(keys, 32)              # ascending key = far -> near, culled (all-ones) last
-    order = [int(i) for i in order if keys[i] != 0xFFFFFFFF]
+    _, full_order = oracle.radix_sort(keys, 32)         # ascending key = far -> near, culled (all-ones) last
+    order = [int(i) for i in full_order if keys[i] != 0xFFFFFFFF]
     assert len(order) >= 12
     got = oracle.render_ref(cloud, view.to_abi(), u, s.to_abi())
-    want = render_reference_semantics(_shader(view, u, s), cloud, order, w, h,
+    shader = _shader(view, u, s)
+    # RasterizeMode::Depth reads its range from entries 1 and count - 1 of the sorted buffer (gaussian.wgsl:331-332):
+    # with culled gaussians in the cloud the last entry IS a culled one -- the literal behaviour, restated as such
+    shader.depth_entries = (Vec(*cloud.position_visibility[int(full_order[1]), :3].tolist()),
+                            Vec(*cloud.position_visibility[int(full_order[len(cloud) - 1]), :3].tolist()))
+    want = render_reference_semantics(shader, cloud, order, w, h,
                                       highlight_selected=s.draw_mode == B.DrawMode.HighlightSelected)
     assert (want[..., :3].max(axis=2) > 0.02).sum() >= 200, "the scene must actually cover pixels"
     diff = np.abs(got.astype(np.float64) - want)

@@ -435,6 +435,17 @@ class Shader:
             world_normal = view.view_from_world * local_normal
             t = normalize(world_normal)
             rgb = Vec(0.5 * (t.x + 1.0), 0.5 * (t.y + 1.0), 0.5 * (t.z + 1.0))
+        elif self.rasterize == "depth":
+            # gaussian.wgsl:329-349 -- the range comes from two entries of the SORTED buffer, literally entry 1 and entry
+            # count - 1 (`self.depth_entries` = their untransformed positions, set by the caller from the sort it feeds in)
+            first_position, last_position = self.depth_entries
+            min_position = (gu.transform * Vec(last_position, 1.0)).xyz
+            max_position = (gu.transform * Vec(first_position, 1.0)).xyz
+            camera_position = view.world_position
+            min_distance = length(min_position - camera_position)
+            max_distance = length(max_position - camera_position)
+            depth = length(transformed_position - camera_position)
+            rgb = self.depth_to_rgb(depth, min_distance, max_distance)
         elif self.rasterize == "position":
             rgb = (transformed_position - gu.min.xyz) / (gu.max.xyz - gu.min.xyz)
         color = Vec(rgb, opacity * gu.global_opacity)
@@ -443,6 +454,22 @@ class Shader:
         out["color"] = color
         out["vertices"] = [dict(uv=q, position=Vec(projected_position.xy + bb.xy, projected_position.zw), bb=bb) for q, bb in verts]
         return out
+
+    # ---- material/depth.wgsl:3-11 (clamp, smoothstep: WGSL built-ins; smoothstep(e0, e1, x) = t*t*(3 - 2t), t = clamp((x-e0)/(e1-e0), 0, 1))
+    @staticmethod
+    def depth_to_rgb(depth, min_depth, max_depth):
+        def clamp(x, lo, hi):
+            return min(max(x, lo), hi)
+
+        def smoothstep(e0, e1, x):
+            t = clamp((x - e0) / (e1 - e0), 0.0, 1.0)
+            return t * t * (3.0 - 2.0 * t)
+
+        normalized_depth = clamp((depth - min_depth) / (max_depth - min_depth), 0.0, 1.0)
+        r = smoothstep(0.5, 1.0, normalized_depth)
+        g = 1.0 - abs(normalized_depth - 0.5) * 2.0
+        b = 1.0 - smoothstep(0.0, 0.5, normalized_depth)
+        return Vec(r, g, b)
 
     # ---- fs_main, gaussian.wgsl:438-505: the fragment's premultiplied colour, or None for `discard`
     def fs_main(self, vs, uv, major_minor=None):
