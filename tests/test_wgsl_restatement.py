@@ -155,10 +155,11 @@ def test_oracle_projection_matches_wgsl_literal(oracle, kw):
                                         (dict(gaussian_mode=B.GaussianMode.Gaussian2d, aabb=True), 40, 0.5),
                                         (dict(gaussian_mode=B.GaussianMode.Gaussian2d, global_opacity=1.5), 36, 0.5),
                                         (dict(draw_mode=B.DrawMode.HighlightSelected), 30, 0.4),
+                                        (dict(draw_mode=B.DrawMode.Selected), 45, 0.45),
                                         (dict(rasterize_mode=B.RasterizeMode.Depth), 40, 0.45),
                                         (dict(rasterize_mode=B.RasterizeMode.Normal), 36, 0.45),
                                         (dict(rasterize_mode=B.RasterizeMode.Position, gaussian_mode=B.GaussianMode.Gaussian2d), 36, 0.5)],
-                         ids=["3dgs-obb", "3dgs-aabb", "2dgs-aabb", "2dgs-obb", "highlight", "depth", "normal", "2dgs-position"])
+                         ids=["3dgs-obb", "3dgs-aabb", "2dgs-aabb", "2dgs-obb", "highlight", "selected", "depth", "normal", "2dgs-position"])
 def test_oracle_ref_mode_matches_wgsl_literal_frame(oracle, kw, n, scale):
     """Whole frames: the emulator rasterises the emitted quads (vs_points -> affine patch -> fs_main -> premultiplied
     "over", far -> near) and must reproduce the oracle's ref_mode image."""
@@ -180,6 +181,7 @@ def test_oracle_ref_mode_matches_wgsl_literal_frame(oracle, kw, n, scale):
     shader.depth_entries = (Vec(*cloud.position_visibility[int(full_order[1]), :3].tolist()),
                             Vec(*cloud.position_visibility[int(full_order[len(cloud) - 1]), :3].tolist()))
     want = render_reference_semantics(shader, cloud, order, w, h,
+                                      draw_selected=s.draw_mode == B.DrawMode.Selected,
                                       highlight_selected=s.draw_mode == B.DrawMode.HighlightSelected)
     assert (want[..., :3].max(axis=2) > 0.02).sum() >= 200, "the scene must actually cover pixels"
     diff = np.abs(got.astype(np.float64) - want)
